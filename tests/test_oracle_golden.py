@@ -1,0 +1,108 @@
+"""CPU: the numpy oracle (oracle/) against golden vectors produced by the real reference
+(tests/golden/*.npz, made by oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from conftest import golden, oracle_model, spec_for, GOLDEN_SPECS
+from oracle.sk_oracle import sk_table, V_NAMES
+from oracle.sktb_oracle import OracleModel, lorentz_dos
+
+
+def test_sk_table_matches_reference():
+    g = golden("sk_table")
+    assert list(g["V_names"]) == list(V_NAMES)
+    for V, d, T in zip(g["V"], g["lmn"], g["T"]):
+        mine = sk_table({n: V[i] for i, n in enumerate(V_NAMES)}, *d)
+        np.testing.assert_allclose(mine, T, rtol=0, atol=2e-15 * max(1.0, np.abs(T).max()))
+
+
+def test_sk_table_unknown_key_raises():
+    with pytest.raises(TypeError):
+        sk_table({"V_xyz": 1.0}, 1, 0, 0)
+
+
+def test_kmesh_bit_exact():
+    g = golden("kmesh")
+    for i in range(5):
+        assert np.array_equal(OracleModel.kmesh(list(g[f"nk{i}"])), g[f"mesh{i}"])
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_SPECS))
+def test_model_tables_and_spectrum(name):
+    g = golden(name)
+    m = oracle_model(spec_for(name))
+    assert np.array_equal(m.bond_mat, g["bond_mat"])
+    assert np.array_equal(np.array(m.bonds, dtype=np.int32).reshape(-1, 3), g["bond_list"])
+    bv = np.array([m.dist_mat_vec[i, a, b] for i, a, b in m.bonds]).reshape(-1, 3)
+    assert np.array_equal(bv, g["bond_vec"])                      # same np.dot per pair -> same bits here
+    H = np.zeros(tuple(g["H_wo_g_shape"]), dtype=complex)
+    H[tuple(g["H_wo_g_idx"].T)] = g["H_wo_g_val"]
+    np.testing.assert_allclose(m.H_wo_g, H, rtol=0, atol=1e-14)
+    assert np.array_equal(m.soc_mat, g["soc_mat"])
+    soc = bool(g["soc"])
+    k = g["k_test"]
+    for i in range(3):
+        np.testing.assert_allclose(m.get_ham(k[i], l_soc=soc), g["ham_k"][i], rtol=0, atol=1e-13)
+    if bool(g["raises"]):
+        with pytest.raises(Exception, match="not hermitian"):
+            m.solve_kpath(list(k[:2]), soc=soc)
+        return
+    ev = m.solve_kpath(list(k), soc=soc)
+    np.testing.assert_allclose(ev, g["evals"], rtol=0, atol=1e-11)
+    if "evals_nosoc" in g:
+        np.testing.assert_allclose(m.solve_kpath(list(k[:8]), soc=False), g["evals_nosoc"], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", ["C1_cubic_sp3", "C2_graphene_pz", "C3_sb_buckled", "sp_chain", "C5_zigzag_8",
+                                  "T_ce_spdf_1atom"])
+def test_kpath_bit_exact(name):
+    g = golden(name)
+    m = oracle_model(spec_for(name))
+    i = 0
+    while f"path{i}_in" in g:
+        pts, lens, spl = m.get_kpts(g[f"path{i}_in"].tolist(), int(g[f"path{i}_nk"]))
+        assert np.array_equal(np.array([np.asarray(p, float) for p in pts]), g[f"path{i}_k"])
+        assert np.array_equal(lens, g[f"path{i}_len"])
+        assert np.array_equal(spl, g[f"path{i}_spl"])
+        i += 1
+    assert i > 0
+
+
+def test_known_answers_quickstart():
+    """Quick Start bands at Gamma / R and the path length."""
+    g = golden("C1_cubic_sp3")
+    m = oracle_model(spec_for("C1_cubic_sp3"))
+    pts, lens, _ = m.get_kpts([[0, 0, 0], [0.5, 0.5, 0.5]], 50)
+    assert len(pts) == 51 and lens[-1] == 0.24743582965269698
+    ev = m.solve_kpath([pts[0], pts[-1]])
+    np.testing.assert_allclose(ev[:, 0], [-3, -3] + [2.3] * 6, atol=1e-12)
+    np.testing.assert_allclose(ev[:, 1], [0.7] * 6 + [3, 3], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["C1_cubic_sp3", "C2_graphene_pz", "C3_sb_buckled", "C5_zigzag_8", "lowsym_spd_laws"])
+def test_dos_ldos_inverse_path(name):
+    g = golden(name)
+    m = oracle_model(spec_for(name))
+    soc = bool(g["soc"])
+    if name == "C2_graphene_pz":   # 400 energies x 64 k inverses is slow in pure python: subsample energies
+        sel = slice(None, None, 16)
+    else:
+        sel = slice(None)
+    d = m.dos(g["dos_E"][sel], list(g["dos_nk"]), float(g["dos_eta"]), soc)
+    np.testing.assert_allclose(d, g["dos"][sel], rtol=1e-10)
+    if "ldos" in g:
+        orbs = list(g["ldos_orbs"]) or None
+        l = m.ldos(g["ldos_E"], list(g["ldos_atoms"]), orbs, list(g["ldos_nk"]), float(g["ldos_eta"]), soc)
+        np.testing.assert_allclose(l, g["ldos"], rtol=1e-10)
+    if "edge_dos" in g:
+        e = m.edge_dos(g["edge_E"], list(g["edge_atoms"]), nk=int(g["edge_nk"]), eta=float(g["edge_eta"]), soc=soc)
+        np.testing.assert_allclose(e, g["edge_dos"], rtol=1e-10)
+
+
+def test_lorentz_closed_form_equals_reference_dos():
+    """The identity the CUDA path relies on, checked against the REFERENCE's inverse-based DOS."""
+    for name in ["C2_graphene_pz", "C3_sb_buckled", "C5_zigzag_8"]:
+        g = golden(name)
+        m = oracle_model(spec_for(name))
+        ev = m.solve_kpath(list(m.kmesh(list(g["dos_nk"]))), soc=bool(g["soc"]))
+        np.testing.assert_allclose(lorentz_dos(ev, g["dos_E"], float(g["dos_eta"])), g["dos"], rtol=1e-10)
