@@ -278,6 +278,14 @@ class OracleModel:
         return np.array([[i / max(nk[0], 1), j / max(nk[1], 1), l / max(nk[2], 1)]
                          for i in range(nk[0]) for j in range(nk[1]) for l in range(nk[2])])
 
+    @staticmethod
+    def kmesh_point(nk, idx):
+        """Point `idx` of kmesh(nk) (same loop order and divisions as greens.py:104-109)."""
+        l = idx % nk[2]
+        j = (idx // nk[2]) % nk[1]
+        i = idx // (nk[1] * nk[2])
+        return np.array([i / max(nk[0], 1), j / max(nk[1], 1), l / max(nk[2], 1)])
+
     def spectral(self, E, k, eta=0.01, soc=True):
         H = self.get_ham(k, l_soc=soc)
         G = sla.inv((E + 1j * eta) * np.eye(H.shape[0]) - H)

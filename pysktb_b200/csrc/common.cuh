@@ -1,0 +1,150 @@
+// Shared device helpers for libsktb (sm_100a).  FP64 CUDA-core arithmetic throughout: the batched Hermitian
+// eigenproblem of tight binding (N ~ 2..1024) is not GEMM-shaped, so there is no tensor-core path here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sktb {
+
+typedef double2 cplx;
+
+#define SKTB_HD __host__ __device__ __forceinline__
+#define SKTB_D __device__ __forceinline__
+
+SKTB_HD cplx cmake(double x, double y) { cplx r; r.x = x; r.y = y; return r; }
+SKTB_HD cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+SKTB_HD cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+SKTB_HD cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+SKTB_HD cplx cmul(cplx a, cplx b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+SKTB_HD cplx cmulc(cplx a, cplx b) { return cmake(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }  // conj(a)*b
+SKTB_HD cplx cscale(double s, cplx a) { return cmake(s * a.x, s * a.y); }
+// acc += a*b
+SKTB_HD void cfma(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a)*b
+SKTB_HD void cfmac(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc -= a*b
+SKTB_HD void cfms(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc -= conj(a)*b
+SKTB_HD void cfmsc(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Householder generator, LAPACK zlarfg semantics without the safmin rescaling loop (eV-scale inputs).
+// In : alpha = x[0], xnorm2 = sum_{i>=1} |x_i|^2.   Out: beta (real, new x[0]), tau, scale (x[1:] *= scale).
+// Returns false when H = I (tau = 0): then beta = Re(alpha).
+// ---------------------------------------------------------------------------------------------------------
+SKTB_HD bool householder(cplx alpha, double xnorm2, double& beta, cplx& tau, cplx& scale) {
+    if (xnorm2 == 0.0 && alpha.y == 0.0) {
+        beta = alpha.x; tau = cmake(0.0, 0.0); scale = cmake(0.0, 0.0);
+        return false;
+    }
+    double nrm = sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2);
+    beta = (alpha.x >= 0.0) ? -nrm : nrm;   // -sign(nrm, Re alpha)
+    double ib = 1.0 / beta;
+    tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
+    double dx = alpha.x - beta, dy = alpha.y;
+    double id = 1.0 / (dx * dx + dy * dy);
+    scale = cmake(dx * id, -dy * id);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Implicit-shift QL on a real symmetric tridiagonal (d[0..n), e[0..n-1) couples i,i+1), eigenvalues only,
+// strided storage (element i at base[i*stride]) so that a warp can keep one matrix per lane with
+// conflict-free shared memory.  e must have room for n entries; destroyed.  Returns iterations > limit ? 1 : 0.
+// ---------------------------------------------------------------------------------------------------------
+SKTB_HD int tql_values(double* d, double* e, int n, int stride) {
+    const double eps = 2.220446049250313e-16;
+#define D_(i) d[(i) * stride]
+#define E_(i) e[(i) * stride]
+    if (n > 0) E_(n - 1) = 0.0;
+    int fail = 0;
+    for (int l = 0; l < n; ++l) {
+        int iter = 0;
+        while (true) {
+            int m = l;
+            for (; m < n - 1; ++m) {
+                double dd = fabs(D_(m)) + fabs(D_(m + 1));
+                if (fabs(E_(m)) <= eps * dd) break;
+            }
+            if (m == l) break;
+            if (++iter > 80) { fail = 1; break; }
+            double el = E_(l);
+            double g = (D_(l + 1) - D_(l)) / (2.0 * el);
+            double r = sqrt(g * g + 1.0);
+            g = D_(m) - D_(l) + el / (g + (g >= 0.0 ? r : -r));
+            double s = 1.0, c = 1.0, p = 0.0;
+            int i = m - 1;
+            bool under = false;
+            for (; i >= l; --i) {
+                double ei = E_(i);
+                double f = s * ei, b = c * ei;
+                r = sqrt(f * f + g * g);
+                E_(i + 1) = r;
+                if (r == 0.0) { D_(i + 1) -= p; E_(m) = 0.0; under = true; break; }
+                double ir = 1.0 / r;
+                s = f * ir; c = g * ir;
+                g = D_(i + 1) - p;
+                r = (D_(i) - g) * s + 2.0 * c * b;
+                p = s * r;
+                D_(i + 1) = g + p;
+                g = c * r - b;
+            }
+            if (under) continue;
+            D_(l) -= p; E_(l) = g; E_(m) = 0.0;
+        }
+    }
+#undef D_
+#undef E_
+    return fail;
+}
+
+// block-wide sums (all threads get the result). scratch: >= 64 doubles of shared memory.
+SKTB_D double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+SKTB_D double block_sum(double v, double* scratch) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect scratch from the previous use
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double t = (lane < nw) ? scratch[lane] : 0.0;
+    return warp_sum(t);
+}
+SKTB_D cplx block_sum(cplx v, double* scratch) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+    __syncthreads();
+    if (lane == 0) { scratch[wid] = v.x; scratch[32 + wid] = v.y; }
+    __syncthreads();
+    double tx = (lane < nw) ? scratch[lane] : 0.0, ty = (lane < nw) ? scratch[32 + lane] : 0.0;
+    return cmake(warp_sum(tx), warp_sum(ty));
+}
+
+// k-mesh point of flat index idx (greens.py:104-109): true IEEE divisions, no reciprocal multiply.
+SKTB_HD void kmesh_point(long long idx, int n0, int n1, int n2, double& kx, double& ky, double& kz) {
+    long long l = idx % n2, t = idx / n2;
+    long long j = t % n1, i = t / n1;
+    double d0 = (double)(n0 > 1 ? n0 : 1), d1 = (double)(n1 > 1 ? n1 : 1), d2 = (double)(n2 > 1 ? n2 : 1);
+#ifdef __CUDA_ARCH__
+    kx = __ddiv_rn((double)i, d0); ky = __ddiv_rn((double)j, d1); kz = __ddiv_rn((double)l, d2);
+#else
+    kx = (double)i / d0; ky = (double)j / d1; kz = (double)l / d2;
+#endif
+}
+
+}  // namespace sktb

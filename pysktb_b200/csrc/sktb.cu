@@ -1,0 +1,739 @@
+// libsktb.so - C ABI (include/sktb.h) over the sm_100a kernels.  Host side: plan construction, workspace,
+// chunking, stream pipelining.  No CPU compute path: every numerical entry point launches kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <string>
+#include <vector>
+
+#include "../../include/sktb.h"
+#include "common.cuh"
+#include "sk_table.cuh"
+#include "kernels_generic.cuh"
+#include "heev_small.cuh"
+
+using namespace sktb;
+
+// ------------------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local std::string g_kinfo;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define LAUNCHED()                                                                                   \
+    do {                                                                                             \
+        ++g_launches;                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 1; }
+            want = bytes;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct sktb_plan {
+    int device = 0;
+    int n_atoms = 0, n_orb = 0, n_bonds = 0, n_pairs = 0, soc_nnz = 0;
+    PlanView view{};
+    std::vector<void*> owned;                 // device allocations of the tables
+    std::vector<double> T_host_creation_order;  // hopping blocks in the caller's bond order
+    std::vector<int> bond_ni, bond_nj;
+    double asym_bound = 0.0;
+    small::SmallTables small_tab{};           // dense tables for the register-resident path
+    bool small_ok = false;
+    struct WorkSet { Buf H, RT, K; };
+    WorkSet ws[3];                            // [0],[1]: the two host-front-end streams; [2]: caller-stream API
+    Buf wsE, wsVec, wsFlag, wsPart, wsMisc;
+    int* d_any = nullptr;                     // device int: any Hermiticity-gate hit
+    int* d_fail = nullptr;                    // device int: QL non-convergence count
+    int* h_pinned = nullptr;                  // 4 pinned ints
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool timing_valid = false;
+    // host front end
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    Buf hK[2], hE[2], hV[2], hF[2];
+};
+
+template <class T>
+static int upload(sktb_plan* p, const T* src, size_t n, const T** dst) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return fail("cudaMalloc(%zu) failed", bytes);
+    if (n && cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D copy failed");
+    p->owned.push_back(d);
+    *dst = reinterpret_cast<const T*>(d);
+    return 0;
+}
+
+extern "C" const char* sktb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* sktb_version(void) { return "sktb-b200 0.1 (sm_100a)"; }
+extern "C" const char* sktb_last_kernel_info(void) { return g_kinfo.c_str(); }
+extern "C" long long sktb_launch_count(void) { return g_launches.load(); }
+extern "C" const char* sktb_v_names(void) {
+    return "V_sss,V_sps,V_pps,V_ppp,V_sds,V_pds,V_pdp,V_dds,V_ddp,V_ddd,V_sfs,V_pfs,V_pfp,V_dfs,V_dfp,V_dfd,"
+           "V_ffs,V_ffp,V_ffd,V_fff,V_SSs,V_sSs,V_Sps,V_Sds,V_Sfs";
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4 / K0 entry points
+// ------------------------------------------------------------------------------------------------------
+extern "C" int sktb_sk_table(const double* V_d, const double* lmn_d, double* out_d, int32_t nb, void* stream) {
+    if (nb <= 0) return 0;
+    sk_table_kernel<<<(nb + 63) / 64, 64, 0, (cudaStream_t)stream>>>(V_d, lmn_d, out_d, nb);
+    LAUNCHED();
+    return 0;
+}
+
+extern "C" int sktb_kmesh(const int32_t nk[3], int64_t first, int64_t count, double* k_out_d, void* stream) {
+    if (count <= 0) return 0;
+    if (nk[0] < 0 || nk[1] < 0 || nk[2] < 0) return fail("negative mesh size");
+    long long blocks = std::min<long long>((count + 255) / 256, 148 * 32);
+    kmesh_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(nk[0], nk[1], nk[2], first, count, k_out_d);
+    LAUNCHED();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------------
+extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan** out) {
+    if (!D || !out) return fail("null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: libsktb has no CPU fallback (cudaGetDeviceCount: %s)", cudaGetErrorString(cudaGetLastError()));
+    if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    const int na = D->n_atoms, n = D->n_orb, nb = D->n_bonds;
+    if (na <= 0 || n <= 0 || nb < 0) return fail("bad model sizes");
+    for (int a = 0; a < na; ++a)
+        if (D->atom_orb_start[a + 1] <= D->atom_orb_start[a]) return fail("atom %d has no orbitals", a);
+    if (D->atom_orb_start[0] != 0 || D->atom_orb_start[na] != n) return fail("atom_orb_start inconsistent with n_orb");
+    for (int i = 0; i < n; ++i)
+        if (D->orb_kind[i] < 0 || D->orb_kind[i] >= SKTB_N_ORB_KINDS) return fail("orb_kind[%d] out of range", i);
+    for (int b = 0; b < nb; ++b)
+        if (D->bond_i[b] < 0 || D->bond_i[b] >= na || D->bond_j[b] < 0 || D->bond_j[b] >= na) return fail("bond %d: atom index out of range", b);
+    for (int t = 0; t < D->soc_nnz; ++t)
+        if (D->soc_row[t] < 0 || D->soc_row[t] >= 2 * n || D->soc_col[t] < 0 || D->soc_col[t] >= 2 * n) return fail("soc entry %d out of range", t);
+
+    sktb_plan* p = new sktb_plan();
+    p->device = device; p->n_atoms = na; p->n_orb = n; p->n_bonds = nb; p->soc_nnz = D->soc_nnz;
+    auto bail = [&](int rc) { sktb_plan_destroy(p); return rc; };
+
+    // ---- K4 on the device: full 17x17 tables per bond -----------------------------------------------
+    std::vector<double> tab((size_t)nb * 289);
+    if (nb) {
+        double *dV = nullptr, *dL = nullptr, *dT = nullptr;
+        if (cudaMalloc(&dV, (size_t)nb * 25 * 8) != cudaSuccess || cudaMalloc(&dL, (size_t)nb * 3 * 8) != cudaSuccess ||
+            cudaMalloc(&dT, (size_t)nb * 289 * 8) != cudaSuccess) return bail(fail("cudaMalloc failed (sk tables)"));
+        cudaMemcpy(dV, D->bond_V, (size_t)nb * 25 * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(dL, D->bond_lmn, (size_t)nb * 3 * 8, cudaMemcpyHostToDevice);
+        int rc = sktb_sk_table(dV, dL, dT, nb, nullptr);
+        cudaError_t e = cudaMemcpy(tab.data(), dT, tab.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(dV); cudaFree(dL); cudaFree(dT);
+        if (rc) return bail(rc);
+        if (e != cudaSuccess) return bail(fail("sk_table kernel failed: %s", cudaGetErrorString(e)));
+    }
+
+    // ---- gather orbital sub-blocks, creation order (for H_wo_g) --------------------------------------
+    p->bond_ni.resize(nb); p->bond_nj.resize(nb);
+    std::vector<long long> off_creation(nb + 1, 0);
+    for (int b = 0; b < nb; ++b) {
+        int i = D->bond_i[b], j = D->bond_j[b];
+        p->bond_ni[b] = D->atom_orb_start[i + 1] - D->atom_orb_start[i];
+        p->bond_nj[b] = D->atom_orb_start[j + 1] - D->atom_orb_start[j];
+        off_creation[b + 1] = off_creation[b] + (long long)p->bond_ni[b] * p->bond_nj[b];
+    }
+    p->T_host_creation_order.resize(off_creation[nb]);
+    for (int b = 0; b < nb; ++b) {
+        int i = D->bond_i[b], j = D->bond_j[b];
+        for (int r = 0; r < p->bond_ni[b]; ++r)
+            for (int c = 0; c < p->bond_nj[b]; ++c)
+                p->T_host_creation_order[off_creation[b] + (long long)r * p->bond_nj[b] + c] =
+                    tab[(size_t)b * 289 + D->orb_kind[D->atom_orb_start[i] + r] * 17 + D->orb_kind[D->atom_orb_start[j] + c]];
+    }
+
+    // ---- pair-sorted bond arrays ----------------------------------------------------------------------
+    std::vector<int> order(nb);
+    for (int b = 0; b < nb; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        if (D->bond_i[x] != D->bond_i[y]) return D->bond_i[x] < D->bond_i[y];
+        if (D->bond_j[x] != D->bond_j[y]) return D->bond_j[x] < D->bond_j[y];
+        return D->bond_image[x] < D->bond_image[y];
+    });
+    std::vector<int> pair_of((size_t)na * na, -1), pair_begin;
+    std::vector<double> bvec((size_t)nb * 3), Tsorted(off_creation[nb]);
+    std::vector<long long> boff(nb);
+    long long run = 0;
+    int npairs = 0;
+    for (int s = 0; s < nb; ++s) {
+        int b = order[s], i = D->bond_i[b], j = D->bond_j[b];
+        if (pair_of[(size_t)i * na + j] < 0) { pair_of[(size_t)i * na + j] = npairs++; pair_begin.push_back(s); }
+        for (int c = 0; c < 3; ++c) bvec[3 * s + c] = D->bond_vec[3 * b + c];
+        boff[s] = run;
+        long long len = (long long)p->bond_ni[b] * p->bond_nj[b];
+        std::copy(p->T_host_creation_order.begin() + off_creation[b], p->T_host_creation_order.begin() + off_creation[b] + len, Tsorted.begin() + run);
+        run += len;
+    }
+    pair_begin.push_back(nb);
+    p->n_pairs = npairs;
+    std::vector<int> orb_atom(n);
+    for (int a = 0; a < na; ++a)
+        for (int o = D->atom_orb_start[a]; o < D->atom_orb_start[a + 1]; ++o) orb_atom[o] = a;
+
+    // ---- Hermiticity-gate bound -------------------------------------------------------------------------
+    // Re(H - H^dagger)[mu,nu] = sum_{b in pair(i,j)} (T_b[mu,nu] - T_rev(b)[nu,mu]) cos(phi_b), rev(b) = the bond
+    // (j,i,-d).  For i == j the bonds b and rev(b) sit in the same pair with equal cos(phi) and are combined
+    // before taking magnitudes (this is what makes odd-parity blocks such as s-p or p-f cancel exactly).
+    {
+        std::map<std::tuple<int, int, long long, long long, long long>, int> by_vec;
+        auto key = [&](int i, int j, const double* v, double sgn) {
+            return std::make_tuple(i, j, llround(sgn * v[0] * 1e7), llround(sgn * v[1] * 1e7), llround(sgn * v[2] * 1e7));
+        };
+        for (int b = 0; b < nb; ++b) by_vec[key(D->bond_i[b], D->bond_j[b], D->bond_vec + 3 * b, 1.0)] = b;
+        auto Tb = [&](int b, int r, int c) { return b < 0 ? 0.0 : p->T_host_creation_order[off_creation[b] + (long long)r * p->bond_nj[b] + c]; };
+        std::vector<double> acc((size_t)n * n, 0.0);
+        for (int b = 0; b < nb; ++b) {
+            int i = D->bond_i[b], j = D->bond_j[b];
+            auto it = by_vec.find(key(j, i, D->bond_vec + 3 * b, -1.0));
+            int rb = it == by_vec.end() ? -1 : it->second;
+            if (i == j && rb >= 0 && rb < b) continue;          // handled together with its partner
+            for (int r = 0; r < p->bond_ni[b]; ++r)
+                for (int c = 0; c < p->bond_nj[b]; ++c) {
+                    double v = Tb(b, r, c) - Tb(rb, c, r);
+                    if (i == j && rb >= 0 && rb != b) v += Tb(rb, r, c) - Tb(b, c, r);
+                    acc[(size_t)(D->atom_orb_start[i] + r) * n + D->atom_orb_start[j] + c] += fabs(v);
+                }
+        }
+        double bound = 0.0;
+        for (double x : acc) bound = std::max(bound, x);
+        std::map<std::pair<int, int>, double> sre;
+        for (int t = 0; t < D->soc_nnz; ++t) sre[{D->soc_row[t], D->soc_col[t]}] = D->soc_val[2 * t];
+        double sb = 0.0;
+        for (auto& kv : sre) {
+            auto it = sre.find({kv.first.second, kv.first.first});
+            double other = it == sre.end() ? 0.0 : it->second;
+            sb = std::max(sb, fabs(kv.second - other));
+        }
+        p->asym_bound = bound + sb;
+    }
+
+    // ---- upload ---------------------------------------------------------------------------------------
+    PlanView& V = p->view;
+    V.n_atoms = na; V.n_orb = n; V.n_bonds = nb; V.n_pairs = npairs; V.soc_nnz = D->soc_nnz;
+    std::vector<cplx> sval(D->soc_nnz);
+    for (int t = 0; t < D->soc_nnz; ++t) sval[t] = cmake(D->soc_val[2 * t], D->soc_val[2 * t + 1]);
+    int rc = 0;
+    rc |= upload(p, D->atom_orb_start, (size_t)na + 1, &V.atom_start);
+    rc |= upload(p, orb_atom.data(), (size_t)n, &V.orb_atom);
+    rc |= upload(p, pair_of.data(), pair_of.size(), &V.pair_of);
+    rc |= upload(p, pair_begin.data(), pair_begin.size(), &V.pair_begin);
+    rc |= upload(p, bvec.data(), bvec.size(), &V.bond_vec);
+    rc |= upload(p, boff.data(), boff.size(), &V.bond_off);
+    rc |= upload(p, Tsorted.data(), Tsorted.size(), &V.T);
+    rc |= upload(p, D->onsite, (size_t)n, &V.onsite);
+    rc |= upload(p, D->soc_row, (size_t)D->soc_nnz, &V.soc_row);
+    rc |= upload(p, D->soc_col, (size_t)D->soc_nnz, &V.soc_col);
+    rc |= upload(p, sval.data(), sval.size(), &V.soc_val);
+    if (rc) return bail(1);
+    for (int c = 0; c < 9; ++c) V.rec[c] = D->rec_lattice[c];
+
+    // ---- dense tables for the register-resident path (N <= 32) -----------------------------------------
+    {
+        std::string why;
+        p->small_ok = small::build_tables(D, p->T_host_creation_order, off_creation, p->bond_ni, p->bond_nj, &p->small_tab, &p->owned, &why);
+        p->small_tab.asym_bound = p->asym_bound;
+        if (!p->small_ok && !why.empty()) g_kinfo = "small path unavailable: " + why;
+    }
+
+    if (cudaMalloc((void**)&p->d_any, 2 * sizeof(int)) != cudaSuccess) return bail(fail("cudaMalloc failed"));
+    p->d_fail = p->d_any + 1;
+    cudaMemset(p->d_any, 0, 2 * sizeof(int));
+    if (cudaMallocHost((void**)&p->h_pinned, 4 * sizeof(int)) != cudaSuccess) return bail(fail("cudaMallocHost failed"));
+    cudaEventCreate(&p->ev0); cudaEventCreate(&p->ev1);
+    CK(cudaDeviceSynchronize());
+    *out = p;
+    return 0;
+}
+
+extern "C" void sktb_plan_destroy(sktb_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (void* d : p->owned) cudaFree(d);
+    for (auto& w : p->ws) { w.H.release(); w.RT.release(); w.K.release(); }
+    for (Buf* b : {&p->wsE, &p->wsVec, &p->wsFlag, &p->wsPart, &p->wsMisc}) b->release();
+    for (int s = 0; s < 2; ++s) {
+        p->hK[s].release(); p->hE[s].release(); p->hV[s].release(); p->hF[s].release();
+        if (p->hs[s]) cudaStreamDestroy(p->hs[s]);
+    }
+    if (p->d_any) cudaFree(p->d_any);
+    if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+extern "C" int sktb_plan_hoppings(const sktb_plan* p, double* out_host, int64_t capacity) {
+    if (!p || !out_host) return fail("null argument");
+    if ((int64_t)p->T_host_creation_order.size() > capacity) return fail("capacity %lld < %zu", (long long)capacity, p->T_host_creation_order.size());
+    std::copy(p->T_host_creation_order.begin(), p->T_host_creation_order.end(), out_host);
+    return 0;
+}
+
+extern "C" int sktb_plan_asym_bound(const sktb_plan* p, double* bound) {
+    if (!p || !bound) return fail("null argument");
+    *bound = p->asym_bound;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------------
+static int launch_hk(sktb_plan* p, const double* k_d, long long nk, int soc, cplx* H, int* flag, long long flag_off, cudaStream_t st) {
+    size_t smem = (size_t)std::max(p->n_bonds, 1) * sizeof(cplx);
+    if (smem > 200 * 1024) return fail("model has %d bonds: phase table exceeds shared memory", p->n_bonds);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(hk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int N = soc ? 2 * p->n_orb : p->n_orb;
+    int threads = N * N >= 1024 ? 256 : (N * N >= 256 ? 128 : 64);
+    unsigned grid = (unsigned)std::min<long long>(nk, 148LL * 16);
+    hk_kernel<<<grid, threads, smem, st>>>(p->view, k_d, nk, soc, H, flag, flag_off);
+    LAUNCHED();
+    return 0;
+}
+
+static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+    const int N = a.N;
+    int T = std::min(1024, std::max(32, (N + 31) / 32 * 32));
+    size_t aux = ((size_t)4 * N + 64) * sizeof(double) + (size_t)2 * N * sizeof(cplx);
+    size_t withA = aux + (size_t)N * N * sizeof(cplx);
+    bool smemA = withA <= 200 * 1024;
+    size_t smem = smemA ? withA : aux;
+    a.fail = p->d_fail;
+    unsigned grid = (unsigned)std::min<long long>(a.nm, 148LL * 32);
+    if (smemA) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(heev_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heev_generic_kernel<true><<<grid, T, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(heev_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heev_generic_kernel<false><<<grid, T, smem, st>>>(a);
+    }
+    LAUNCHED();
+    char buf[256];
+    snprintf(buf, sizeof buf, "heev_generic<smemA=%d> N=%d threads=%d smem=%zuB grid=%u rows=%d", (int)smemA, N, T, smem, grid, a.n_rows);
+    g_kinfo = buf;
+    return 0;
+}
+
+static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked workspaces
+
+// shared body of sktb_solve / sktb_solve_mesh.  k_d == NULL -> mesh.
+static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc,
+                      double* evals_d, double* evecs_d, long long ld, long long k_off, int* flags_d, cudaStream_t st, bool timed,
+                      int ws_id = 2) {
+    sktb_plan::WorkSet& W = p->ws[ws_id];
+    if (!p || !evals_d) return fail("null argument");
+    if (nk <= 0) return 0;
+    CK(cudaSetDevice(p->device));
+    const int N = soc ? 2 * p->n_orb : p->n_orb;
+    int launches0 = (int)g_launches.load();
+    if (timed) CK(cudaEventRecord(p->ev0, st));
+
+    const bool want_vecs = evecs_d != nullptr;
+    if (!want_vecs && p->small_ok && small::supports(N)) {
+        int rc = small::launch_solve(p->small_tab, k_d, nk_mesh, first, nk, soc, N, evals_d, ld, k_off, flags_d, p->d_fail, st, &g_kinfo);
+        if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
+        g_launches += rc;
+    } else {
+        size_t perH = (size_t)N * N * sizeof(cplx);
+        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));
+        if (W.H.ensure(perH * chunk)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
+        if (want_vecs && W.RT.ensure(perH * chunk)) return fail("out of device memory (RT workspace)");
+        if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
+        for (long long c0 = 0; c0 < nk; c0 += chunk) {
+            long long cnt = std::min(chunk, nk - c0);
+            const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
+            if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
+            int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
+            if (rc) return rc;
+            HeevArgs a{};
+            a.H = (cplx*)W.H.p; a.N = N; a.nm = (int)cnt;
+            a.evals = evals_d; a.ld = ld; a.col0 = k_off + c0;
+            if (want_vecs) {
+                a.RT = (cplx*)W.RT.p; a.n_rows = N; a.rows = nullptr;
+                a.vec_out = (cplx*)evecs_d; a.vs_band = ld * N; a.vs_k = N; a.vcol0 = k_off + c0;
+            }
+            rc = launch_heev_generic(p, a, st);
+            if (rc) return rc;
+        }
+    }
+    if (timed) { CK(cudaEventRecord(p->ev1, st)); p->timing_valid = true; p->last_launches = (int)g_launches.load() - launches0; }
+    return 0;
+}
+
+extern "C" int sktb_hk(sktb_plan* p, const double* k_d, int64_t nk, int32_t soc, double* H_d, int32_t* nonherm_d, void* stream) {
+    if (!p || !k_d || !H_d) return fail("null argument");
+    if (nk <= 0) return 0;
+    CK(cudaSetDevice(p->device));
+    return launch_hk(p, k_d, nk, soc, (cplx*)H_d, nonherm_d, 0, (cudaStream_t)stream);
+}
+
+extern "C" int sktb_solve(sktb_plan* p, const double* k_d, int64_t nk, int32_t soc, double* evals_d, double* evecs_d,
+                          int64_t ld_k, int64_t k_off, int32_t* nonherm_d, void* stream) {
+    if (!k_d) return fail("null k pointer");
+    return solve_impl(p, k_d, nullptr, 0, nk, soc, evals_d, evecs_d, ld_k, k_off, nonherm_d, (cudaStream_t)stream, true);
+}
+
+extern "C" int sktb_solve_mesh(sktb_plan* p, const int32_t nk_mesh[3], int64_t first, int64_t count, int32_t soc,
+                               double* evals_d, int64_t ld_k, int64_t k_off, int32_t* nonherm_d, void* stream) {
+    if (!nk_mesh) return fail("null mesh");
+    long long total = (long long)nk_mesh[0] * nk_mesh[1] * nk_mesh[2];
+    if (first < 0 || first + count > total) return fail("mesh range [%lld,%lld) outside %lld points", (long long)first, (long long)(first + count), total);
+    return solve_impl(p, nullptr, nk_mesh, first, count, soc, evals_d, nullptr, ld_k, k_off, nonherm_d, (cudaStream_t)stream, true);
+}
+
+extern "C" int sktb_ql_failures(sktb_plan* p, int32_t* count) {
+    if (!p || !count) return fail("null argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpy(count, p->d_fail, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sktb_last_solve_time(sktb_plan* p, double* ms, int32_t* n_launches) {
+    if (!p || !p->timing_valid) return fail("no timed solve on this plan");
+    CK(cudaEventSynchronize(p->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, p->ev0, p->ev1));
+    if (ms) *ms = t;
+    if (n_launches) *n_launches = p->last_launches;
+    return 0;
+}
+
+// Batched Hermitian eigensolve of caller-supplied matrices (Hamiltonian._sol_ham, hamiltonian.py:108-126):
+// gate flags on the matrices as given, then K2 on a workspace copy (K2 destroys its input).
+__global__ void herm_gate_kernel(const cplx* __restrict__ H, int N, long long nm, int* __restrict__ flag) {
+    __shared__ int s_bad;
+    for (long long m = blockIdx.x; m < nm; m += gridDim.x) {
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        const cplx* A = H + (size_t)m * N * N;
+        int bad = 0;
+        for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+            int r = e / N, c = e - r * N;
+            if (A[e].x - A[(size_t)c * N + r].x > 1.0e-9) bad = 1;
+        }
+        if (bad) s_bad = 1;
+        __syncthreads();
+        if (threadIdx.x == 0) flag[m] = s_bad;
+        __syncthreads();
+    }
+}
+
+extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm, double* evals_d, double* evecs_d, int32_t* nonherm_d,
+                         void* stream) {
+    if (!p || !H_d || !evals_d) return fail("null argument");
+    if (N <= 0) return fail("bad matrix size");
+    if (nm <= 0) return 0;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t perH = (size_t)N * N * sizeof(cplx);
+    long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / perH)));
+    if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(perH * chunk))) return fail("out of device memory (heev workspace)");
+    if (nonherm_d) {
+        herm_gate_kernel<<<(unsigned)std::min<long long>(nm, 148LL * 8), 128, 0, st>>>((const cplx*)H_d, N, nm, nonherm_d);
+        LAUNCHED();
+    }
+    for (long long c0 = 0; c0 < nm; c0 += chunk) {
+        long long cnt = std::min(chunk, (long long)nm - c0);
+        CK(cudaMemcpyAsync(p->ws[2].H.p, (const cplx*)H_d + (size_t)c0 * N * N, perH * cnt, cudaMemcpyDeviceToDevice, st));
+        HeevArgs a{};
+        a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
+        a.evals = evals_d; a.ld = nm; a.col0 = c0;
+        if (evecs_d) {
+            a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = N; a.rows = nullptr;
+            a.vec_out = (cplx*)evecs_d; a.vs_band = (long long)nm * N; a.vs_k = N; a.vcol0 = c0;
+        }
+        int rc = launch_heev_generic(p, a, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-buffer front end: two streams, chunked H2D(k) -> K1+K2 -> D2H(evals[, evecs]) overlapped
+// ------------------------------------------------------------------------------------------------------
+extern "C" int sktb_solve_host(sktb_plan* p, const double* k_h, int64_t nk, int32_t soc, double* evals_h, double* evecs_h,
+                               int32_t* nonherm_any) {
+    if (!p || !k_h || !evals_h) return fail("null argument");
+    CK(cudaSetDevice(p->device));
+    if (nonherm_any) *nonherm_any = 0;
+    if (nk <= 0) return 0;
+    const int N = soc ? 2 * p->n_orb : p->n_orb;
+    for (int s = 0; s < 2; ++s)
+        if (!p->hs[s]) CK(cudaStreamCreateWithFlags(&p->hs[s], cudaStreamNonBlocking));
+    // chunk: bounded device staging (<= 512 MB of eigenvalues, <= 1 GB of eigenvectors per stream)
+    long long chunk = std::min<long long>(nk, std::max<long long>(1, ((long long)512 << 20) / ((long long)N * 8)));
+    if (evecs_h) chunk = std::min<long long>(chunk, std::max<long long>(1, ((long long)1 << 30) / ((long long)N * N * 16)));
+    if (nk > 4 * 148 && chunk > (nk + 3) / 4) chunk = (nk + 3) / 4;      // at least 4 chunks so the copies overlap
+    const bool gate = p->asym_bound > 0.5e-9;
+    CK(cudaMemsetAsync(p->d_any, 0, sizeof(int), p->hs[0]));
+    CK(cudaStreamSynchronize(p->hs[0]));
+    long long c_index = 0;
+    for (long long c0 = 0; c0 < nk; c0 += chunk, ++c_index) {
+        int s = (int)(c_index & 1);
+        cudaStream_t st = p->hs[s];
+        long long cnt = std::min(chunk, nk - c0);
+        if (p->hK[s].ensure((size_t)chunk * 24) || p->hE[s].ensure((size_t)chunk * N * 8) ||
+            (evecs_h && p->hV[s].ensure((size_t)chunk * N * N * 16)) || (gate && p->hF[s].ensure((size_t)chunk * 4)))
+            return fail("out of device memory (host front-end staging)");
+        CK(cudaMemcpyAsync(p->hK[s].p, k_h + 3 * c0, (size_t)cnt * 24, cudaMemcpyHostToDevice, st));
+        int rc = solve_impl(p, (const double*)p->hK[s].p, nullptr, 0, cnt, soc, (double*)p->hE[s].p, evecs_h ? (double*)p->hV[s].p : nullptr,
+                            cnt, 0, gate ? (int*)p->hF[s].p : nullptr, st, false, s);
+        if (rc) return rc;
+        if (gate) { any_flag_kernel<<<64, 256, 0, st>>>((const int*)p->hF[s].p, cnt, p->d_any); LAUNCHED(); }
+        const size_t max_pitch = (size_t)1 << 30;     // stay well inside cudaDeviceProp::memPitch
+        if ((size_t)nk * 8 <= max_pitch) {
+            CK(cudaMemcpy2DAsync(evals_h + c0, (size_t)nk * 8, p->hE[s].p, (size_t)cnt * 8, (size_t)cnt * 8, N, cudaMemcpyDeviceToHost, st));
+        } else {
+            for (int b = 0; b < N; ++b)
+                CK(cudaMemcpyAsync(evals_h + (size_t)b * nk + c0, (const double*)p->hE[s].p + (size_t)b * cnt, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (evecs_h) {   // device [N][cnt][N] -> host [N][nk][N]
+            if ((size_t)nk * N * 16 <= max_pitch) {
+                CK(cudaMemcpy2DAsync(evecs_h + (size_t)2 * c0 * N, (size_t)nk * N * 16, p->hV[s].p, (size_t)cnt * N * 16, (size_t)cnt * N * 16, N,
+                                     cudaMemcpyDeviceToHost, st));
+            } else {
+                for (int b = 0; b < N; ++b)
+                    CK(cudaMemcpyAsync(evecs_h + ((size_t)b * nk + c0) * N * 2, (const double*)p->hV[s].p + (size_t)b * cnt * N * 2, (size_t)cnt * N * 16,
+                                       cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    CK(cudaMemcpyAsync(p->h_pinned, p->d_any, sizeof(int), cudaMemcpyDeviceToHost, p->hs[0]));
+    CK(cudaStreamSynchronize(p->hs[1]));
+    CK(cudaStreamSynchronize(p->hs[0]));
+    // d_any may have been set by the other stream after the copy was queued: re-read once everything is done
+    CK(cudaMemcpy(p->h_pinned, p->d_any, sizeof(int), cudaMemcpyDeviceToHost));
+    if (nonherm_any) *nonherm_any = p->h_pinned[0];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1+K2+K3: DOS / LDOS, and A(k,E) maps
+// ------------------------------------------------------------------------------------------------------
+static int tracked_rows(sktb_plan* p, int N, int n_groups, const int32_t* grp_ptr, const int32_t* grp_idx,
+                        std::vector<int>* rows, std::vector<int>* grp_rows) {
+    rows->clear(); grp_rows->clear();
+    int total = n_groups > 0 ? grp_ptr[n_groups] : 0;
+    for (int q = 0; q < total; ++q) {
+        if (grp_idx[q] < 0 || grp_idx[q] >= N) return fail("group index %d outside the %d x %d Hamiltonian", grp_idx[q], N, N);
+        rows->push_back(grp_idx[q]);
+    }
+    std::sort(rows->begin(), rows->end());
+    rows->erase(std::unique(rows->begin(), rows->end()), rows->end());
+    for (int q = 0; q < total; ++q)
+        grp_rows->push_back((int)(std::lower_bound(rows->begin(), rows->end(), grp_idx[q]) - rows->begin()));
+    (void)p;
+    return 0;
+}
+
+extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3], int64_t k_first, int64_t k_count, int32_t soc,
+                        const double* energies_d, int32_t nE, double eta, int32_t n_groups, const int32_t* grp_ptr,
+                        const int32_t* grp_idx, double* out_d, int32_t* nonherm_any_h, void* stream) {
+    if (!p || !energies_d || !out_d) return fail("null argument");
+    if (!k_d && !nk_mesh) return fail("need k points or a mesh");
+    if (nE <= 0) return 0;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = soc ? 2 * p->n_orb : p->n_orb;
+    const int ng = n_groups > 0 ? n_groups : 1;
+    std::vector<int> rows, grp_rows;
+    if (tracked_rows(p, N, n_groups, grp_ptr, grp_idx, &rows, &grp_rows)) return 1;
+    const int n_rows = (int)rows.size();
+    CK(cudaMemsetAsync(out_d, 0, (size_t)ng * nE * 8, st));
+    CK(cudaMemsetAsync(p->d_any, 0, sizeof(int), st));
+    if (k_count <= 0) { if (nonherm_any_h) *nonherm_any_h = 0; return 0; }
+
+    // device copies of the group tables
+    int *d_rows = nullptr, *d_gptr = nullptr, *d_grows = nullptr;
+    if (n_groups > 0) {
+        size_t need = (rows.size() + (size_t)n_groups + 1 + grp_rows.size()) * sizeof(int);
+        if (p->wsMisc.ensure(need)) return fail("out of device memory");
+        d_rows = (int*)p->wsMisc.p; d_gptr = d_rows + rows.size(); d_grows = d_gptr + n_groups + 1;
+        CK(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_gptr, grp_ptr, ((size_t)n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_grows, grp_rows.data(), grp_rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // host vectors go out of scope at return; keep it simple
+    }
+    const bool gate = p->asym_bound > 0.5e-9;
+    const bool use_small = n_rows == 0 && p->small_ok && small::supports(N);
+    size_t per_k = (size_t)N * 8 + (use_small ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4;
+    long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(WS_BUDGET / per_k)));
+    const int LOR_GRID = 148 * 4;
+    if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
+        (n_rows && (p->ws[2].RT.ensure((size_t)chunk * N * n_rows * 16) || p->wsVec.ensure((size_t)chunk * N * n_rows * 16))) ||
+        (!k_d && !use_small && p->ws[2].K.ensure((size_t)chunk * 24)) || (gate && p->wsFlag.ensure((size_t)chunk * 4)) ||
+        p->wsPart.ensure((size_t)LOR_GRID * ng * nE * 8))
+        return fail("out of device memory (dos workspaces)");
+
+    for (long long c0 = 0; c0 < k_count; c0 += chunk) {
+        long long cnt = std::min(chunk, (long long)k_count - c0);
+        int* flags = gate ? (int*)p->wsFlag.p : nullptr;
+        if (use_small) {
+            int rc = small::launch_solve(p->small_tab, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, k_first + c0, cnt, soc, N, (double*)p->wsE.p, cnt, 0,
+                                         flags, p->d_fail, st, &g_kinfo);
+            if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        } else {
+            const double* kk = k_d ? k_d + 3 * c0 : (const double*)p->ws[2].K.p;
+            if (!k_d) { int rc = sktb_kmesh(nk_mesh, k_first + c0, cnt, (double*)p->ws[2].K.p, st); if (rc) return rc; }
+            int rc = launch_hk(p, kk, cnt, soc, (cplx*)p->ws[2].H.p, flags, 0, st);
+            if (rc) return rc;
+            HeevArgs a{};
+            a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
+            a.evals = (double*)p->wsE.p; a.ld = cnt; a.col0 = 0;
+            if (n_rows) {
+                a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = n_rows; a.rows = d_rows;
+                a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * n_rows; a.vs_k = n_rows; a.vcol0 = 0;
+            }
+            rc = launch_heev_generic(p, a, st);
+            if (rc) return rc;
+        }
+        if (gate) { any_flag_kernel<<<64, 256, 0, st>>>(flags, cnt, p->d_any); LAUNCHED(); }
+        long long tiles = (cnt * N + SKTB_LOR_TILE - 1) / SKTB_LOR_TILE;
+        int gx = (int)std::min<long long>(tiles, LOR_GRID);
+        for (int e_base = 0; e_base < nE; e_base += 256 * SKTB_LOR_EPT) {
+            lorentz_partial_kernel<<<dim3(gx, ng), 256, 0, st>>>((const double*)p->wsE.p, cnt, 0, cnt, N, (const cplx*)p->wsVec.p, n_rows, d_gptr,
+                                                                 d_grows, n_groups, energies_d, nE, e_base, eta, (double*)p->wsPart.p);
+            LAUNCHED();
+        }
+        lorentz_reduce_kernel<<<(ng * nE + 127) / 128, 128, 0, st>>>((const double*)p->wsPart.p, gx, ng * nE, out_d, 1);
+        LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(p->h_pinned, p->d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nonherm_any_h) *nonherm_any_h = p->h_pinned[0];
+    return 0;
+}
+
+extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_t soc, const double* energies_d, int32_t nE, double eta,
+                             int32_t n_idx, const int32_t* idx, double* out_d, int32_t* nonherm_any_h, void* stream) {
+    if (!p || !k_d || !energies_d || !out_d) return fail("null argument");
+    if (nk <= 0 || nE <= 0) return 0;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = soc ? 2 * p->n_orb : p->n_orb;
+    std::vector<int> rows, grp_rows;
+    int gp[2] = {0, n_idx};
+    if (tracked_rows(p, N, n_idx > 0 ? 1 : 0, gp, idx, &rows, &grp_rows)) return 1;
+    const int n_rows = (int)rows.size();
+    // duplicated indices count twice in the reference's loop (greens.py:462-465): weight rows by multiplicity
+    // by tracking each occurrence separately when duplicates exist
+    if ((int)grp_rows.size() != n_rows) { rows.assign(idx, idx + n_idx); }
+    const int nr = (int)rows.size();
+    int* d_rows = nullptr;
+    if (nr) {
+        if (p->wsMisc.ensure(rows.size() * sizeof(int))) return fail("out of device memory");
+        d_rows = (int*)p->wsMisc.p;
+        CK(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    const bool gate = p->asym_bound > 0.5e-9;
+    CK(cudaMemsetAsync(p->d_any, 0, sizeof(int), st));
+    size_t per_k = (size_t)N * 8 + (size_t)N * N * 16 + (size_t)N * nr * 32 + 4;
+    long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
+    if (p->wsE.ensure((size_t)chunk * N * 8) || p->ws[2].H.ensure((size_t)chunk * N * N * 16) ||
+        (nr && (p->ws[2].RT.ensure((size_t)chunk * N * nr * 16) || p->wsVec.ensure((size_t)chunk * N * nr * 16))) ||
+        (gate && p->wsFlag.ensure((size_t)chunk * 4)))
+        return fail("out of device memory (spectral workspaces)");
+    for (long long c0 = 0; c0 < nk; c0 += chunk) {
+        long long cnt = std::min(chunk, (long long)nk - c0);
+        int* flags = gate ? (int*)p->wsFlag.p : nullptr;
+        int rc = launch_hk(p, k_d + 3 * c0, cnt, soc, (cplx*)p->ws[2].H.p, flags, 0, st);
+        if (rc) return rc;
+        HeevArgs a{};
+        a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
+        a.evals = (double*)p->wsE.p; a.ld = cnt; a.col0 = 0;
+        if (nr) {
+            a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = nr; a.rows = d_rows;
+            a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * nr; a.vs_k = nr; a.vcol0 = 0;
+        }
+        rc = launch_heev_generic(p, a, st);
+        if (rc) return rc;
+        if (gate) { any_flag_kernel<<<64, 256, 0, st>>>(flags, cnt, p->d_any); LAUNCHED(); }
+        unsigned grid = (unsigned)std::min<long long>(cnt, 148LL * 8);
+        spectral_map_kernel<<<grid, 128, (size_t)2 * N * 8, st>>>((const double*)p->wsE.p, cnt, 0, cnt, N, (const cplx*)p->wsVec.p, nr, energies_d, nE, eta,
+                                                                out_d, c0);
+        LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(p->h_pinned, p->d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nonherm_any_h) *nonherm_any_h = p->h_pinned[0];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// measurement helper
+// ------------------------------------------------------------------------------------------------------
+extern "C" int sktb_fp64_peak(int device, double* tflops, double* ms_out) {
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 1 << 16, threads = 512, blocks = prop.multiProcessorCount * 4;
+    fp64_peak_kernel<<<blocks, threads>>>(d, 1024, 1.0);           // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float t; cudaEventElapsedTime(&t, e0, e1);
+        best = std::min(best, t);
+    }
+    g_launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return 0;
+}

@@ -1,0 +1,344 @@
+"""GPU (B200): the CUDA path, called through the Python shim -> C ABI (libsktb.so), against
+(a) golden vectors produced by the real reference (tests/golden, committed) and
+(b) the numpy oracle on seeded inputs, plus size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): eigenvalues 1e-10 absolute; H(k) 1e-13; projections / DOS / LDOS 1e-8
+relative; k-points and bond indexing bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, oracle_model, spec_for, GOLDEN_SPECS
+
+pytestmark = pytest.mark.gpu
+
+EIG_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import pysktb_b200
+    return pysktb_b200
+
+
+_ham_cache = {}
+
+
+def ham_for(tb, name):
+    from pysktb_b200 import workloads as W
+    if name not in _ham_cache:
+        _ham_cache[name] = W.instantiate(spec_for(name), tb, tb.scaling)
+    return _ham_cache[name]
+
+
+def dense_H_wo_g(g):
+    H = np.zeros(tuple(g["H_wo_g_shape"]), dtype=complex)
+    H[tuple(g["H_wo_g_idx"].T)] = g["H_wo_g_val"]
+    return H
+
+
+# ---------------------------------------------------------------------------------------------------
+# K4 / K0
+# ---------------------------------------------------------------------------------------------------
+def _sk_device(tb, V, lmn):
+    import torch
+    from pysktb_b200 import _lib
+    Vd, Ld = torch.from_numpy(np.ascontiguousarray(V)).cuda(), torch.from_numpy(np.ascontiguousarray(lmn)).cuda()
+    out = torch.empty((len(V), 17, 17), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().sktb_sk_table(Vd.data_ptr(), Ld.data_ptr(), out.data_ptr(), len(V), None))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_sk_table_kernel_vs_reference_golden(tb):
+    g = golden("sk_table")
+    T = _sk_device(tb, g["V"], g["lmn"])
+    scale = np.maximum(1.0, np.abs(g["T"]).max(axis=(1, 2)))[:, None, None]
+    assert np.abs(T - g["T"]).max() / scale.max() < 1e-14
+    np.testing.assert_allclose(T / scale, g["T"] / scale, rtol=0, atol=4e-15)
+
+
+def test_sk_table_kernel_vs_oracle_seeded(tb):
+    from oracle.sk_oracle import sk_table, V_NAMES
+    r = np.random.default_rng(7)
+    lmn = r.standard_normal((300, 3))
+    lmn /= np.linalg.norm(lmn, axis=1)[:, None]
+    lmn[:6] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [1e-7, 0, 1], [0.6, 0.8, 0]]
+    V = r.uniform(-2, 2, (300, 25))
+    T = _sk_device(tb, V, lmn)
+    for b in range(300):
+        ref = sk_table({n: V[b, i] for i, n in enumerate(V_NAMES)}, *lmn[b])
+        np.testing.assert_allclose(T[b], ref, rtol=0, atol=1e-13 * max(1.0, np.abs(ref).max()))
+
+
+def test_kmesh_bit_exact(tb):
+    from pysktb_b200 import workloads as W
+    g = golden("kmesh")
+    gf = tb.GreensFunction(ham_for(tb, "C2_graphene_pz")[1])
+    for i in range(5):
+        assert np.array_equal(gf._generate_kmesh(list(g[f"nk{i}"])), g[f"mesh{i}"])
+    # large mesh, sampled against the defining formula with true division
+    nk = [512, 384, 7]
+    mesh = gf._generate_kmesh(nk)
+    idx = np.random.default_rng(1).integers(0, len(mesh), 4000)
+    i, j, l = idx // (nk[1] * nk[2]), (idx // nk[2]) % nk[1], idx % nk[2]
+    assert np.array_equal(mesh[idx], np.stack([i / nk[0], j / nk[1], l / nk[2]], axis=1))
+
+
+# ---------------------------------------------------------------------------------------------------
+# model tables, H(k), eigenvalues, eigenvectors: every golden model
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(GOLDEN_SPECS))
+def test_model_against_reference_golden(tb, name):
+    g = golden(name)
+    st, ham = ham_for(tb, name)
+    soc = bool(g["soc"])
+    assert np.array_equal(ham.bond_mat, g["bond_mat"])
+    assert np.array_equal(st.bond_list(), g["bond_list"])
+    np.testing.assert_allclose(ham.H_wo_g, dense_H_wo_g(g), rtol=0, atol=1e-14)       # K4 + scatter
+    assert np.array_equal(ham.soc_mat, g["soc_mat"])
+    k = g["k_test"]
+    Hk = ham.get_ham_batch(k[:3], l_soc=soc)
+    np.testing.assert_allclose(Hk, g["ham_k"], rtol=0, atol=1e-13)                    # K1
+    np.testing.assert_allclose(ham.get_ham(k[1], l_soc=soc), g["ham_k"][1], rtol=0, atol=1e-13)
+    nz = np.nonzero(dense_H_wo_g(g))
+    np.testing.assert_allclose(ham.calc_g(k[5])[nz], g["g_mat0_nz"], rtol=0, atol=1e-14)
+    if bool(g["raises"]):
+        with pytest.raises(Exception, match="not hermitian"):
+            ham.solve_kpath(list(k[:3]), soc=soc)
+        with pytest.raises(Exception, match="not hermitian"):
+            ham.solve_kpath(list(k[:3]), soc=soc, eig_vectors=True)
+        return
+    ev = ham.solve_kpath(list(k), soc=soc)                                            # K1+K2
+    assert ev.shape == g["evals"].shape and ev.dtype == np.float64
+    assert np.abs(ev - g["evals"]).max() < EIG_TOL, ham.last_kernel_info()
+    ev1 = ham.solve_kpath(list(k), soc=soc, parallel=0)
+    assert np.array_equal(ev, ev1)
+    if "evals_nosoc" in g:
+        assert np.abs(ham.solve_kpath(list(k[:8]), soc=False) - g["evals_nosoc"]).max() < EIG_TOL
+    # eigenvectors: reference layout [band, k, comp]; gauge-free checks + degenerate-subspace projectors
+    nv = g["evecs"].shape[1]
+    vals, vecs = ham.solve_kpath(list(k[:nv]), eig_vectors=True, soc=soc)
+    assert vecs.shape == g["evecs"].shape and vecs.dtype == np.complex128
+    assert np.abs(vals - g["evals_vec"]).max() < EIG_TOL
+    N = vals.shape[0]
+    for q in range(nv):
+        H = g["ham_k"][q] if q < 3 else ham.get_ham(k[q], l_soc=soc)
+        A = np.tril(H, -1)
+        A = A + A.conj().T + np.diag(H.diagonal().real)                               # what LAPACK 'L' reads
+        U = vecs[:, q, :].T                                                            # columns = eigenvectors
+        scale = max(1.0, np.abs(vals[:, q]).max())
+        assert np.abs(A @ U - U * vals[:, q][None, :]).max() < 1e-11 * scale
+        assert np.abs(U.conj().T @ U - np.eye(N)).max() < 1e-11
+        Uref = g["evecs"][:, q, :].T
+        # group eigenvalues closer than 1e-6 and compare subspace projectors
+        edges = [0] + [i for i in range(1, N) if vals[i, q] - vals[i - 1, q] > 1e-6] + [N]
+        for a, b in zip(edges[:-1], edges[1:]):
+            P, Pref = U[:, a:b] @ U[:, a:b].conj().T, Uref[:, a:b] @ Uref[:, a:b].conj().T
+            assert np.abs(P - Pref).max() < 1e-8
+
+
+def test_solve_k_and_sol_ham(tb):
+    g = golden("C3_sb_buckled")
+    _, ham = ham_for(tb, "C3_sb_buckled")
+    k = g["k_test"][5]
+    assert np.abs(ham.solve_k(k) - g["evals"][:, 5]).max() < EIG_TOL
+    vals, vec = ham.solve_k(k, eig_vectors=True)
+    assert vec.shape == (12, 12) and np.abs(vals - g["evals"][:, 5]).max() < EIG_TOL
+    H = ham.get_ham(k)
+    assert np.abs(ham._sol_ham(H) - g["evals"][:, 5]).max() < EIG_TOL
+    v2, U2 = ham._sol_ham(H, eig_vectors=True)
+    assert np.abs(H @ U2.T - U2.T * v2[None, :]).max() < 1e-11
+    bad = H.copy()
+    bad[0, 1] += 0.5                                       # real asymmetry -> the reference's gate fires
+    with pytest.raises(Exception, match="not hermitian"):
+        ham._sol_ham(bad)
+    bad = H.copy()
+    bad[0, 1] += 0.5j                                      # purely imaginary asymmetry passes ...
+    ev = ham._sol_ham(bad)                                 # ... and the LOWER triangle is what gets solved
+    assert np.abs(ev - g["evals"][:, 5]).max() < EIG_TOL
+    assert ham.solve_kpath(None) is None and ham.solve_kpath([k], parallel=3) is None
+    with pytest.raises(Exception, match="parallel=2 not ready"):
+        ham.solve_kpath([k], parallel=2)
+
+
+def test_known_answers(tb):
+    """SURVEY.md §4 known-answer values."""
+    _, ham = ham_for(tb, "C1_cubic_sp3")
+    kpts, dist, spl = ham.get_kpts([[0, 0, 0], [0.5, 0.5, 0.5]], 50)
+    assert len(kpts) == 51 and dist[-1] == 0.24743582965269698
+    ev = ham.solve_kpath(kpts)
+    assert ev.shape == (8, 51)
+    np.testing.assert_allclose(ev[:, 0], [-3, -3] + [2.3] * 6, atol=1e-12)
+    np.testing.assert_allclose(ev[:, -1], [0.7] * 6 + [3, 3], atol=1e-12)
+    kx = np.array([np.asarray(k, float) for k in kpts])
+    e_s = 0 + 2 * (-0.5) * np.cos(2 * np.pi * kx).sum(axis=1)        # analytic s band along Gamma-R (no s-p mixing at R/Gamma)
+    assert abs(ev[0, 0] - e_s[0]) < 1e-12
+    # graphene: E = +-|t| |1 + e^{2 pi i k1} + e^{2 pi i k2}|
+    _, hg = ham_for(tb, "C2_graphene_pz")
+    k = np.random.default_rng(5).random((257, 3))
+    ev = hg.solve_kpath(list(k), soc=False)
+    f = np.abs(1 + np.exp(2j * np.pi * k[:, 0]) + np.exp(2j * np.pi * k[:, 1]))
+    np.testing.assert_allclose(ev[1], 2.7 * f, atol=1e-11)
+    np.testing.assert_allclose(ev[0], -2.7 * f, atol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------------
+# oracle on seeded inputs, sizes beyond the fixtures
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,nk", [("T_ce_spdf_1atom", 40), ("C3_sb_buckled", 100), ("C1_cubic_sp3", 70),
+                                     ("C2_graphene_pz", 130), ("ce_spf_example", 20), ("C4_ce_spdf_2atom", 6),
+                                     ("lowsym_spd_laws", 6), ("sp_chain", 33), ("C5_zigzag_8", 40)])
+def test_eigenvalues_vs_oracle_seeded(tb, name, nk):
+    spec = spec_for(name)
+    m = oracle_model(spec)
+    _, ham = ham_for(tb, name)
+    k = np.random.default_rng(nk).random((nk, 3)) * 3 - 1.5
+    ref = m.solve_kpath(list(k), soc=spec["soc"])
+    ev = ham.solve_kpath(list(k), soc=spec["soc"])
+    assert np.abs(ev - ref).max() < EIG_TOL, ham.last_kernel_info()
+
+
+def test_ragged_and_tiny_batches(tb):
+    """1, 31, 32, 33, 63 ... k-points: partial warps / partial batches of the register kernel."""
+    spec = spec_for("T_ce_spdf_1atom")
+    _, ham = ham_for(tb, "T_ce_spdf_1atom")
+    k = np.random.default_rng(3).random((97, 3))
+    full = ham.solve_kpath(list(k))
+    for n in (1, 2, 31, 32, 33, 63, 64, 65, 96):
+        assert np.array_equal(ham.solve_kpath(list(k[:n])), full[:, :n]), n
+    assert ham.solve_kpath([]).shape == (32, 0)
+
+
+def test_mesh_solver_equals_list_solver(tb):
+    import torch
+    _, ham = ham_for(tb, "T_ce_spdf_1atom")
+    gf = tb.GreensFunction(ham)
+    nk = [6, 5, 4]
+    mesh = gf._generate_kmesh(nk)
+    a = ham.solve_kpath(list(mesh))
+    b = ham.solve_kmesh(nk).cpu().numpy()
+    assert np.array_equal(a, b)
+    c = ham.solve_kmesh(nk, first=17, count=50).cpu().numpy()
+    assert np.array_equal(c, a[:, 17:67])
+    assert isinstance(ham.solve_kmesh(nk), torch.Tensor)
+
+
+def test_large_ribbon_against_lapack_on_device_hamiltonian(tb):
+    """C5 at full size (512 pz orbitals): K1 vs oracle H(k) at one k, K2 (global-memory path) vs LAPACK on the
+    SAME matrices, eigenvector residuals, and the trace identity."""
+    from pysktb_b200 import workloads as W
+    spec = W.zigzag_ribbon(256)
+    st, ham = W.instantiate(spec, tb, tb.scaling)
+    assert ham.n_orbitals == 512 and len(st.bond_list()) == 1534
+    k = np.array([[0.0, 0, 0], [0.37, 0, 0], [0.5, 0, 0]])
+    H = ham.get_ham_batch(k, l_soc=False)
+    assert np.abs(H - H.conj().transpose(0, 2, 1)).max() < 1e-13
+    ev = ham.solve_kpath(list(k), soc=False)
+    for q in range(3):
+        ref = np.linalg.eigvalsh(H[q])
+        assert np.abs(ev[:, q] - ref).max() < EIG_TOL
+        assert abs(ev[:, q].sum() - np.trace(H[q]).real) < 1e-9
+    vals, vecs = ham.solve_kpath(list(k[1:2]), eig_vectors=True, soc=False)
+    U = vecs[:, 0, :].T
+    assert np.abs(H[1] @ U - U * vals[:, 0][None, :]).max() < 1e-10
+    assert np.abs(U.conj().T @ U - np.eye(512)).max() < 1e-10
+    # oracle H(k) on a smaller ribbon of the same family (the oracle's Python loops are slow at 512)
+    m = oracle_model(W.zigzag_ribbon(48))
+    _, h48 = W.instantiate(W.zigzag_ribbon(48), tb, tb.scaling)
+    assert np.abs(h48.get_ham(k[1], l_soc=False) - m.get_ham(k[1], l_soc=False)).max() < 1e-13
+    assert np.abs(h48.solve_kpath(list(k), soc=False) - m.solve_kpath(list(k), soc=False)).max() < EIG_TOL
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 47, 64, 96, 110, 111, 160])
+def test_heev_random_hermitian_vs_lapack(tb, N):
+    """K2 alone (sktb_heev) on random complex matrices, lower-triangle semantics, both storage regimes."""
+    import torch
+    from pysktb_b200 import _lib
+    _, ham = ham_for(tb, "C1_cubic_sp3")
+    r = np.random.default_rng(N)
+    nm = 5
+    M = r.standard_normal((nm, N, N)) + 1j * r.standard_normal((nm, N, N))          # NOT Hermitian on purpose
+    if N >= 8:
+        M[1] = np.kron(M[1][: N // 2 + N % 2, : N // 2 + N % 2], np.eye(2))[:N, :N]  # exact degeneracies
+        M[2] = np.diag(r.standard_normal(N))                                         # already diagonal
+        M[3][N // 2:, : N // 2] = 0                                                  # decoupled blocks
+    Md = torch.from_numpy(np.ascontiguousarray(M)).cuda()
+    ev = torch.empty((N, nm), dtype=torch.float64, device="cuda")
+    vec = torch.empty((N, nm, N), dtype=torch.complex128, device="cuda")
+    _lib.check(_lib.lib().sktb_heev(ham._plan, Md.data_ptr(), N, nm, ev.data_ptr(), vec.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    ev2 = torch.empty((N, nm), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().sktb_heev(ham._plan, Md.data_ptr(), N, nm, ev2.data_ptr(), None, None, None))
+    torch.cuda.synchronize()
+    ev, ev2, vec = ev.cpu().numpy(), ev2.cpu().numpy(), vec.cpu().numpy()
+    for q in range(nm):
+        A = np.tril(M[q], -1)
+        A = A + A.conj().T + np.diag(M[q].diagonal().real)
+        ref = np.linalg.eigvalsh(M[q])                                               # numpy reads the lower triangle too
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(ev[:, q] - ref).max() < 1e-12 * scale * max(1, N // 8)
+        assert np.abs(ev2[:, q] - ref).max() < 1e-12 * scale * max(1, N // 8)
+        U = vec[:, q, :].T
+        assert np.abs(A @ U - U * ev[:, q][None, :]).max() < 1e-11 * scale * max(1, N // 8)
+        assert np.abs(U.conj().T @ U - np.eye(N)).max() < 1e-11 * max(1, N // 8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Green's functions: DOS / LDOS / edge DOS / spectral maps against the reference's inverse-based numbers
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["C1_cubic_sp3", "C2_graphene_pz", "C3_sb_buckled", "C5_zigzag_8", "lowsym_spd_laws"])
+def test_dos_ldos_vs_reference_golden(tb, name):
+    g = golden(name)
+    st, ham = ham_for(tb, name)
+    gf = tb.GreensFunction(ham)
+    soc = bool(g["soc"])
+    dos = gf.dos(g["dos_E"], nk=list(g["dos_nk"]), eta=float(g["dos_eta"]), soc=soc)
+    np.testing.assert_allclose(dos, g["dos"], rtol=1e-8)
+    if "ldos" in g:
+        orbs = [int(x) for x in g["ldos_orbs"]] or None
+        atoms = [int(x) for x in g["ldos_atoms"]]
+        ld = gf.ldos(g["ldos_E"], atom_indices=atoms, orbital_indices=orbs, nk=list(g["ldos_nk"]), eta=float(g["ldos_eta"]), soc=soc)
+        assert ld.shape == g["ldos"].shape
+        np.testing.assert_allclose(ld, g["ldos"], rtol=1e-8)
+        by = gf.ldos_by_orbital(g["ldos_E"], atom_index=atoms[0], nk=list(g["ldos_nk"]), eta=float(g["ldos_eta"]), soc=soc)
+        assert list(by.keys()) == list(st.atoms[atoms[0]].orbitals)
+        np.testing.assert_allclose(np.array([by[o] for o in st.atoms[atoms[0]].orbitals]), g["ldos_by_orbital"], rtol=1e-8)
+    if "edge_dos" in g:
+        sgf = tb.SurfaceGreensFunction(ham, surface_atoms=[int(x) for x in g["edge_atoms"]])
+        ed = sgf.edge_dos(g["edge_E"], nk=int(g["edge_nk"]), eta=float(g["edge_eta"]), soc=soc)
+        np.testing.assert_allclose(ed, g["edge_dos"], rtol=1e-8)
+        sp = sgf.edge_spectral_kpath(g["edge_spec_k"], g["edge_E"][::4], eta=float(g["edge_eta"]), soc=soc)
+        np.testing.assert_allclose(sp, g["edge_spec"], rtol=1e-8)
+        assert abs(sgf.surface_spectral(g["edge_E"][8], [g["edge_spec_k"][2], 0, 0], eta=float(g["edge_eta"]), soc=soc) - g["edge_spec"][2, 2]) < 1e-8 * abs(g["edge_spec"][2, 2])
+        kd, sm, spl = gf.spectral_kpath([[0, 0, 0], [0.5, 0, 0]], g["edge_E"][::4], nk=5, eta=float(g["edge_eta"]), soc=soc)
+        np.testing.assert_allclose(sm, g["spec_kpath"], rtol=1e-8)
+
+
+def test_retarded_and_spectral_matrices(tb):
+    from scipy import linalg
+    _, ham = ham_for(tb, "C3_sb_buckled")
+    gf = tb.GreensFunction(ham)
+    k, E, eta = [0.21, 0.4, 0.0], 0.3, 0.05
+    H = ham.get_ham(k)
+    G = linalg.inv((E + 1j * eta) * np.eye(12) - H)
+    np.testing.assert_allclose(gf.retarded(E, k, eta), G, rtol=0, atol=1e-10 * np.abs(G).max())
+    np.testing.assert_allclose(gf.spectral(E, k, eta), -G.imag / np.pi, rtol=0, atol=1e-10 * np.abs(G).max())
+
+
+def test_dos_properties_large_mesh(tb):
+    """Size-independent properties at a mesh the oracle cannot do: normalisation (integral of the Lorentzian
+    DOS = N within the tails), particle-hole symmetry of graphene, and chunk/shard invariance."""
+    _, ham = ham_for(tb, "C2_graphene_pz")
+    gf = tb.GreensFunction(ham)
+    E = np.linspace(-40, 40, 1601)
+    dos = gf.dos(E, nk=[384, 384, 1], eta=0.1, soc=False)
+    assert np.abs(dos - dos[::-1]).max() < 1e-9 * dos.max()
+    integral = np.trapezoid(dos, E)
+    assert abs(integral - 2.0) < 0.02                       # Lorentzian tails beyond +-40 eV carry ~0.3 %
+    ld = gf.ldos(E[::16], nk=[96, 96, 1], eta=0.1, soc=False)
+    np.testing.assert_allclose(ld.sum(axis=0), gf.dos(E[::16], nk=[96, 96, 1], eta=0.1, soc=False), rtol=1e-10)
+    np.testing.assert_allclose(ld[0], ld[1], rtol=1e-9)     # sublattice symmetry
