@@ -1,18 +1,28 @@
-// K1+K2 fused, register-resident, for N <= 32 (configs C1-C3 and the north-star 32-orbital model):
-// H(k) is assembled straight into registers and never touches HBM; per k-point the only traffic is
-// 24 B of k in (0 B for meshes: K0 is fused too) and 8*N B of eigenvalues out.
+// K0+K1+K2 for N <= 32 (configs C1-C3 and the north-star 32-orbital model), register-resident.
+// H(k) is assembled straight into registers and never touches HBM; per k-point the HBM traffic is 24 B of k in
+// (0 B for meshes: K0 is fused), a 16*NC-byte (d,e) scratch round trip through L2, and 8*N B of eigenvalues out.
 //
-// Mapping.  L = 4/8/16/32 lanes own one matrix (32/L matrices per warp side by side); lane i holds row i of the
-// mirrored-lower Hermitian matrix  A_eff[i][k] = H[i][k] (k<i), conj(H[k][i]) (k>i), Re H[i][i]  - LAPACK
-// zheevd(UPLO='L') semantics, which is what the reference's numpy call reads (hamiltonian.py:119).  The
-// mirrored tables are prepared on the host (build_tables) so no cross-lane transposition is needed:
-//   Lt[b][kappa][iota] = T_b[iota][kappa] (kappa <= iota) | T_b[kappa][iota] (kappa > iota, used with conj phase).
-// Householder tridiagonalisation is fully unrolled over the column index (static register indexing);
-// v and w are exchanged through a 1 KB shared-memory buffer per warp (broadcast LDS.128), norms and dots
-// by xor-shuffles inside the L-lane group.  After 32 matrices the warp transposes (d,e) through shared
-// memory and every lane runs the implicit-shift QL of ITS OWN matrix (no idle lanes, rsqrt-based rotations),
-// sorts its eigenvalues with a register bitonic network and the warp stores them coalesced along k.
-// FP64 CUDA cores only: the work is batched rank-2 updates on 32x32 Hermitian matrices, not a GEMM.
+// Two kernels per chunk of k-points:
+//
+//  tridiag_small_kernel  (FP64-pipe bound)   L = 4/8/16/32 lanes own one matrix (32/L matrices per warp side by
+//    side); lane i holds row i of the mirrored-lower Hermitian matrix
+//        A_eff[i][k] = H[i][k] (k<i), conj(H[k][i]) (k>i), Re H[i][i]
+//    i.e. LAPACK zheevd(UPLO='L') semantics, which is what the reference's numpy call reads (hamiltonian.py:119).
+//    The mirrored tables are prepared on the host (build_tables) so no cross-lane transposition is needed:
+//        Lt[b][kappa][iota] = T_b[iota][kappa] (kappa <= iota) | T_b[kappa][iota] (kappa > iota, conj phase).
+//    Householder tridiagonalisation keeps register indexing static WITHOUT unrolling the column loop: after
+//    every step the register window is rotated by one column (column j always sits in register 0), and the
+//    loop is split into phases of S steps whose bodies are compiled for a fixed window width W = NC, NC-S, ...
+//    (a fully unrolled N=32 body is ~600 KB of SASS and made the kernel instruction-fetch bound at 3 % of FP64
+//    peak; the rolled phases are ~40 KB and stay in the instruction cache).  v and w are exchanged through a
+//    2 KB shared-memory buffer per warp (broadcast LDS.128), norms and dots by xor-shuffles inside the group.
+//
+//  tql_small_kernel      (latency bound, high occupancy)   one tridiagonal matrix PER LANE: (d,e) are transposed
+//    through shared memory (odd stride, conflict-free), every lane runs the implicit-shift QL of its own matrix
+//    (no idle lanes, rsqrt-based rotations), sorts its eigenvalues with a register bitonic network and the warp
+//    stores them coalesced along k (the reference's [band, k] layout).
+//
+// FP64 CUDA cores only: the work is batched rank-2 updates on <=32x32 Hermitian matrices, not a GEMM.
 #pragma once
 #include <string>
 #include <vector>
@@ -40,16 +50,22 @@ struct SmallArgs {
     SmallTables t;
     const double* k;            // [nk][3] or NULL -> mesh
     int mesh0, mesh1, mesh2;
-    long long first, nk;
+    long long first, nk;        // this launch: mesh points first.. / k rows 0..nk
     int N, soc;
+    double* scratch;            // [nk][2][NC]  (d | e) of every matrix
+    int* flags; long long flag_off;
+};
+
+struct TqlArgs {
+    const double* scratch; long long nk; int N;
     double* evals; long long ld, col0;
-    int* flags; int* fail;
+    int* fail;
 };
 
 inline bool supports(int N) { return N >= 1 && N <= 32; }
 
 constexpr int SMALL_WARPS = 4;
-constexpr int DSTRIDE = 33;   // odd stride: conflict-free both for the per-row stores and the per-lane QL
+constexpr int DSTRIDE = 33;   // odd stride: conflict-free both for the transposing stores and the per-lane QL
 
 // ---------------------------------------------------------------------------------------------------------
 template <int P2>
@@ -73,6 +89,7 @@ SKTB_D void bitonic_sort(double (&a)[P2]) {
 }
 
 // implicit-shift QL, one matrix per lane, strided shared memory (stride DSTRIDE doubles), rsqrt rotations.
+// The deflation test of the next sweep is folded into the rotation loop (no separate rescan per sweep).
 SKTB_D int tql_lane(double* d, double* e, int n) {
     const double eps = 2.220446049250313e-16;
 #define D_(i) d[(i) * DSTRIDE]
@@ -81,15 +98,17 @@ SKTB_D int tql_lane(double* d, double* e, int n) {
     int fail = 0;
     for (int l = 0; l < n; ++l) {
         int iter = 0;
-        while (true) {
-            int m = l;
+        // first small off-diagonal at or after l
+        int m = l;
+        {
             double dm = fabs(D_(m));
             for (; m < n - 1; ++m) {
                 double dn = fabs(D_(m + 1));
                 if (fabs(E_(m)) <= eps * (dm + dn)) break;
                 dm = dn;
             }
-            if (m == l) break;
+        }
+        while (m != l) {
             if (++iter > 80) { fail = 1; break; }
             double el = E_(l), dl = D_(l);
             double g = (D_(l + 1) - dl) / (2.0 * el);
@@ -98,7 +117,9 @@ SKTB_D int tql_lane(double* d, double* e, int n) {
             double s = 1.0, c = 1.0, p = 0.0;
             int i = m - 1;
             bool under = false;
-            double di1 = D_(m);                       // d[i+1]
+            double di1 = D_(m);                       // original d[i+1]
+            double dnext = (m + 1 < n) ? fabs(D_(m + 1)) : 0.0;   // |d[i+2]| (final) for the folded deflation test
+            int m_new = m;
             for (; i >= l; --i) {
                 double ei = E_(i), di = D_(i);
                 double f = s * ei, b = c * ei;
@@ -106,17 +127,37 @@ SKTB_D int tql_lane(double* d, double* e, int n) {
                 if (h2 == 0.0) { E_(i + 1) = 0.0; D_(i + 1) = di1 - p; E_(m) = 0.0; under = true; break; }
                 double ir = rsqrt(h2);
                 r = h2 * ir;
-                E_(i + 1) = r;
                 s = f * ir; c = g * ir;
                 g = di1 - p;
-                r = fma(di - g, s, 2.0 * c * b);
-                p = s * r;
-                D_(i + 1) = g + p;
-                g = fma(c, r, -b);
+                double rr = fma(di - g, s, 2.0 * c * b);
+                p = s * rr;
+                double dnew = g + p;
+                D_(i + 1) = dnew;
+                if (i + 1 < m) {                       // e[i+1] couples i+1 and i+2 (both final now)
+                    E_(i + 1) = r;
+                    double an = fabs(dnew);
+                    if (r <= eps * (an + dnext)) m_new = i + 1;
+                    dnext = an;
+                } else {
+                    dnext = fabs(dnew);                // e[m] is reset to 0 below
+                }
+                g = fma(c, rr, -b);
                 di1 = di;
             }
-            if (under) continue;
-            D_(l) = di1 - p; E_(l) = g; E_(m) = 0.0;
+            if (under) {                              // rare: rescan
+                m = l;
+                double dm = fabs(D_(m));
+                for (; m < n - 1; ++m) {
+                    double dn = fabs(D_(m + 1));
+                    if (fabs(E_(m)) <= eps * (dm + dn)) break;
+                    dm = dn;
+                }
+                continue;
+            }
+            double dl_new = di1 - p;
+            D_(l) = dl_new; E_(l) = g; E_(m) = 0.0;
+            if (fabs(g) <= eps * (fabs(dl_new) + dnext)) m_new = l;
+            m = m_new;
         }
     }
 #undef D_
@@ -132,13 +173,95 @@ SKTB_D double group_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One Householder step on a register window of W columns: B[q] = A[i][j+q].  v/w buffers hold 2L entries per
+// group, the upper L are zero, so window columns beyond the matrix read v = w = 0.
+// ---------------------------------------------------------------------------------------------------------
+template <int NC> struct PhaseSteps { static constexpr int value = NC >= 16 ? 8 : 4; };
+
+template <int W, int NC, int L>
+SKTB_D void hh_step(cplx (&B)[NC], const int j, const int i, const int g, const int lane, cplx* vbuf, cplx* wbuf, double& dval,
+                    double& eval) {
+    const cplx x = B[0];
+    const bool below = i > j + 1;
+    double xn = below ? fma(x.x, x.x, x.y * x.y) : 0.0;
+    xn = group_sum<L>(xn);
+    cplx alpha;
+    alpha.x = __shfl_sync(0xffffffffu, x.x, j + 1, L);
+    alpha.y = __shfl_sync(0xffffffffu, x.y, j + 1, L);
+    dval = (i == j) ? x.x : dval;
+    // Householder generator (zlarfg): one rsqrt + one reciprocal
+    double beta; cplx tau, scale;
+    {
+        const bool trivial = (xn == 0.0) && (alpha.y == 0.0);
+        double n2 = fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xn));
+        double inrm = trivial ? 0.0 : rsqrt(n2);
+        double nrm = n2 * inrm;
+        double sgn = alpha.x >= 0.0 ? -1.0 : 1.0;
+        beta = trivial ? alpha.x : sgn * nrm;
+        double ib = sgn * inrm;                                   // 1 / beta
+        tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
+        double dx = alpha.x - beta, dy = alpha.y;
+        double den = fma(dx, dx, dy * dy);
+        double id = trivial ? 0.0 : __drcp_rn(den);
+        scale = cmake(dx * id, -dy * id);
+    }
+    eval = (i == j) ? beta : eval;
+    if (j == NC - 2) return;                                      // the last reflector only fixes e[NC-2]
+    cplx v = (i == j + 1) ? cmake(1.0, 0.0) : (below ? cmul(x, scale) : cmake(0.0, 0.0));
+    vbuf[lane + g * L] = v;                                       // group g owns [2gL, 2gL+L), zero tail above
+    __syncwarp();
+    const cplx* vg = vbuf + 2 * g * L + j;
+    const cplx* wg = wbuf + 2 * g * L + j;
+    cplx acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = cmake(0.0, 0.0);
+#pragma unroll
+    for (int q = 1; q < W; ++q) cfma(acc[q & 3], B[q], vg[q]);
+    cplx p = cmul(tau, cadd(cadd(acc[0], acc[1]), cadd(acc[2], acc[3])));
+    if (i <= j) p = cmake(0.0, 0.0);
+    cplx dp = cmulc(p, v);
+    dp.x = group_sum<L>(dp.x); dp.y = group_sum<L>(dp.y);
+    cplx a2 = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dp);
+    cplx w = p;
+    cfma(w, a2, v);
+    wbuf[lane + g * L] = w;
+    __syncwarp();
+#pragma unroll
+    for (int q = 1; q < W; ++q) {
+        cplx vk = vg[q], wk = wg[q];
+        cplx t = B[q];
+        // A[i][k] -= v_i conj(w_k) + w_i conj(v_k)
+        t.x = fma(-v.x, wk.x, t.x); t.x = fma(-v.y, wk.y, t.x);
+        t.y = fma(-v.y, wk.x, t.y); t.y = fma(v.x, wk.y, t.y);
+        t.x = fma(-w.x, vk.x, t.x); t.x = fma(-w.y, vk.y, t.x);
+        t.y = fma(-w.y, vk.x, t.y); t.y = fma(w.x, vk.y, t.y);
+        B[q] = t;
+    }
+    __syncwarp();
+}
+
+template <int W, int S, int NC, int L>
+SKTB_D void hh_phases(cplx (&B)[NC], int& j, const int i, const int g, const int lane, cplx* vbuf, cplx* wbuf, double& dval,
+                      double& eval) {
+    constexpr int steps = (W <= S) ? W - 1 : S;
+#pragma unroll 1
+    for (int s = 0; s < steps; ++s, ++j) {
+        hh_step<W, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval);
+#pragma unroll
+        for (int q = 0; q + 1 < W; ++q) B[q] = B[q + 1];          // rotate: column j+1 -> register 0
+        B[W - 1] = cmake(0.0, 0.0);
+    }
+    if constexpr (W > S) hh_phases<W - S, S, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // NC: compile-time column count (>= N, multiple of 4); L: lanes per matrix (power of two >= NC);
 // SOC: kron(h, I2) + soc_mat assembly; GATE: evaluate the reference's Hermiticity gate per k.
 // ---------------------------------------------------------------------------------------------------------
 template <int NC, int L, bool SOC, bool GATE>
-__global__ void __launch_bounds__(SMALL_WARPS * 32) heev_small_kernel(SmallArgs a) {
+__global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_small_kernel(SmallArgs a) {
     constexpr int G = 32 / L;                 // matrices side by side in a warp
-    constexpr int P2 = L;                     // bitonic width
+    constexpr int NH = SOC ? NC / 2 : NC;     // orbital columns built per row
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.t.n_orb, nb = a.t.n_bonds, N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -154,167 +277,148 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) heev_small_kernel(SmallArgs 
     off = (off + 1) & ~(size_t)1;              // 16-byte align
     cplx* sSt = reinterpret_cast<cplx*>(sLt + off);
     cplx* wbase = sSt + (SOC ? N * N : 0);
-    const size_t per_warp_cplx = (size_t)2 * 32 + (size_t)G * nb + (size_t)NC * DSTRIDE;   // v,w | phases | d,e (2*NC*DSTRIDE doubles)
+    const size_t per_warp_cplx = (size_t)2 * 64 + (size_t)G * nb;   // v,w (zero-padded) | phases
     cplx* myw = wbase + per_warp_cplx * warp;
     cplx* vbuf = myw;
-    cplx* wbuf = myw + 32;
-    cplx* phs = myw + 64 + (size_t)g * nb;
-    double* dbuf = reinterpret_cast<double*>(myw + 64 + (size_t)G * nb);
-    double* ebuf = dbuf + NC * DSTRIDE;
+    cplx* wbuf = myw + 64;
+    cplx* phs = myw + 128 + (size_t)g * nb;
 
     for (int t = tid; t < nb * n * n; t += blockDim.x) { sLt[t] = a.t.Lt[t]; if (GATE) sDt[t] = a.t.Dt[t]; }
     for (int t = tid; t < n; t += blockDim.x) sOn[t] = a.t.onsite[t];
     for (int t = tid; t < 3 * nb; t += blockDim.x) sBv[t] = a.t.bvec[t];
     if (SOC) for (int t = tid; t < N * N; t += blockDim.x) { sSt[t] = a.t.St[t]; if (GATE) sSA[t] = a.t.SAt[t]; }
+    for (int t = lane; t < 128; t += 32) myw[t] = cmake(0.0, 0.0);      // v/w buffers incl. their zero tails
     __syncthreads();
 
-    const long long n_batches = (a.nk + 31) / 32;
     const long long gwarp = (long long)blockIdx.x * SMALL_WARPS + warp, nwarps = (long long)gridDim.x * SMALL_WARPS;
     const bool row_ok = i < N;
     const int mu = SOC ? (i >> 1) : i;
+    const int mu_c = (row_ok && mu < n) ? mu : 0;
     const int spin = i & 1;
 
-    for (long long batch = gwarp; batch < n_batches; batch += nwarps) {
-        const long long kbase = batch * 32;
 #pragma unroll 1
-        for (int it = 0; it < L; ++it) {
-            const int slot = it * G + g;
-            long long kq = kbase + slot;
-            const bool k_ok = kq < a.nk;
-            if (!k_ok) kq = a.nk - 1;
-            double k0, k1, k2;
-            if (a.k) { k0 = a.k[3 * kq]; k1 = a.k[3 * kq + 1]; k2 = a.k[3 * kq + 2]; }
-            else kmesh_point(a.first + kq, a.mesh0, a.mesh1, a.mesh2, k0, k1, k2);
+    for (long long k0q = gwarp * G; k0q < a.nk; k0q += nwarps * G) {
+        long long kq = k0q + g;
+        const bool k_ok = kq < a.nk;
+        if (!k_ok) kq = a.nk - 1;
+        double k0, k1, k2;
+        if (a.k) { k0 = a.k[3 * kq]; k1 = a.k[3 * kq + 1]; k2 = a.k[3 * kq + 2]; }
+        else kmesh_point(a.first + kq, a.mesh0, a.mesh1, a.mesh2, k0, k1, k2);
 
-            // ---- bond phases (one sincos per lane) ----
-            {
-                double c0 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[0]), __dmul_rn(k1, a.t.rec[3])), __dmul_rn(k2, a.t.rec[6]));
-                double c1 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[1]), __dmul_rn(k1, a.t.rec[4])), __dmul_rn(k2, a.t.rec[7]));
-                double c2 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[2]), __dmul_rn(k1, a.t.rec[5])), __dmul_rn(k2, a.t.rec[8]));
-                for (int b = i; b < nb; b += L) {
-                    double dot = __dadd_rn(__dadd_rn(__dmul_rn(c0, sBv[3 * b]), __dmul_rn(c1, sBv[3 * b + 1])), __dmul_rn(c2, sBv[3 * b + 2]));
-                    cplx ph;
-                    sincos(__dmul_rn(6.283185307179586, dot), &ph.y, &ph.x);
-                    phs[b] = ph;
+        // ---- bond phases exp(2 pi i (k@rec).d), one sincos per lane (calc_g arithmetic, hamiltonian.py:280,311)
+        {
+            double c0 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[0]), __dmul_rn(k1, a.t.rec[3])), __dmul_rn(k2, a.t.rec[6]));
+            double c1 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[1]), __dmul_rn(k1, a.t.rec[4])), __dmul_rn(k2, a.t.rec[7]));
+            double c2 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[2]), __dmul_rn(k1, a.t.rec[5])), __dmul_rn(k2, a.t.rec[8]));
+            for (int b = i; b < nb; b += L) {
+                double dot = __dadd_rn(__dadd_rn(__dmul_rn(c0, sBv[3 * b]), __dmul_rn(c1, sBv[3 * b + 1])), __dmul_rn(c2, sBv[3 * b + 2]));
+                cplx ph;
+                sincos(__dmul_rn(6.283185307179586, dot), &ph.y, &ph.x);
+                phs[b] = ph;
+            }
+        }
+        __syncwarp();
+
+        // ---- K1: row i of the mirrored-lower H(k), straight into registers (bond loop outside: NH independent
+        //      FMA chains per bond) ----
+        cplx A[NC];
+        double gate_max = -1.0;
+        {
+            double re[NH], im[NH], gs[GATE ? NH : 1];
+#pragma unroll
+            for (int nu = 0; nu < NH; ++nu) { re[nu] = 0.0; im[nu] = 0.0; if (GATE) gs[nu] = 0.0; }
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                const cplx ph = phs[b];
+                const double* Lb = sLt + (size_t)b * n * n + mu_c;
+                const double* Db = sDt + (size_t)b * n * n + mu_c;
+#pragma unroll
+                for (int nu = 0; nu < NH; ++nu) {
+                    if (nu < n) {
+                        double t = Lb[nu * n];
+                        re[nu] = fma(t, ph.x, re[nu]); im[nu] = fma(t, ph.y, im[nu]);
+                        if (GATE) gs[nu] = fma(Db[nu * n], ph.x, gs[nu]);
+                    }
                 }
             }
-            __syncwarp();
-
-            // ---- K1: row i of the mirrored-lower H(k), straight into registers ----
-            cplx A[NC];
-            double gate_max = -1.0;
-            if (SOC) {
+            const bool orb_ok = row_ok && mu < n;
 #pragma unroll
-                for (int nu = 0; nu < NC / 2; ++nu) {
-                    double re = 0.0, im = 0.0, gsum = 0.0;
-                    if (row_ok && nu < n) {
-                        for (int b = 0; b < nb; ++b) {
-                            double t = sLt[((size_t)b * n + nu) * n + mu];
-                            cplx ph = phs[b];
-                            re = fma(t, ph.x, re); im = fma(t, ph.y, im);
-                            if (GATE) gsum = fma(sDt[((size_t)b * n + nu) * n + mu], ph.x, gsum);
-                        }
-                        if (nu == mu) { re += sOn[mu]; im = 0.0; }
-                        else if (nu > mu) im = -im;
-                    }
+            for (int nu = 0; nu < NH; ++nu) {
+                double r_ = orb_ok ? re[nu] : 0.0, i_ = orb_ok ? im[nu] : 0.0;
+                if (nu == mu) { r_ += orb_ok ? sOn[mu_c] : 0.0; i_ = 0.0; }
+                else if (nu > mu) i_ = -i_;
+                if (SOC) {
                     cplx s0 = cmake(0.0, 0.0), s1 = s0;
                     if (row_ok && 2 * nu < N) {
                         s0 = sSt[(size_t)(2 * nu) * N + i]; s1 = sSt[(size_t)(2 * nu + 1) * N + i];
                         if (GATE) {
-                            gate_max = fmax(gate_max, (spin == 0 ? gsum : 0.0) + sSA[(size_t)(2 * nu) * N + i]);
-                            gate_max = fmax(gate_max, (spin == 1 ? gsum : 0.0) + sSA[(size_t)(2 * nu + 1) * N + i]);
+                            double gq = (orb_ok && nu < n) ? gs[nu] : 0.0;
+                            gate_max = fmax(gate_max, (spin == 0 ? gq : 0.0) + sSA[(size_t)(2 * nu) * N + i]);
+                            gate_max = fmax(gate_max, (spin == 1 ? gq : 0.0) + sSA[(size_t)(2 * nu + 1) * N + i]);
                         }
                     }
-                    A[2 * nu] = cmake((spin == 0 ? re : 0.0) + s0.x, (spin == 0 ? im : 0.0) + s0.y);
-                    A[2 * nu + 1] = cmake((spin == 1 ? re : 0.0) + s1.x, (spin == 1 ? im : 0.0) + s1.y);
-                }
-            } else {
-#pragma unroll
-                for (int nu = 0; nu < NC; ++nu) {
-                    double re = 0.0, im = 0.0, gsum = 0.0;
-                    if (row_ok && nu < n) {
-                        for (int b = 0; b < nb; ++b) {
-                            double t = sLt[((size_t)b * n + nu) * n + mu];
-                            cplx ph = phs[b];
-                            re = fma(t, ph.x, re); im = fma(t, ph.y, im);
-                            if (GATE) gsum = fma(sDt[((size_t)b * n + nu) * n + mu], ph.x, gsum);
-                        }
-                        if (nu == mu) { re += sOn[mu]; im = 0.0; }
-                        else if (nu > mu) im = -im;
-                        if (GATE) gate_max = fmax(gate_max, gsum);
-                    }
-                    A[nu] = cmake(re, im);
+                    A[2 * nu] = cmake((spin == 0 ? r_ : 0.0) + s0.x, (spin == 0 ? i_ : 0.0) + s0.y);
+                    A[2 * nu + 1] = cmake((spin == 1 ? r_ : 0.0) + s1.x, (spin == 1 ? i_ : 0.0) + s1.y);
+                } else {
+                    if (GATE && orb_ok && nu < n) gate_max = fmax(gate_max, gs[nu]);
+                    A[nu] = cmake(r_, i_);
                 }
             }
+        }
+        if (a.flags) {
+            int bad = 0;
             if (GATE) {
-                bool bad = gate_max > 1.0e-9;
-                unsigned m = __ballot_sync(0xffffffffu, bad);
+                unsigned m = __ballot_sync(0xffffffffu, gate_max > 1.0e-9);
                 unsigned gm = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (g * L));
-                if (i == 0 && k_ok && a.flags) a.flags[a.col0 + kq] = (m & gm) ? 1 : 0;
-            } else {
-                if (i == 0 && k_ok && a.flags) a.flags[a.col0 + kq] = 0;
+                bad = (m & gm) ? 1 : 0;
             }
-
-            // ---- K2a: Householder tridiagonalisation, columns unrolled ----
-            double dval = 0.0, eval = 0.0;
-#pragma unroll
-            for (int j = 0; j < NC - 1; ++j) {
-                const cplx x = A[j];
-                const bool below = i > j + 1;
-                double xn = below ? fma(x.x, x.x, x.y * x.y) : 0.0;
-                xn = group_sum<L>(xn);
-                cplx alpha;
-                alpha.x = __shfl_sync(0xffffffffu, x.x, j + 1, L);
-                alpha.y = __shfl_sync(0xffffffffu, x.y, j + 1, L);
-                dval = (i == j) ? x.x : dval;
-                double beta; cplx tau, scale;
-                householder(alpha, xn, beta, tau, scale);
-                eval = (i == j) ? beta : eval;
-                if (j == NC - 2) break;                       // the last reflector only fixes e[NC-2]
-                cplx v = (i == j + 1) ? cmake(1.0, 0.0) : (below ? cmul(x, scale) : cmake(0.0, 0.0));
-                vbuf[lane] = v;
-                __syncwarp();
-                cplx acc0 = cmake(0.0, 0.0), acc1 = acc0;
-#pragma unroll
-                for (int k = j + 1; k < NC; ++k) {
-                    cplx vk = vbuf[g * L + k];
-                    if ((k - j) & 1) cfma(acc0, A[k], vk); else cfma(acc1, A[k], vk);
-                }
-                cplx p = cmul(tau, cadd(acc0, acc1));
-                if (i <= j) p = cmake(0.0, 0.0);
-                cplx dp = cmulc(p, v);
-                dp.x = group_sum<L>(dp.x); dp.y = group_sum<L>(dp.y);
-                cplx a2 = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dp);
-                cplx w = p;
-                cfma(w, a2, v);
-                wbuf[lane] = w;
-                __syncwarp();
-                const cplx vc = v, wc = w;
-#pragma unroll
-                for (int k = j + 1; k < NC; ++k) {
-                    cplx vk = vbuf[g * L + k], wk = wbuf[g * L + k];
-                    cplx t = A[k];
-                    // A[i][k] -= v_i conj(w_k) + w_i conj(v_k)
-                    t.x = fma(-vc.x, wk.x, t.x); t.x = fma(-vc.y, wk.y, t.x);
-                    t.y = fma(-vc.y, wk.x, t.y); t.y = fma(vc.x, wk.y, t.y);
-                    t.x = fma(-wc.x, vk.x, t.x); t.x = fma(-wc.y, vk.y, t.x);
-                    t.y = fma(-wc.y, vk.x, t.y); t.y = fma(wc.x, vk.y, t.y);
-                    A[k] = t;
-                }
-                __syncwarp();
-            }
-            dval = (i == NC - 1) ? A[NC - 1].x : dval;
-            if (i < NC) { dbuf[i * DSTRIDE + slot] = dval; ebuf[i * DSTRIDE + slot] = eval; }
-            __syncwarp();
+            if (i == 0 && k_ok) a.flags[a.flag_off + kq] = bad;
         }
 
-        // ---- K2b: one tridiagonal matrix per lane ----
+        // ---- K2a: Householder tridiagonalisation, rotating register window ----
+        double dval = 0.0, eval = 0.0;
+        {
+            int j = 0;
+            hh_phases<NC, PhaseSteps<NC>::value, NC, L>(A, j, i, g, lane, vbuf, wbuf, dval, eval);
+        }
+        dval = (i == NC - 1) ? A[0].x : dval;        // after NC-1 rotations column NC-1 sits in register 0
+        if (i < NC && k_ok) {
+            double* out = a.scratch + (size_t)kq * (2 * NC);
+            out[i] = dval; out[NC + i] = eval;
+        }
+        __syncwarp();
+    }
+}
+
+// one tridiagonal matrix per lane: transpose (d,e) through shared memory, QL, bitonic sort, coalesced store
+template <int NC, int P2>
+__global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* dbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * NC * DSTRIDE;
+    double* ebuf = dbuf + NC * DSTRIDE;
+    const long long n_batches = (a.nk + 31) / 32;
+    const long long gwarp = (long long)blockIdx.x * SMALL_WARPS + warp, nwarps = (long long)gridDim.x * SMALL_WARPS;
+    const int N = a.N;
+#pragma unroll 1
+    for (long long batch = gwarp; batch < n_batches; batch += nwarps) {
+        const long long kbase = batch * 32;
+        const int cnt = (int)min((long long)32, a.nk - kbase);
+#pragma unroll 4
+        for (int m = 0; m < 32; ++m) {
+            const double* src = a.scratch + (size_t)(kbase + min(m, cnt - 1)) * (2 * NC);
+            for (int t = lane; t < 2 * NC; t += 32) {
+                double v = src[t];
+                if (t < NC) dbuf[t * DSTRIDE + m] = v; else ebuf[(t - NC) * DSTRIDE + m] = v;
+            }
+        }
+        __syncwarp();
         if (tql_lane(dbuf + lane, ebuf + lane, N)) atomicAdd(a.fail, 1);
         double ev[P2];
 #pragma unroll
         for (int q = 0; q < P2; ++q) ev[q] = (q < N && q < NC) ? dbuf[q * DSTRIDE + lane] : __longlong_as_double(0x7ff0000000000000LL);
         bitonic_sort<P2>(ev);
-        if (kbase + lane < a.nk) {
+        if (lane < cnt) {
 #pragma unroll
             for (int q = 0; q < P2; ++q)
                 if (q < N) a.evals[(long long)q * a.ld + a.col0 + kbase + lane] = ev[q];
@@ -348,7 +452,7 @@ static bool build_tables(const sktb_model_desc* D, const std::vector<double>& T,
                          std::string* why) {
     const int n = D->n_orb, nb = D->n_bonds;
     if (n > 32) { *why = ""; return false; }
-    if (table_doubles(n, nb, 2 * n <= 32 ? 2 * n : n, 2 * n <= 32, true) * 8 > 110 * 1024) { *why = "dense bond tables exceed the shared-memory budget"; return false; }
+    if (table_doubles(n, nb, 2 * n <= 32 ? 2 * n : n, 2 * n <= 32, true) * 8 > 64 * 1024) { *why = "dense bond tables exceed the shared-memory budget"; return false; }
     std::vector<double> Lt((size_t)nb * n * n, 0.0), Dt((size_t)nb * n * n, 0.0), dense((size_t)n * n);
     for (int b = 0; b < nb; ++b) {
         std::fill(dense.begin(), dense.end(), 0.0);
@@ -379,42 +483,76 @@ static bool build_tables(const sktb_model_desc* D, const std::vector<double>& T,
     return true;
 }
 
+struct LaunchCtx {
+    SmallArgs a;               // a.nk / a.first / a.k describe the WHOLE request
+    double* evals; long long ld, col0;
+    int* fail;
+    double* scratch; size_t scratch_bytes;
+    cudaStream_t st;
+    std::string* info;
+};
+
 template <int NC, int L, bool SOC, bool GATE>
-static int launch_one(const SmallArgs& a, cudaStream_t st, std::string* info) {
+static int launch_one(const LaunchCtx& c) {
     constexpr int G = 32 / L;
-    const int n = a.t.n_orb, nb = a.t.n_bonds, N = a.N;
-    size_t smem = table_doubles(n, nb, N, SOC, GATE) * 8 + (size_t)SMALL_WARPS * ((size_t)64 + (size_t)G * nb + (size_t)NC * DSTRIDE) * 16;
-    auto kern = heev_small_kernel<NC, L, SOC, GATE>;
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        *info = "cudaFuncSetAttribute(smem=" + std::to_string(smem) + ") failed"; return -1;
+    constexpr int P2 = L;
+    const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
+    size_t smemA = table_doubles(n, nb, N, SOC, GATE) * 8 + (size_t)SMALL_WARPS * ((size_t)128 + (size_t)G * nb) * 16;
+    size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
+    auto kA = tridiag_small_kernel<NC, L, SOC, GATE>;
+    auto kB = tql_small_kernel<NC, P2>;
+    if (smemA > 48 * 1024 && cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA) != cudaSuccess) {
+        *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemA) + ") failed"; return -1;
     }
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SMALL_WARPS * 32, smem);
-    if (occ < 1) { *info = "kernel does not fit (smem=" + std::to_string(smem) + ")"; return -1; }
+    if (smemB > 48 * 1024 && cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) {
+        *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemB) + ") failed"; return -1;
+    }
+    int occA = 0, occB = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, kA, SMALL_WARPS * 32, smemA);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
+    if (occA < 1 || occB < 1) { *c.info = "small kernels do not fit (smem " + std::to_string(smemA) + "/" + std::to_string(smemB) + ")"; return -1; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long batches = (a.nk + 31) / 32;
-    long long want = (batches + SMALL_WARPS - 1) / SMALL_WARPS;
-    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)sms * occ));
-    kern<<<grid, SMALL_WARPS * 32, smem, st>>>(a);
-    if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
-    char buf[256];
-    snprintf(buf, sizeof buf, "heev_small<NC=%d,L=%d,soc=%d,gate=%d> N=%d grid=%u x %d thr, smem=%zuB, %d CTA/SM", NC, L, (int)SOC, (int)GATE, N, grid,
-             SMALL_WARPS * 32, smem, occ);
-    *info = buf;
-    return 1;
+    const long long per_k = 2LL * NC * 8;
+    const long long chunk = std::max<long long>(32, std::min<long long>(c.a.nk, (long long)(c.scratch_bytes / per_k) / 32 * 32));
+    int launches = 0;
+    unsigned gridA = 0, gridB = 0;
+    for (long long c0 = 0; c0 < c.a.nk; c0 += chunk) {
+        const long long cnt = std::min(chunk, c.a.nk - c0);
+        SmallArgs a = c.a;
+        a.k = c.a.k ? c.a.k + 3 * c0 : nullptr;
+        a.first = c.a.first + c0; a.nk = cnt; a.scratch = c.scratch;
+        a.flag_off = c.a.flag_off + c0;
+        long long wantA = (cnt + (long long)SMALL_WARPS * G - 1) / ((long long)SMALL_WARPS * G);
+        gridA = (unsigned)std::max<long long>(1, std::min<long long>(wantA, (long long)sms * occA));
+        kA<<<gridA, SMALL_WARPS * 32, smemA, c.st>>>(a);
+        TqlArgs t{c.scratch, cnt, N, c.evals, c.ld, c.col0 + c0, c.fail};
+        long long wantB = ((cnt + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS;
+        gridB = (unsigned)std::max<long long>(1, std::min<long long>(wantB, (long long)sms * occB));
+        kB<<<gridB, SMALL_WARPS * 32, smemB, c.st>>>(t);
+        launches += 2;
+        if (cudaGetLastError() != cudaSuccess) { *c.info = "launch failed"; return -1; }
+    }
+    char buf[320];
+    snprintf(buf, sizeof buf, "tridiag_small<NC=%d,L=%d,soc=%d,gate=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
+             NC, L, (int)SOC, (int)GATE, gridA, SMALL_WARPS * 32, smemA, occA, gridB, smemB, occB, N, chunk);
+    *c.info = buf;
+    return launches;
 }
 
 template <int NC, int L>
-static int launch_nc(const SmallArgs& a, bool gate, cudaStream_t st, std::string* info) {
-    if (a.soc) return gate ? launch_one<NC, L, true, true>(a, st, info) : launch_one<NC, L, true, false>(a, st, info);
-    return gate ? launch_one<NC, L, false, true>(a, st, info) : launch_one<NC, L, false, false>(a, st, info);
+static int launch_nc(const LaunchCtx& c, bool gate) {
+    if (c.a.soc) return gate ? launch_one<NC, L, true, true>(c) : launch_one<NC, L, true, false>(c);
+    return gate ? launch_one<NC, L, false, true>(c) : launch_one<NC, L, false, false>(c);
 }
 
-// returns number of kernels launched (1) or -1 on error (text in *info)
+inline int padded_nc(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 12 ? 12 : (N <= 16 ? 16 : (N <= 24 ? 24 : 32)))); }
+
+// returns number of kernels launched or -1 on error (text in *info).  scratch: >= 32 * 2*NC*8 bytes.
 int launch_solve(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N,
-                 double* evals, long long ld, long long col0, int* flags, int* fail, cudaStream_t st, std::string* info);
+                 double* evals, long long ld, long long col0, int* flags, long long flag_off, int* fail, double* scratch, size_t scratch_bytes,
+                 cudaStream_t st, std::string* info);
 
 }  // namespace small
 }  // namespace sktb

@@ -77,7 +77,7 @@ struct sktb_plan {
     double asym_bound = 0.0;
     small::SmallTables small_tab{};           // dense tables for the register-resident path
     bool small_ok = false;
-    struct WorkSet { Buf H, RT, K; };
+    struct WorkSet { Buf H, RT, K, S; };
     WorkSet ws[3];                            // [0],[1]: the two host-front-end streams; [2]: caller-stream API
     Buf wsE, wsVec, wsFlag, wsPart, wsMisc;
     int* d_any = nullptr;                     // device int: any Hermiticity-gate hit
@@ -297,7 +297,7 @@ extern "C" void sktb_plan_destroy(sktb_plan* p) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     for (void* d : p->owned) cudaFree(d);
-    for (auto& w : p->ws) { w.H.release(); w.RT.release(); w.K.release(); }
+    for (auto& w : p->ws) { w.H.release(); w.RT.release(); w.K.release(); w.S.release(); }
     for (Buf* b : {&p->wsE, &p->wsVec, &p->wsFlag, &p->wsPart, &p->wsMisc}) b->release();
     for (int s = 0; s < 2; ++s) {
         p->hK[s].release(); p->hE[s].release(); p->hV[s].release(); p->hF[s].release();
@@ -363,6 +363,13 @@ static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
 
 static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked workspaces
 
+// (d,e) scratch of the register-resident path: 2*NC doubles per k-point, at most 2M k-points per launch pair
+static size_t small_scratch_bytes(int N, long long nk) {
+    long long chunk = std::min<long long>(std::max<long long>(nk, 32), 1LL << 21);
+    chunk = (chunk + 31) / 32 * 32;
+    return (size_t)chunk * 2 * small::padded_nc(N) * 8;
+}
+
 // shared body of sktb_solve / sktb_solve_mesh.  k_d == NULL -> mesh.
 static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc,
                       double* evals_d, double* evecs_d, long long ld, long long k_off, int* flags_d, cudaStream_t st, bool timed,
@@ -377,7 +384,10 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
 
     const bool want_vecs = evecs_d != nullptr;
     if (!want_vecs && p->small_ok && small::supports(N)) {
-        int rc = small::launch_solve(p->small_tab, k_d, nk_mesh, first, nk, soc, N, evals_d, ld, k_off, flags_d, p->d_fail, st, &g_kinfo);
+        size_t sbytes = small_scratch_bytes(N, nk);
+        if (W.S.ensure(sbytes)) return fail("out of device memory (tridiagonal scratch %zu B)", sbytes);
+        int rc = small::launch_solve(p->small_tab, k_d, nk_mesh, first, nk, soc, N, evals_d, ld, k_off, flags_d, k_off, p->d_fail,
+                                     (double*)W.S.p, sbytes, st, &g_kinfo);
         if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
         g_launches += rc;
     } else {
@@ -616,8 +626,10 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
         long long cnt = std::min(chunk, (long long)k_count - c0);
         int* flags = gate ? (int*)p->wsFlag.p : nullptr;
         if (use_small) {
+            size_t sbytes = small_scratch_bytes(N, cnt);
+            if (p->ws[2].S.ensure(sbytes)) return fail("out of device memory (tridiagonal scratch)");
             int rc = small::launch_solve(p->small_tab, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, k_first + c0, cnt, soc, N, (double*)p->wsE.p, cnt, 0,
-                                         flags, p->d_fail, st, &g_kinfo);
+                                         flags, 0, p->d_fail, (double*)p->ws[2].S.p, sbytes, st, &g_kinfo);
             if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
         } else {
