@@ -65,6 +65,9 @@ struct TqlArgs {
 inline bool supports(int N) { return N >= 1 && N <= 32; }
 
 constexpr int SMALL_WARPS = 4;
+#ifndef SKTB_SMALL_SYNC
+#define SKTB_SMALL_SYNC 1
+#endif
 constexpr int DSTRIDE = 33;   // odd stride: conflict-free both for the transposing stores and the per-lane QL
 
 // ---------------------------------------------------------------------------------------------------------
@@ -178,16 +181,31 @@ SKTB_D double group_sum(double v) {
 // ---------------------------------------------------------------------------------------------------------
 template <int NC> struct PhaseSteps { static constexpr int value = NC >= 16 ? 8 : 4; };
 
-template <int W, int NC, int L>
-SKTB_D void hh_step(cplx (&B)[NC], const int j, const int i, const int g, const int lane, cplx* vbuf, cplx* wbuf, double& dval,
-                    double& eval) {
-    const cplx x = B[0];
-    const bool below = i > j + 1;
-    double xn = below ? fma(x.x, x.x, x.y * x.y) : 0.0;
-    xn = group_sum<L>(xn);
-    cplx alpha;
+// reduction inputs of a pivot column: xn = sum_{i > j+1} |A[i][j]|^2, alpha = A[j+1][j]
+template <int L>
+SKTB_D void pivot_reduce(const cplx x, const int j, const int i, double& xn, cplx& alpha) {
+    double t = (i > j + 1) ? fma(x.x, x.x, x.y * x.y) : 0.0;
+    xn = group_sum<L>(t);
     alpha.x = __shfl_sync(0xffffffffu, x.x, j + 1, L);
     alpha.y = __shfl_sync(0xffffffffu, x.y, j + 1, L);
+}
+
+// A[i][k] -= v_i conj(w_k) + w_i conj(v_k)
+SKTB_D void rank2(cplx& t, const cplx v, const cplx w, const cplx vk, const cplx wk) {
+    t.x = fma(-v.x, wk.x, t.x); t.x = fma(-v.y, wk.y, t.x);
+    t.y = fma(-v.y, wk.x, t.y); t.y = fma(v.x, wk.y, t.y);
+    t.x = fma(-w.x, vk.x, t.x); t.x = fma(-w.y, vk.y, t.x);
+    t.y = fma(-w.y, vk.x, t.y); t.y = fma(w.x, vk.y, t.y);
+}
+
+// Software-pipelined step: (xn, alpha) of the current pivot column arrive from the previous step; the next pivot
+// column (window register 1) is updated first and its shuffle reduction + the scalar Householder chain are issued
+// before the remaining W-2 column updates, which are independent of it and hide its latency.
+template <int W, int NC, int L>
+SKTB_D void hh_step(cplx (&B)[NC], const int j, const int i, const int g, const int lane, cplx* vbuf, cplx* wbuf, double& dval,
+                    double& eval, double& xn, cplx& alpha) {
+    const cplx x = B[0];
+    const bool below = i > j + 1;
     dval = (i == j) ? x.x : dval;
     // Householder generator (zlarfg): one rsqrt + one reciprocal
     double beta; cplx tau, scale;
@@ -226,32 +244,27 @@ SKTB_D void hh_step(cplx (&B)[NC], const int j, const int i, const int g, const 
     cfma(w, a2, v);
     wbuf[lane + g * L] = w;
     __syncwarp();
-#pragma unroll
-    for (int q = 1; q < W; ++q) {
-        cplx vk = vg[q], wk = wg[q];
-        cplx t = B[q];
-        // A[i][k] -= v_i conj(w_k) + w_i conj(v_k)
-        t.x = fma(-v.x, wk.x, t.x); t.x = fma(-v.y, wk.y, t.x);
-        t.y = fma(-v.y, wk.x, t.y); t.y = fma(v.x, wk.y, t.y);
-        t.x = fma(-w.x, vk.x, t.x); t.x = fma(-w.y, vk.y, t.x);
-        t.y = fma(-w.y, vk.x, t.y); t.y = fma(w.x, vk.y, t.y);
-        B[q] = t;
+    if (W > 1) {
+        rank2(B[1], v, w, vg[1], wg[1]);
+        pivot_reduce<L>(B[1], j + 1, i, xn, alpha);               // next step's reduction, overlapped with the rest
     }
+#pragma unroll
+    for (int q = 2; q < W; ++q) rank2(B[q], v, w, vg[q], wg[q]);
     __syncwarp();
 }
 
 template <int W, int S, int NC, int L>
 SKTB_D void hh_phases(cplx (&B)[NC], int& j, const int i, const int g, const int lane, cplx* vbuf, cplx* wbuf, double& dval,
-                      double& eval) {
+                      double& eval, double& xn, cplx& alpha) {
     constexpr int steps = (W <= S) ? W - 1 : S;
 #pragma unroll 1
     for (int s = 0; s < steps; ++s, ++j) {
-        hh_step<W, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval);
+        hh_step<W, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval, xn, alpha);
 #pragma unroll
         for (int q = 0; q + 1 < W; ++q) B[q] = B[q + 1];          // rotate: column j+1 -> register 0
         B[W - 1] = cmake(0.0, 0.0);
     }
-    if constexpr (W > S) hh_phases<W - S, S, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval);
+    if constexpr (W > S) hh_phases<W - S, S, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval, xn, alpha);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -290,15 +303,17 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_
     for (int t = lane; t < 128; t += 32) myw[t] = cmake(0.0, 0.0);      // v/w buffers incl. their zero tails
     __syncthreads();
 
-    const long long gwarp = (long long)blockIdx.x * SMALL_WARPS + warp, nwarps = (long long)gridDim.x * SMALL_WARPS;
     const bool row_ok = i < N;
     const int mu = SOC ? (i >> 1) : i;
     const int mu_c = (row_ok && mu < n) ? mu : 0;
     const int spin = i & 1;
 
 #pragma unroll 1
-    for (long long k0q = gwarp * G; k0q < a.nk; k0q += nwarps * G) {
-        long long kq = k0q + g;
+    for (long long kcta = (long long)blockIdx.x * SMALL_WARPS * G; kcta < a.nk; kcta += (long long)gridDim.x * SMALL_WARPS * G) {
+#if SKTB_SMALL_SYNC
+        __syncthreads();          // keep the CTA's warps on the same phase body: one instruction stream per CTA
+#endif
+        long long kq = kcta + warp * G + g;
         const bool k_ok = kq < a.nk;
         if (!k_ok) kq = a.nk - 1;
         double k0, k1, k2;
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_
             double re[NH], im[NH], gs[GATE ? NH : 1];
 #pragma unroll
             for (int nu = 0; nu < NH; ++nu) { re[nu] = 0.0; im[nu] = 0.0; if (GATE) gs[nu] = 0.0; }
-#pragma unroll 1
+#pragma unroll 2
             for (int b = 0; b < nb; ++b) {
                 const cplx ph = phs[b];
                 const double* Lb = sLt + (size_t)b * n * n + mu_c;
@@ -379,7 +394,9 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_
         double dval = 0.0, eval = 0.0;
         {
             int j = 0;
-            hh_phases<NC, PhaseSteps<NC>::value, NC, L>(A, j, i, g, lane, vbuf, wbuf, dval, eval);
+            double xn; cplx alpha;
+            pivot_reduce<L>(A[0], 0, i, xn, alpha);
+            hh_phases<NC, PhaseSteps<NC>::value, NC, L>(A, j, i, g, lane, vbuf, wbuf, dval, eval, xn, alpha);
         }
         dval = (i == NC - 1) ? A[0].x : dval;        // after NC-1 rotations column NC-1 sits in register 0
         if (i < NC && k_ok) {
