@@ -253,7 +253,8 @@ SKTB_D void hh_step(cplx (&B)[NC], const int j, const int i, const int g, const 
     __syncwarp();
 }
 
-template <int W, int S, int NC, int L>
+// phases W, W-S, ... down to (but not including) WEND; WEND = 0 runs the whole tridiagonalisation
+template <int W, int S, int NC, int L, int WEND = 0>
 SKTB_D void hh_phases(cplx (&B)[NC], int& j, const int i, const int g, const int lane, cplx* vbuf, cplx* wbuf, double& dval,
                       double& eval, double& xn, cplx& alpha) {
     constexpr int steps = (W <= S) ? W - 1 : S;
@@ -264,7 +265,108 @@ SKTB_D void hh_phases(cplx (&B)[NC], int& j, const int i, const int g, const int
         for (int q = 0; q + 1 < W; ++q) B[q] = B[q + 1];          // rotate: column j+1 -> register 0
         B[W - 1] = cmake(0.0, 0.0);
     }
-    if constexpr (W > S) hh_phases<W - S, S, NC, L>(B, j, i, g, lane, vbuf, wbuf, dval, eval, xn, alpha);
+    if constexpr (W > S && W - S > WEND) hh_phases<W - S, S, NC, L, WEND>(B, j, i, g, lane, vbuf, wbuf, dval, eval, xn, alpha);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NC: compile-time column count (>= N, multiple of 4); L: lanes per matrix (power of two >= NC);
+// SOC: kron(h, I2) + soc_mat assembly; GATE: evaluate the reference's Hermiticity gate per k.
+// ---------------------------------------------------------------------------------------------------------
+struct SmemView {
+    double *Lt, *Dt, *On, *Bv, *SA;
+    cplx *St, *warp_base;
+};
+
+template <bool SOC, bool GATE>
+SKTB_D SmemView carve_and_load(unsigned char* smem_raw, const SmallArgs& a) {
+    const int n = a.t.n_orb, nb = a.t.n_bonds, N = a.N, tid = threadIdx.x;
+    SmemView s;
+    s.Lt = reinterpret_cast<double*>(smem_raw);
+    s.Dt = s.Lt + (size_t)nb * n * n;
+    s.On = s.Dt + (GATE ? (size_t)nb * n * n : 0);
+    s.Bv = s.On + n;
+    s.SA = s.Bv + 3 * nb;
+    size_t off = (size_t)((s.SA + ((GATE && SOC) ? N * N : 0)) - s.Lt);
+    off = (off + 1) & ~(size_t)1;              // 16-byte align
+    s.St = reinterpret_cast<cplx*>(s.Lt + off);
+    s.warp_base = s.St + (SOC ? N * N : 0);
+    for (int t = tid; t < nb * n * n; t += blockDim.x) { s.Lt[t] = a.t.Lt[t]; if (GATE) s.Dt[t] = a.t.Dt[t]; }
+    for (int t = tid; t < n; t += blockDim.x) s.On[t] = a.t.onsite[t];
+    for (int t = tid; t < 3 * nb; t += blockDim.x) s.Bv[t] = a.t.bvec[t];
+    if (SOC) for (int t = tid; t < N * N; t += blockDim.x) { s.St[t] = a.t.St[t]; if (GATE) s.SA[t] = a.t.SAt[t]; }
+    return s;
+}
+
+// bond phases exp(2 pi i (k@rec).d) of one k-point, one sincos per lane of the group (calc_g arithmetic,
+// hamiltonian.py:280,311); lanes i, i+L, ... of the group fill phs[0..nb)
+template <int L>
+SKTB_D void bond_phases(const SmallArgs& a, const SmemView& s, long long kq, int i, cplx* phs) {
+    double k0, k1, k2;
+    if (a.k) { k0 = a.k[3 * kq]; k1 = a.k[3 * kq + 1]; k2 = a.k[3 * kq + 2]; }
+    else kmesh_point(a.first + kq, a.mesh0, a.mesh1, a.mesh2, k0, k1, k2);
+    double c0 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[0]), __dmul_rn(k1, a.t.rec[3])), __dmul_rn(k2, a.t.rec[6]));
+    double c1 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[1]), __dmul_rn(k1, a.t.rec[4])), __dmul_rn(k2, a.t.rec[7]));
+    double c2 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[2]), __dmul_rn(k1, a.t.rec[5])), __dmul_rn(k2, a.t.rec[8]));
+    for (int b = i; b < a.t.n_bonds; b += L) {
+        double dot = __dadd_rn(__dadd_rn(__dmul_rn(c0, s.Bv[3 * b]), __dmul_rn(c1, s.Bv[3 * b + 1])), __dmul_rn(c2, s.Bv[3 * b + 2]));
+        cplx ph;
+        sincos(__dmul_rn(6.283185307179586, dot), &ph.y, &ph.x);
+        phs[b] = ph;
+    }
+}
+
+// K1: row i of the mirrored-lower H(k), straight into registers (bond loop outside: NH independent FMA chains per
+// bond).  Returns max_k Re(H - H^dagger)[i][k] when GATE (else -1).
+template <int NC, bool SOC, bool GATE>
+SKTB_D double build_row(cplx (&A)[NC], const SmallArgs& a, const SmemView& s, const cplx* phs, const int i) {
+    constexpr int NH = SOC ? NC / 2 : NC;     // orbital columns built per row
+    const int n = a.t.n_orb, nb = a.t.n_bonds, N = a.N;
+    const bool row_ok = i < N;
+    const int mu = SOC ? (i >> 1) : i;
+    const int mu_c = (row_ok && mu < n) ? mu : 0;
+    const int spin = i & 1;
+    double gate_max = -1.0;
+    double re[NH], im[NH], gs[GATE ? NH : 1];
+#pragma unroll
+    for (int nu = 0; nu < NH; ++nu) { re[nu] = 0.0; im[nu] = 0.0; if (GATE) gs[nu] = 0.0; }
+#pragma unroll 2
+    for (int b = 0; b < nb; ++b) {
+        const cplx ph = phs[b];
+        const double* Lb = s.Lt + (size_t)b * n * n + mu_c;
+        const double* Db = s.Dt + (size_t)b * n * n + mu_c;
+#pragma unroll
+        for (int nu = 0; nu < NH; ++nu) {
+            if (nu < n) {
+                double t = Lb[nu * n];
+                re[nu] = fma(t, ph.x, re[nu]); im[nu] = fma(t, ph.y, im[nu]);
+                if (GATE) gs[nu] = fma(Db[nu * n], ph.x, gs[nu]);
+            }
+        }
+    }
+    const bool orb_ok = row_ok && mu < n;
+#pragma unroll
+    for (int nu = 0; nu < NH; ++nu) {
+        double r_ = orb_ok ? re[nu] : 0.0, i_ = orb_ok ? im[nu] : 0.0;
+        if (nu == mu) { r_ += orb_ok ? s.On[mu_c] : 0.0; i_ = 0.0; }
+        else if (nu > mu) i_ = -i_;
+        if (SOC) {
+            cplx s0 = cmake(0.0, 0.0), s1 = s0;
+            if (row_ok && 2 * nu < N) {
+                s0 = s.St[(size_t)(2 * nu) * N + i]; s1 = s.St[(size_t)(2 * nu + 1) * N + i];
+                if (GATE) {
+                    double gq = (orb_ok && nu < n) ? gs[nu] : 0.0;
+                    gate_max = fmax(gate_max, (spin == 0 ? gq : 0.0) + s.SA[(size_t)(2 * nu) * N + i]);
+                    gate_max = fmax(gate_max, (spin == 1 ? gq : 0.0) + s.SA[(size_t)(2 * nu + 1) * N + i]);
+                }
+            }
+            A[2 * nu] = cmake((spin == 0 ? r_ : 0.0) + s0.x, (spin == 0 ? i_ : 0.0) + s0.y);
+            A[2 * nu + 1] = cmake((spin == 1 ? r_ : 0.0) + s1.x, (spin == 1 ? i_ : 0.0) + s1.y);
+        } else {
+            if (GATE && orb_ok && nu < n) gate_max = fmax(gate_max, gs[nu]);
+            A[nu] = cmake(r_, i_);
+        }
+    }
+    return gate_max;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -274,39 +376,18 @@ SKTB_D void hh_phases(cplx (&B)[NC], int& j, const int i, const int g, const int
 template <int NC, int L, bool SOC, bool GATE>
 __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_small_kernel(SmallArgs a) {
     constexpr int G = 32 / L;                 // matrices side by side in a warp
-    constexpr int NH = SOC ? NC / 2 : NC;     // orbital columns built per row
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = a.t.n_orb, nb = a.t.n_bonds, N = a.N;
+    const int nb = a.t.n_bonds;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = lane & (L - 1), g = lane / L;
-
-    // ---- shared memory carve-up: CTA-wide tables, then per-warp scratch ---------------------------------
-    double* sLt = reinterpret_cast<double*>(smem_raw);
-    double* sDt = sLt + (size_t)nb * n * n;
-    double* sOn = sDt + (GATE ? (size_t)nb * n * n : 0);
-    double* sBv = sOn + n;
-    double* sSA = sBv + 3 * nb;
-    size_t off = (size_t)((sSA + ((GATE && SOC) ? N * N : 0)) - sLt);
-    off = (off + 1) & ~(size_t)1;              // 16-byte align
-    cplx* sSt = reinterpret_cast<cplx*>(sLt + off);
-    cplx* wbase = sSt + (SOC ? N * N : 0);
+    const SmemView s = carve_and_load<SOC, GATE>(smem_raw, a);
     const size_t per_warp_cplx = (size_t)2 * 64 + (size_t)G * nb;   // v,w (zero-padded) | phases
-    cplx* myw = wbase + per_warp_cplx * warp;
+    cplx* myw = s.warp_base + per_warp_cplx * warp;
     cplx* vbuf = myw;
     cplx* wbuf = myw + 64;
     cplx* phs = myw + 128 + (size_t)g * nb;
-
-    for (int t = tid; t < nb * n * n; t += blockDim.x) { sLt[t] = a.t.Lt[t]; if (GATE) sDt[t] = a.t.Dt[t]; }
-    for (int t = tid; t < n; t += blockDim.x) sOn[t] = a.t.onsite[t];
-    for (int t = tid; t < 3 * nb; t += blockDim.x) sBv[t] = a.t.bvec[t];
-    if (SOC) for (int t = tid; t < N * N; t += blockDim.x) { sSt[t] = a.t.St[t]; if (GATE) sSA[t] = a.t.SAt[t]; }
     for (int t = lane; t < 128; t += 32) myw[t] = cmake(0.0, 0.0);      // v/w buffers incl. their zero tails
     __syncthreads();
-
-    const bool row_ok = i < N;
-    const int mu = SOC ? (i >> 1) : i;
-    const int mu_c = (row_ok && mu < n) ? mu : 0;
-    const int spin = i & 1;
 
 #pragma unroll 1
     for (long long kcta = (long long)blockIdx.x * SMALL_WARPS * G; kcta < a.nk; kcta += (long long)gridDim.x * SMALL_WARPS * G) {
@@ -316,70 +397,10 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_
         long long kq = kcta + warp * G + g;
         const bool k_ok = kq < a.nk;
         if (!k_ok) kq = a.nk - 1;
-        double k0, k1, k2;
-        if (a.k) { k0 = a.k[3 * kq]; k1 = a.k[3 * kq + 1]; k2 = a.k[3 * kq + 2]; }
-        else kmesh_point(a.first + kq, a.mesh0, a.mesh1, a.mesh2, k0, k1, k2);
-
-        // ---- bond phases exp(2 pi i (k@rec).d), one sincos per lane (calc_g arithmetic, hamiltonian.py:280,311)
-        {
-            double c0 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[0]), __dmul_rn(k1, a.t.rec[3])), __dmul_rn(k2, a.t.rec[6]));
-            double c1 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[1]), __dmul_rn(k1, a.t.rec[4])), __dmul_rn(k2, a.t.rec[7]));
-            double c2 = __dadd_rn(__dadd_rn(__dmul_rn(k0, a.t.rec[2]), __dmul_rn(k1, a.t.rec[5])), __dmul_rn(k2, a.t.rec[8]));
-            for (int b = i; b < nb; b += L) {
-                double dot = __dadd_rn(__dadd_rn(__dmul_rn(c0, sBv[3 * b]), __dmul_rn(c1, sBv[3 * b + 1])), __dmul_rn(c2, sBv[3 * b + 2]));
-                cplx ph;
-                sincos(__dmul_rn(6.283185307179586, dot), &ph.y, &ph.x);
-                phs[b] = ph;
-            }
-        }
+        bond_phases<L>(a, s, kq, i, phs);
         __syncwarp();
-
-        // ---- K1: row i of the mirrored-lower H(k), straight into registers (bond loop outside: NH independent
-        //      FMA chains per bond) ----
         cplx A[NC];
-        double gate_max = -1.0;
-        {
-            double re[NH], im[NH], gs[GATE ? NH : 1];
-#pragma unroll
-            for (int nu = 0; nu < NH; ++nu) { re[nu] = 0.0; im[nu] = 0.0; if (GATE) gs[nu] = 0.0; }
-#pragma unroll 2
-            for (int b = 0; b < nb; ++b) {
-                const cplx ph = phs[b];
-                const double* Lb = sLt + (size_t)b * n * n + mu_c;
-                const double* Db = sDt + (size_t)b * n * n + mu_c;
-#pragma unroll
-                for (int nu = 0; nu < NH; ++nu) {
-                    if (nu < n) {
-                        double t = Lb[nu * n];
-                        re[nu] = fma(t, ph.x, re[nu]); im[nu] = fma(t, ph.y, im[nu]);
-                        if (GATE) gs[nu] = fma(Db[nu * n], ph.x, gs[nu]);
-                    }
-                }
-            }
-            const bool orb_ok = row_ok && mu < n;
-#pragma unroll
-            for (int nu = 0; nu < NH; ++nu) {
-                double r_ = orb_ok ? re[nu] : 0.0, i_ = orb_ok ? im[nu] : 0.0;
-                if (nu == mu) { r_ += orb_ok ? sOn[mu_c] : 0.0; i_ = 0.0; }
-                else if (nu > mu) i_ = -i_;
-                if (SOC) {
-                    cplx s0 = cmake(0.0, 0.0), s1 = s0;
-                    if (row_ok && 2 * nu < N) {
-                        s0 = sSt[(size_t)(2 * nu) * N + i]; s1 = sSt[(size_t)(2 * nu + 1) * N + i];
-                        if (GATE) {
-                            double gq = (orb_ok && nu < n) ? gs[nu] : 0.0;
-                            gate_max = fmax(gate_max, (spin == 0 ? gq : 0.0) + sSA[(size_t)(2 * nu) * N + i]);
-                            gate_max = fmax(gate_max, (spin == 1 ? gq : 0.0) + sSA[(size_t)(2 * nu + 1) * N + i]);
-                        }
-                    }
-                    A[2 * nu] = cmake((spin == 0 ? r_ : 0.0) + s0.x, (spin == 0 ? i_ : 0.0) + s0.y);
-                    A[2 * nu + 1] = cmake((spin == 1 ? r_ : 0.0) + s1.x, (spin == 1 ? i_ : 0.0) + s1.y);
-                } else {
-                    if (GATE && orb_ok && nu < n) gate_max = fmax(gate_max, gs[nu]);
-                    A[nu] = cmake(r_, i_);
-                }
-            }
-        }
+        const double gate_max = build_row<NC, SOC, GATE>(A, a, s, phs, i);
         if (a.flags) {
             int bad = 0;
             if (GATE) {
@@ -404,6 +425,91 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_
             out[i] = dval; out[NC + i] = eval;
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// N in (24, 32]: "folded" variant.  Rows retire as the reduction proceeds, so after 16 steps half of the lanes of
+// a row-per-lane warp are idle.  Each warp therefore runs the wide phases (window 32, 24: steps 0..15) of TWO
+// matrices one after the other, parks the two remaining 16x16 trailing blocks in shared memory (4 KB each) and
+// finishes both side by side as two 16-lane groups (window 16, 8).  Same arithmetic, ~14 % fewer issue slots.
+// ---------------------------------------------------------------------------------------------------------
+template <bool SOC, bool GATE>
+__global__ void __launch_bounds__(SMALL_WARPS * 32, 3) tridiag_fold32_kernel(SmallArgs a) {
+    constexpr int NC = 32, S = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nb = a.t.n_bonds;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SmemView s = carve_and_load<SOC, GATE>(smem_raw, a);
+    const size_t per_warp_cplx = (size_t)2 * 64 + (size_t)nb + (size_t)2 * 16 * 16;   // v,w | phases | parked blocks
+    cplx* myw = s.warp_base + per_warp_cplx * warp;
+    cplx* vbuf = myw;
+    cplx* wbuf = myw + 64;
+    cplx* phs = myw + 128;
+    cplx* park = myw + 128 + nb;                                        // [2][16 cols][16 rows]
+    for (int t = lane; t < 128; t += 32) myw[t] = cmake(0.0, 0.0);
+    __syncthreads();
+
+#pragma unroll 1
+    for (long long kcta = (long long)blockIdx.x * SMALL_WARPS * 2; kcta < a.nk; kcta += (long long)gridDim.x * SMALL_WARPS * 2) {
+#if SKTB_SMALL_SYNC
+        __syncthreads();
+#endif
+        const long long kpair = kcta + warp * 2;
+        // ---- wide phases of the two matrices, one after the other (32 lanes = 32 rows) ----
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            long long kq = kpair + h;
+            const bool k_ok = kq < a.nk;
+            if (!k_ok) kq = a.nk - 1;
+            bond_phases<32>(a, s, kq, lane, phs);
+            __syncwarp();
+            cplx A[NC];
+            const double gate_max = build_row<NC, SOC, GATE>(A, a, s, phs, lane);
+            if (a.flags) {
+                int bad = 0;
+                if (GATE) bad = __ballot_sync(0xffffffffu, gate_max > 1.0e-9) ? 1 : 0;
+                if (lane == 0 && k_ok) a.flags[a.flag_off + kq] = bad;
+            }
+            double dval = 0.0, eval = 0.0;
+            int j = 0;
+            double xn; cplx alpha;
+            pivot_reduce<32>(A[0], 0, lane, xn, alpha);
+            hh_phases<NC, S, NC, 32, 16>(A, j, lane, 0, lane, vbuf, wbuf, dval, eval, xn, alpha);     // steps 0..15
+            if (lane < 16 && k_ok) {
+                double* out = a.scratch + (size_t)kq * (2 * NC);
+                out[lane] = dval; out[NC + lane] = eval;
+            }
+            if (lane >= 16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) park[(h * 16 + q) * 16 + (lane - 16)] = A[q];
+            }
+            __syncwarp();
+        }
+        // ---- narrow phases of both trailing 16x16 blocks side by side (two 16-lane groups) ----
+        {
+            const int g = lane >> 4, r = lane & 15;
+            // v/w layout changes from one 32-lane group to two 16-lane groups: restore the zero tails
+            for (int t = lane; t < 64; t += 32) { vbuf[t] = cmake(0.0, 0.0); wbuf[t] = cmake(0.0, 0.0); }
+            __syncwarp();
+            cplx B[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) B[q] = park[(g * 16 + q) * 16 + r];
+            double dval = 0.0, eval = 0.0;
+            int j = 0;
+            double xn; cplx alpha;
+            pivot_reduce<16>(B[0], 0, r, xn, alpha);
+            hh_phases<16, S, 16, 16>(B, j, r, g, lane, vbuf, wbuf, dval, eval, xn, alpha);
+            dval = (r == 15) ? B[0].x : dval;
+            const long long kq = kpair + g;
+            if (kq < a.nk) {
+                double* out = a.scratch + (size_t)kq * (2 * NC);
+                out[16 + r] = dval; out[NC + 16 + r] = eval;
+            }
+            __syncwarp();
+            for (int t = lane; t < 64; t += 32) { vbuf[t] = cmake(0.0, 0.0); wbuf[t] = cmake(0.0, 0.0); }
+            __syncwarp();
+        }
     }
 }
 
@@ -511,12 +617,15 @@ struct LaunchCtx {
 
 template <int NC, int L, bool SOC, bool GATE>
 static int launch_one(const LaunchCtx& c) {
-    constexpr int G = 32 / L;
+    constexpr bool FOLD = (NC == 32);         // two matrices per warp in the trailing half (tridiag_fold32_kernel)
+    constexpr int G = FOLD ? 2 : 32 / L;      // k-points per warp per iteration
     constexpr int P2 = L;
     const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
-    size_t smemA = table_doubles(n, nb, N, SOC, GATE) * 8 + (size_t)SMALL_WARPS * ((size_t)128 + (size_t)G * nb) * 16;
+    const size_t per_warp = FOLD ? ((size_t)128 + nb + 512) : ((size_t)128 + (size_t)(32 / L) * nb);
+    size_t smemA = table_doubles(n, nb, N, SOC, GATE) * 8 + (size_t)SMALL_WARPS * per_warp * 16;
     size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
-    auto kA = tridiag_small_kernel<NC, L, SOC, GATE>;
+    void (*kA)(SmallArgs);
+    if constexpr (FOLD) kA = tridiag_fold32_kernel<SOC, GATE>; else kA = tridiag_small_kernel<NC, L, SOC, GATE>;
     auto kB = tql_small_kernel<NC, P2>;
     if (smemA > 48 * 1024 && cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemA) + ") failed"; return -1;
@@ -552,8 +661,8 @@ static int launch_one(const LaunchCtx& c) {
         if (cudaGetLastError() != cudaSuccess) { *c.info = "launch failed"; return -1; }
     }
     char buf[320];
-    snprintf(buf, sizeof buf, "tridiag_small<NC=%d,L=%d,soc=%d,gate=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
-             NC, L, (int)SOC, (int)GATE, gridA, SMALL_WARPS * 32, smemA, occA, gridB, smemB, occB, N, chunk);
+    snprintf(buf, sizeof buf, "%s<NC=%d,L=%d,soc=%d,gate=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
+             FOLD ? "tridiag_fold32" : "tridiag_small", NC, L, (int)SOC, (int)GATE, gridA, SMALL_WARPS * 32, smemA, occA, gridB, smemB, occB, N, chunk);
     *c.info = buf;
     return launches;
 }
