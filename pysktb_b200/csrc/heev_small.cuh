@@ -68,6 +68,9 @@ constexpr int SMALL_WARPS = 4;
 #ifndef SKTB_SMALL_SYNC
 #define SKTB_SMALL_SYNC 1
 #endif
+#ifndef SKTB_FOLD_S
+#define SKTB_FOLD_S 4
+#endif
 constexpr int DSTRIDE = 33;   // odd stride: conflict-free both for the transposing stores and the per-lane QL
 
 // ---------------------------------------------------------------------------------------------------------
@@ -92,76 +95,74 @@ SKTB_D void bitonic_sort(double (&a)[P2]) {
 }
 
 // implicit-shift QL, one matrix per lane, strided shared memory (stride DSTRIDE doubles), rsqrt rotations.
-// The deflation test of the next sweep is folded into the rotation loop (no separate rescan per sweep).
+// Flat state machine: every trip of the single loop is one QL sweep of the lane's current unreduced block
+// [l..m] (or a cheap bookkeeping step), so a warp's trip count is the MAX over lanes of the total number of
+// sweeps instead of the sum over eigenvalues of the per-eigenvalue maximum (lanes converge at different rates).
+// The deflation tests of the next sweep are folded into the rotation loop; rescans happen only at block ends.
+SKTB_D int tql_scan(const double* d, const double* e, int l, int n) {
+    const double eps = 2.220446049250313e-16;
+    int m = l;
+    double dm = fabs(d[m * DSTRIDE]);
+    for (; m < n - 1; ++m) {
+        double dn = fabs(d[(m + 1) * DSTRIDE]);
+        if (fabs(e[m * DSTRIDE]) <= eps * (dm + dn)) break;
+        dm = dn;
+    }
+    return m;
+}
+
 SKTB_D int tql_lane(double* d, double* e, int n) {
     const double eps = 2.220446049250313e-16;
 #define D_(i) d[(i) * DSTRIDE]
 #define E_(i) e[(i) * DSTRIDE]
     E_(n - 1) = 0.0;
-    int fail = 0;
-    for (int l = 0; l < n; ++l) {
-        int iter = 0;
-        // first small off-diagonal at or after l
-        int m = l;
-        {
-            double dm = fabs(D_(m));
-            for (; m < n - 1; ++m) {
-                double dn = fabs(D_(m + 1));
-                if (fabs(E_(m)) <= eps * (dm + dn)) break;
-                dm = dn;
-            }
+    int fail = 0, l = 0, iter = 0;
+    int m = tql_scan(d, e, 0, n);
+    while (true) {
+        if (m == l || iter > 80) {                    // d[l] converged (or given up): next eigenvalue
+            if (m != l) fail = 1;
+            ++l; iter = 0;
+            if (l >= n) break;
+            m = tql_scan(d, e, l, n);
+            continue;
         }
-        while (m != l) {
-            if (++iter > 80) { fail = 1; break; }
-            double el = E_(l), dl = D_(l);
-            double g = (D_(l + 1) - dl) / (2.0 * el);
-            double r = sqrt(fma(g, g, 1.0));
-            g = D_(m) - dl + el / (g + (g >= 0.0 ? r : -r));
-            double s = 1.0, c = 1.0, p = 0.0;
-            int i = m - 1;
-            bool under = false;
-            double di1 = D_(m);                       // original d[i+1]
-            double dnext = (m + 1 < n) ? fabs(D_(m + 1)) : 0.0;   // |d[i+2]| (final) for the folded deflation test
-            int m_new = m;
-            for (; i >= l; --i) {
-                double ei = E_(i), di = D_(i);
-                double f = s * ei, b = c * ei;
-                double h2 = fma(f, f, g * g);
-                if (h2 == 0.0) { E_(i + 1) = 0.0; D_(i + 1) = di1 - p; E_(m) = 0.0; under = true; break; }
-                double ir = rsqrt(h2);
-                r = h2 * ir;
-                s = f * ir; c = g * ir;
-                g = di1 - p;
-                double rr = fma(di - g, s, 2.0 * c * b);
-                p = s * rr;
-                double dnew = g + p;
-                D_(i + 1) = dnew;
-                if (i + 1 < m) {                       // e[i+1] couples i+1 and i+2 (both final now)
-                    E_(i + 1) = r;
-                    double an = fabs(dnew);
-                    if (r <= eps * (an + dnext)) m_new = i + 1;
-                    dnext = an;
-                } else {
-                    dnext = fabs(dnew);                // e[m] is reset to 0 below
-                }
-                g = fma(c, rr, -b);
-                di1 = di;
+        ++iter;
+        double el = E_(l), dl = D_(l);
+        double g = (D_(l + 1) - dl) / (2.0 * el);
+        double r = sqrt(fma(g, g, 1.0));
+        g = D_(m) - dl + el / (g + (g >= 0.0 ? r : -r));
+        double s = 1.0, c = 1.0, p = 0.0;
+        bool under = false;
+        double di1 = D_(m);                           // original d[i+1]
+        double dnext = 0.0;                           // |d[i+2]| after this sweep
+        int mb = m;                                   // smallest index in (l, m) whose new e is negligible
+        for (int i = m - 1; i >= l; --i) {
+            double ei = E_(i), di = D_(i);
+            double f = s * ei, b = c * ei;
+            double h2 = fma(f, f, g * g);
+            if (h2 == 0.0) { E_(i + 1) = 0.0; D_(i + 1) = di1 - p; E_(m) = 0.0; under = true; break; }
+            double ir = rsqrt(h2);
+            r = h2 * ir;
+            s = f * ir; c = g * ir;
+            g = di1 - p;
+            double rr = fma(di - g, s, 2.0 * c * b);
+            p = s * rr;
+            double dnew = g + p;
+            D_(i + 1) = dnew;
+            double an = fabs(dnew);
+            if (i + 1 < m) {                          // e[i+1] couples i+1 and i+2, both final now
+                E_(i + 1) = r;
+                if (r <= eps * (an + dnext)) mb = i + 1;
             }
-            if (under) {                              // rare: rescan
-                m = l;
-                double dm = fabs(D_(m));
-                for (; m < n - 1; ++m) {
-                    double dn = fabs(D_(m + 1));
-                    if (fabs(E_(m)) <= eps * (dm + dn)) break;
-                    dm = dn;
-                }
-                continue;
-            }
-            double dl_new = di1 - p;
-            D_(l) = dl_new; E_(l) = g; E_(m) = 0.0;
-            if (fabs(g) <= eps * (fabs(dl_new) + dnext)) m_new = l;
-            m = m_new;
+            dnext = an;
+            g = fma(c, rr, -b);
+            di1 = di;
         }
+        if (under) { m = tql_scan(d, e, l, n); continue; }
+        double dl_new = di1 - p;
+        D_(l) = dl_new; E_(l) = g; E_(m) = 0.0;
+        if (fabs(g) <= eps * (fabs(dl_new) + dnext)) { ++l; iter = 0; }   // front deflated: block becomes [l+1..mb]
+        m = mb;
     }
 #undef D_
 #undef E_
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, (NC >= 24 ? 3 : 4)) tridiag_
 // ---------------------------------------------------------------------------------------------------------
 template <bool SOC, bool GATE>
 __global__ void __launch_bounds__(SMALL_WARPS * 32, 3) tridiag_fold32_kernel(SmallArgs a) {
-    constexpr int NC = 32, S = 8;
+    constexpr int NC = 32, S = SKTB_FOLD_S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = a.t.n_bonds;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
