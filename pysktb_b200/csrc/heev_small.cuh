@@ -24,6 +24,7 @@
 //
 // FP64 CUDA cores only: the work is batched rank-2 updates on <=32x32 Hermitian matrices, not a GEMM.
 #pragma once
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -551,6 +552,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
     }
 }
 
+#include "heev_pair.cuh"
+
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
@@ -616,17 +619,133 @@ struct LaunchCtx {
     std::string* info;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// pair-layout path (24 < N <= 32, no gate): wide kernel -> tail kernel -> QL, chunked and pipelined over two
+// internal streams so that tail + QL of chunk c run beside the wide kernel of chunk c+1 on the same SMs.
+//   SKTB_PAIR_MODE = 0: one kernel does all 31 steps (no tail kernel), caller's stream
+//                    1: wide, tail, QL back to back on the caller's stream
+//                    2: pipelined (default)
+// ---------------------------------------------------------------------------------------------------------
+struct PairStreams {
+    cudaStream_t sA = nullptr, sB = nullptr;
+    cudaEvent_t evStart = nullptr, evWide[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evEndA = nullptr;
+};
+static PairStreams* pair_streams(int dev) {
+    static thread_local PairStreams tab[64];      // per host thread: calls on one plan are not re-entrant, plans on other threads get their own
+    PairStreams& p = tab[dev & 63];
+    if (!p.sA) {
+        if (cudaStreamCreateWithFlags(&p.sA, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&p.sB, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&p.evStart, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&p.evEndA, cudaEventDisableTiming);
+        for (int b = 0; b < 2; ++b) {
+            cudaEventCreateWithFlags(&p.evWide[b], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&p.evDone[b], cudaEventDisableTiming);
+        }
+    }
+    return &p;
+}
+
+constexpr size_t PAIR_BYTES_PER_K = 2 * 32 * 8 + 256 * 16;      // (d,e) + trailing 16x16 block
+
+template <bool SOC>
+static int launch_pair(const LaunchCtx& c) {
+    constexpr int NC = 32;
+    static const int mode = getenv("SKTB_PAIR_MODE") ? atoi(getenv("SKTB_PAIR_MODE")) : 2;
+    static const int pair_s = getenv("SKTB_PAIR_S") ? atoi(getenv("SKTB_PAIR_S")) : SKTB_PAIR_S;
+    const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
+    const size_t smemW = table_doubles(n, nb, N, SOC, false) * 8 + (size_t)PAIR_WARPS * (pair_buf_cplx<32>() + nb) * 16;
+    const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
+    const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
+    void (*kW)(SmallArgs, cplx*);
+    if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, true> : pair_wide32_kernel<SOC, 4, true>;
+    else kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, false> : pair_wide32_kernel<SOC, 4, false>;
+    void (*kT)(const cplx*, double*, long long) = pair_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
+    auto kB = tql_small_kernel<NC, 32>;
+    if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
+        *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
+    }
+    if (smemB > 48 * 1024 && cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) {
+        *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemB) + ") failed"; return -1;
+    }
+    int occW = 0, occT = 0, occB = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occW, kW, PAIR_WARPS * 32, smemW);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, kT, PAIR_WARPS * 32, smemT);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
+    if (occW < 1 || occT < 1 || occB < 1) { *c.info = "pair kernels do not fit (smem " + std::to_string(smemW) + ")"; return -1; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    PairStreams* ps = mode == 2 ? pair_streams(dev) : nullptr;
+    if (mode == 2 && !ps) { *c.info = "cannot create the pipeline streams"; return -1; }
+    const int nbuf = mode == 2 ? 2 : 1;
+    const long long chunk = std::max<long long>(32, std::min<long long>((c.a.nk + 31) / 32 * 32, (long long)(c.scratch_bytes / (nbuf * PAIR_BYTES_PER_K)) / 32 * 32));
+    unsigned char* base = reinterpret_cast<unsigned char*>(c.scratch);
+    cudaStream_t sW = mode == 2 ? ps->sA : c.st, sT = mode == 2 ? ps->sB : c.st;
+    if (mode == 2) {
+        cudaEventRecord(ps->evStart, c.st);
+        cudaStreamWaitEvent(ps->sA, ps->evStart, 0);
+        cudaStreamWaitEvent(ps->sB, ps->evStart, 0);
+    }
+    int launches = 0;
+    unsigned gridW = 0, gridT = 0, gridB = 0;
+    long long ci = 0;
+    for (long long c0 = 0; c0 < c.a.nk; c0 += chunk, ++ci) {
+        const int b = (int)(ci % nbuf);
+        const long long cnt = std::min(chunk, c.a.nk - c0);
+        double* de = reinterpret_cast<double*>(base + (size_t)b * chunk * PAIR_BYTES_PER_K);
+        cplx* blocks = reinterpret_cast<cplx*>(base + (size_t)b * chunk * PAIR_BYTES_PER_K + (size_t)chunk * 2 * NC * 8);
+        SmallArgs a = c.a;
+        a.k = c.a.k ? c.a.k + 3 * c0 : nullptr;
+        a.first = c.a.first + c0; a.nk = cnt; a.scratch = de;
+        a.flag_off = c.a.flag_off + c0;
+        if (mode == 2 && ci >= nbuf) cudaStreamWaitEvent(sW, ps->evDone[b], 0);       // buffer b is free again
+        gridW = (unsigned)std::max<long long>(1, std::min<long long>((cnt + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * occW));
+        kW<<<gridW, PAIR_WARPS * 32, smemW, sW>>>(a, blocks);
+        ++launches;
+        if (mode == 2) { cudaEventRecord(ps->evWide[b], sW); cudaStreamWaitEvent(sT, ps->evWide[b], 0); }
+        if (mode != 0) {
+            gridT = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
+            kT<<<gridT, PAIR_WARPS * 32, smemT, sT>>>(blocks, de, cnt);
+            ++launches;
+        }
+        TqlArgs t{de, cnt, N, c.evals, c.ld, c.col0 + c0, c.fail};
+        gridB = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * occB));
+        kB<<<gridB, SMALL_WARPS * 32, smemB, sT>>>(t);
+        ++launches;
+        if (mode == 2) cudaEventRecord(ps->evDone[b], sT);
+        if (cudaGetLastError() != cudaSuccess) { *c.info = "launch failed"; return -1; }
+    }
+    if (mode == 2) {
+        cudaEventRecord(ps->evEndA, ps->sA);
+        cudaStreamWaitEvent(c.st, ps->evEndA, 0);
+        cudaStreamWaitEvent(c.st, ps->evDone[(int)((ci - 1) % nbuf)], 0);
+        if (ci >= 2) cudaStreamWaitEvent(c.st, ps->evDone[(int)(ci % nbuf)], 0);
+    }
+    char buf[400];
+    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,S=%d,mode=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + pair_tail16 grid=%u smem=%zuB + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
+             (int)SOC, pair_s, mode, gridW, PAIR_WARPS * 32, smemW, occW, gridT, smemT, gridB, smemB, occB, N, chunk);
+    *c.info = buf;
+    return launches;
+}
+
 template <int NC, int L, bool SOC, bool GATE>
 static int launch_one(const LaunchCtx& c) {
     constexpr bool FOLD = (NC == 32);         // two matrices per warp in the trailing half (tridiag_fold32_kernel)
+    if constexpr (NC == 32 && !GATE) {        // pair layout (heev_pair.cuh); SKTB_NO_PAIR=1 falls back to fold32 (A/B runs)
+        static const bool no_pair = getenv("SKTB_NO_PAIR") != nullptr && getenv("SKTB_NO_PAIR")[0] == '1';
+        if (!no_pair) return launch_pair<SOC>(c);
+    }
     constexpr int G = FOLD ? 2 : 32 / L;      // k-points per warp per iteration
     constexpr int P2 = L;
     const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
     const size_t per_warp = FOLD ? ((size_t)128 + nb + 512) : ((size_t)128 + (size_t)(32 / L) * nb);
-    size_t smemA = table_doubles(n, nb, N, SOC, GATE) * 8 + (size_t)SMALL_WARPS * per_warp * 16;
+    const int warpsA = SMALL_WARPS;
+    size_t smemA = table_doubles(n, nb, N, SOC, GATE) * 8 + (size_t)warpsA * per_warp * 16;
     size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
     void (*kA)(SmallArgs);
-    if constexpr (FOLD) kA = tridiag_fold32_kernel<SOC, GATE>; else kA = tridiag_small_kernel<NC, L, SOC, GATE>;
+    if constexpr (FOLD) kA = tridiag_fold32_kernel<SOC, GATE>;
+    else kA = tridiag_small_kernel<NC, L, SOC, GATE>;
     auto kB = tql_small_kernel<NC, P2>;
     if (smemA > 48 * 1024 && cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemA) + ") failed"; return -1;
@@ -635,7 +754,7 @@ static int launch_one(const LaunchCtx& c) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemB) + ") failed"; return -1;
     }
     int occA = 0, occB = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, kA, SMALL_WARPS * 32, smemA);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, kA, warpsA * 32, smemA);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
     if (occA < 1 || occB < 1) { *c.info = "small kernels do not fit (smem " + std::to_string(smemA) + "/" + std::to_string(smemB) + ")"; return -1; }
     int dev = 0, sms = 148;
@@ -651,9 +770,9 @@ static int launch_one(const LaunchCtx& c) {
         a.k = c.a.k ? c.a.k + 3 * c0 : nullptr;
         a.first = c.a.first + c0; a.nk = cnt; a.scratch = c.scratch;
         a.flag_off = c.a.flag_off + c0;
-        long long wantA = (cnt + (long long)SMALL_WARPS * G - 1) / ((long long)SMALL_WARPS * G);
+        long long wantA = (cnt + (long long)warpsA * G - 1) / ((long long)warpsA * G);
         gridA = (unsigned)std::max<long long>(1, std::min<long long>(wantA, (long long)sms * occA));
-        kA<<<gridA, SMALL_WARPS * 32, smemA, c.st>>>(a);
+        kA<<<gridA, warpsA * 32, smemA, c.st>>>(a);
         TqlArgs t{c.scratch, cnt, N, c.evals, c.ld, c.col0 + c0, c.fail};
         long long wantB = ((cnt + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS;
         gridB = (unsigned)std::max<long long>(1, std::min<long long>(wantB, (long long)sms * occB));
@@ -663,7 +782,7 @@ static int launch_one(const LaunchCtx& c) {
     }
     char buf[320];
     snprintf(buf, sizeof buf, "%s<NC=%d,L=%d,soc=%d,gate=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
-             FOLD ? "tridiag_fold32" : "tridiag_small", NC, L, (int)SOC, (int)GATE, gridA, SMALL_WARPS * 32, smemA, occA, gridB, smemB, occB, N, chunk);
+             FOLD ? "tridiag_fold32" : "tridiag_small", NC, L, (int)SOC, (int)GATE, gridA, warpsA * 32, smemA, occA, gridB, smemB, occB, N, chunk);
     *c.info = buf;
     return launches;
 }

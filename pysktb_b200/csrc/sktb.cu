@@ -363,8 +363,14 @@ static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
 
 static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked workspaces
 
-// (d,e) scratch of the register-resident path: 2*NC doubles per k-point, at most 2M k-points per launch pair
+// (d,e) scratch of the register-resident path: 2*NC doubles per k-point, at most 2M k-points per launch pair.
+// The pair-layout pipeline (24 < N <= 32) keeps two chunks in flight and parks a 4 KB trailing block per k-point.
 static size_t small_scratch_bytes(int N, long long nk) {
+    if (small::padded_nc(N) == 32) {
+        long long chunk = std::min<long long>(std::max<long long>(nk, 32), 1LL << 18);
+        chunk = (chunk + 31) / 32 * 32;
+        return (size_t)chunk * 2 * small::PAIR_BYTES_PER_K;
+    }
     long long chunk = std::min<long long>(std::max<long long>(nk, 32), 1LL << 21);
     chunk = (chunk + 31) / 32 * 32;
     return (size_t)chunk * 2 * small::padded_nc(N) * 8;

@@ -77,6 +77,15 @@ def ce_spdf_1atom():
                 bond_cut={"CeCe": {"NN": a * 1.1}}, params=_ce_params(), soc=True)
 
 
+def ce_partial(n_orb=14):
+    """T with only the first n_orb orbitals of the canonical list (N = 2 n_orb = 26, 28, 30): exercises the
+    zero-padded rows/columns of the 32-wide register kernels.  Not a reference example."""
+    spec = ce_spdf_1atom()
+    spec["name"] = f"ce_partial_{n_orb}"
+    spec["atoms"] = [("Ce", [0, 0, 0], list(SPDF[:n_orb]))]
+    return spec
+
+
 def ce_spdf_2atom():
     """C4 - two Ce-like atoms (bcc-like), 16 bonds. N=64."""
     a = 5.0
@@ -160,7 +169,7 @@ def d_soc_nonhermitian():
                 soc=True)
 
 
-ALL = {f.__name__: f for f in (cubic_sp3, graphene_pz, sb_buckled, ce_spdf_1atom, ce_spdf_2atom, ce_spf_example,
+ALL = {f.__name__: f for f in (cubic_sp3, graphene_pz, sb_buckled, ce_spdf_1atom, ce_partial, ce_spdf_2atom, ce_spf_example,
                                zigzag_ribbon, sp_chain, lowsym_spd, d_soc_nonhermitian)}
 
 

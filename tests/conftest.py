@@ -38,8 +38,15 @@ GOLDEN_SPECS = {
     "d_soc_nonherm": ("d_soc_nonhermitian", {}),
 }
 
+# oracle-only cases (no fixture file): padded / non-SOC variants of the 32-wide register kernels
+ORACLE_ONLY_SPECS = {
+    "ce_partial_13": ("ce_partial", {"n_orb": 13}), "ce_partial_14": ("ce_partial", {"n_orb": 14}),
+    "ce_partial_15": ("ce_partial", {"n_orb": 15}), "zigzag_13": ("zigzag_ribbon", {"n_chains": 13}),
+    "zigzag_14": ("zigzag_ribbon", {"n_chains": 14}), "zigzag_16": ("zigzag_ribbon", {"n_chains": 16}),
+}
+
 
 def spec_for(golden_name):
     from pysktb_b200 import workloads as W
-    fn, kw = GOLDEN_SPECS[golden_name]
+    fn, kw = GOLDEN_SPECS[golden_name] if golden_name in GOLDEN_SPECS else ORACLE_ONLY_SPECS[golden_name]
     return W.ALL[fn](**kw)
