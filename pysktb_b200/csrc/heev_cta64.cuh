@@ -1,0 +1,253 @@
+// K2a for 32 < N <= 64 (config C4: two spdf atoms with SOC): CTA-resident Householder tridiagonalisation, eigenvalues
+// only.  The pair layout of heev_pair.cuh generalised to four column classes: one matrix per CTA of 128 threads,
+//
+//   thread t = r + 32 h,  r in [0,32): slot A = row r, slot B = row 63 - r;  h = warp = column class
+//   register window  B[slot][m]  holds column  base + 4 m + h  (base = 4 floor(j/4)) of the mirrored-lower matrix
+//
+// so the 64 x 64 complex matrix (64 KB) lives in 128 x 128 registers, every warp owns ALL row pairs (norm and
+// dot-product reductions stay inside a warp) and a quarter of the columns (the mat-vec partial sums of the four
+// warps meet in shared memory).  One code body per phase serves the four sub-steps of a register cycle: the
+// register that holds the next pivot column / the unit entry of the next reflector is chosen by a warp-uniform
+// select between registers 0 and 1, and the window is rotated by one register every fourth step.  Three CTA
+// barriers per step (pivot column published | mat-vec partials | reflector published).  H(k) comes from K1
+// (hk_kernel, row-major c128 in the workspace; LAPACK UPLO='L' semantics are applied while loading), (d, e) go to
+// the scratch consumed by tql_small_kernel<64>.  FP64 CUDA cores; see heev_pair.cuh for the update formulas.
+// (included by heev_small.cuh inside namespace sktb::small)
+#pragma once
+
+constexpr int C64_THREADS = 128;
+constexpr int C64_SMEM_CPLX = 4 * 128 + 2 + 4 * 64 + 32 + 32;   // V | P | X | spare | alpha,pad | ypart[4][64] | D[64] | E[64]
+
+struct C64Smem {
+    cplx *V, *P, *X, *alpha, *yp;
+    double *D, *E;
+};
+SKTB_D C64Smem c64_smem(cplx* base) {
+    C64Smem s;
+    s.V = base; s.P = base + 128; s.X = base + 256; s.alpha = base + 512; s.yp = base + 514;
+    s.D = reinterpret_cast<double*>(base + 514 + 256); s.E = s.D + 64;
+    return s;
+}
+
+struct C64Lane {
+    int r, h, iA, iB;
+};
+
+SKTB_D double c64_wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// publish pivot column jn (owner class only): X masked to rows > jn+1, alpha = A[jn+1][jn], d[jn]
+template <int NS>
+SKTB_D void c64_publish(const cplx (&x)[2], const int jn, const bool owner, const C64Lane& L, const C64Smem& S) {
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) {
+        const int i = s ? L.iB : L.iA;
+        const cplx xv = (i > jn + 1) ? x[s] : cmake(0.0, 0.0);
+        if (owner) S.X[i] = xv;
+        if (owner && i == jn + 1) *S.alpha = x[s];
+        if (owner && i == jn) S.D[jn] = x[s].x;
+    }
+}
+
+// after barrier 1: own-row entries of the pivot column, its norm, the reflector scalars
+template <int NS>
+SKTB_D void c64_reflector(const C64Lane& L, const C64Smem& S, cplx (&xo)[2], double& beta, cplx& tau, cplx& scale) {
+    double xnp = 0.0;
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) {
+        xo[s] = S.X[s ? L.iB : L.iA];
+        xnp = fma(xo[s].x, xo[s].x, xnp); xnp = fma(xo[s].y, xo[s].y, xnp);
+    }
+    const cplx alpha = *S.alpha;
+    const double xn = c64_wsum(xnp);
+    pair_larfg(alpha, xn, beta, tau, scale);
+}
+
+// mat-vec partials -> (barrier 2) -> y, p, v, g -> publish v (warp 0), p (warp 1), e (warp 2) -> (barrier 3)
+template <int NS>
+SKTB_D void c64_finish(PairCarry& c, const cplx (&ypart)[2], const cplx (&xo)[2], const double beta, const cplx tau, const cplx scale,
+                       const int jn, const C64Lane& L, const C64Smem& S) {
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) S.yp[L.h * 64 + (s ? L.iB : L.iA)] = ypart[s];
+    __syncthreads();
+    c.tau2 = fma(tau.x, tau.x, tau.y * tau.y);
+    double g = 0.0;
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) {
+        const int i = s ? L.iB : L.iA;
+        const cplx y0 = S.yp[i], y1 = S.yp[64 + i], y2 = S.yp[128 + i], y3 = S.yp[192 + i];
+        cplx y = cmake((y0.x + y1.x) + (y2.x + y3.x), (y0.y + y1.y) + (y2.y + y3.y));
+        if (i <= jn) y = cmake(0.0, 0.0);
+        c.p[s] = cmul(tau, y);
+        c.v[s] = (i == jn + 1) ? cmake(1.0, 0.0) : cmul(xo[s], scale);
+        g = fma(y.x, c.v[s].x, g); g = fma(y.y, c.v[s].y, g);
+    }
+    c.g = g;
+    if (L.h < 2) {
+        cplx* dst = L.h ? S.P : S.V;
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) dst[s ? L.iB : L.iA] = L.h ? c.p[s] : c.v[s];
+    }
+    if (L.h == 2 && L.r == 0) S.E[jn] = beta;
+    __syncthreads();
+}
+
+// one Householder step j (runtime), HALF live registers per slot, NS live slots
+template <int HALF, int NS>
+SKTB_D void c64_step(cplx (&B)[2][16], PairCarry& c, const int j, const C64Lane& L, const C64Smem& S) {
+    const int base = j & ~3, jn = j + 1;
+    const cplx* Pl = S.P + base + L.h;
+    const cplx* Vl = S.V + base + L.h;
+    const cplx* Xl = S.X + base + L.h;
+    const double G = c64_wsum(c.g);
+    // ---- p-half of the update on the live window ----
+#pragma unroll
+    for (int m = 0; m < HALF; ++m) {
+        const cplx pq = Pl[4 * m];
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) pair_upd1(B[s][m], c.v[s], pq);
+    }
+    const double coef = -c.tau2 * G;
+    cplx wp[2], x[2];
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) wp[s] = cmake(fma(coef, c.v[s].x, c.p[s].x), fma(coef, c.v[s].y, c.p[s].y));
+    // ---- v-half on registers 0 and 1 (one of them holds the next pivot column), publish it ----
+    {
+        const cplx v0 = Vl[0], v1 = Vl[4];
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) { pair_upd1(B[s][0], wp[s], v0); pair_upd1(B[s][1], wp[s], v1); }
+    }
+    const bool me1 = (jn - base) >= 4;            // next pivot column sits in register 1 (class 0) after a full cycle
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) x[s] = me1 ? B[s][1] : B[s][0];
+    c64_publish<NS>(x, jn, L.h == (jn & 3), L, S);
+    __syncthreads();
+    cplx xo[2];
+    double beta; cplx tau, scale;
+    c64_reflector<NS>(L, S, xo, beta, tau, scale);
+    // ---- v-half on the remaining registers fused with the look-ahead mat-vec ----
+    cplx z[2];
+    {
+        const cplx x0 = Xl[0], x1 = Xl[4];        // masked: zero for columns <= jn + 1
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) {
+            z[s] = cmake(0.0, 0.0);
+            cfma(z[s], B[s][0], x0); cfma(z[s], B[s][1], x1);
+        }
+    }
+#pragma unroll
+    for (int m = 2; m < HALF; ++m) {
+        const cplx vq = Vl[4 * m];
+        const cplx xq = Xl[4 * m];
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) {
+            pair_upd1(B[s][m], wp[s], vq);
+            cfma(z[s], B[s][m], xq);
+        }
+    }
+    // column jn+1 (where v' = 1): class (jn+1)&3, register 0 or 1
+    const bool ma1 = (jn + 1 - base) >= 4;
+    const bool a_here = L.h == ((jn + 1) & 3);
+    cplx ypart[2];
+#pragma unroll
+    for (int s = 2 - NS; s < 2; ++s) {
+        const cplx acol = ma1 ? B[s][1] : B[s][0];
+        cplx yp = cmul(scale, z[s]);
+        yp.x += a_here ? acol.x : 0.0; yp.y += a_here ? acol.y : 0.0;
+        ypart[s] = yp;
+    }
+    c64_finish<NS>(c, ypart, xo, beta, tau, scale, jn, L, S);
+}
+
+template <int HALF>
+SKTB_D void c64_phases(cplx (&B)[2][16], PairCarry& c, int& j, const C64Lane& L, const C64Smem& S) {
+    constexpr int NS = HALF > 8 ? 2 : 1;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q, ++j)
+            if (j <= 62) c64_step<HALF, NS>(B, c, j, L, S);       // step 63 does not exist (warp-uniform guard)
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) {
+#pragma unroll
+            for (int m = 0; m + 1 < HALF; ++m) B[s][m] = B[s][m + 1];
+            B[s][HALF - 1] = cmake(0.0, 0.0);
+        }
+    }
+    if constexpr (HALF > 2) c64_phases<HALF - 2>(B, c, j, L, S);
+}
+
+struct C64Args {
+    const cplx* H;          // [nm][N][N] row-major (K1 output)
+    int N; long long nm;
+    double* scratch;        // [nm][2][64]  (d | e)
+};
+
+template <int UNUSED>
+__global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a) {
+    __shared__ __align__(16) cplx smem[C64_SMEM_CPLX];
+    const int t = threadIdx.x;
+    C64Lane L;
+    L.r = t & 31; L.h = t >> 5; L.iA = L.r; L.iB = 63 - L.r;
+    const C64Smem S = c64_smem(smem);
+    for (int q = t; q < C64_SMEM_CPLX; q += C64_THREADS) smem[q] = cmake(0.0, 0.0);
+    __syncthreads();
+    const int N = a.N;
+#pragma unroll 1
+    for (long long km = blockIdx.x; km < a.nm; km += gridDim.x) {
+        // ---- load rows iA, iB x columns 4m + h with zheevd(UPLO='L') semantics: upper triangle = conj(lower) ----
+        const cplx* H = a.H + (size_t)km * N * N;
+        cplx B[2][16];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int i = s ? L.iB : L.iA;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int col = 4 * m + L.h;
+                cplx e = cmake(0.0, 0.0);
+                if (i < N && col < N) {
+                    if (col < i) e = H[(size_t)i * N + col];
+                    else if (col > i) e = cconj(H[(size_t)col * N + i]);
+                    else e = cmake(H[(size_t)i * N + i].x, 0.0);
+                }
+                B[s][m] = e;
+            }
+        }
+        // ---- prologue: pivot column 0 (class 0, register 0), plain mat-vec ----
+        PairCarry c;
+        c.eval = 0.0;
+        {
+            cplx x[2] = {B[0][0], B[1][0]};
+            c64_publish<2>(x, 0, L.h == 0, L, S);
+            __syncthreads();
+            cplx xo[2];
+            double beta; cplx tau, scale;
+            c64_reflector<2>(L, S, xo, beta, tau, scale);
+            const cplx* Xl = S.X + L.h;
+            cplx ypart[2];
+            ypart[0] = ypart[1] = cmake(0.0, 0.0);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const cplx xq = Xl[4 * m];
+                cfma(ypart[0], B[0][m], xq); cfma(ypart[1], B[1][m], xq);
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                cplx yp = cmul(scale, ypart[s]);
+                yp.x += (L.h == 1) ? B[s][0].x : 0.0; yp.y += (L.h == 1) ? B[s][0].y : 0.0;     // column 1 = class 1, register 0
+                ypart[s] = yp;
+            }
+            c64_finish<2>(c, ypart, xo, beta, tau, scale, 0, L, S);
+        }
+        int j = 0;
+        c64_phases<16>(B, c, j, L, S);
+        if (t < 64) {
+            double* out = a.scratch + (size_t)km * 128;
+            out[t] = S.D[t]; out[64 + t] = S.E[t];
+        }
+        __syncthreads();
+    }
+}

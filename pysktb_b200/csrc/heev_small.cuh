@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
 }
 
 #include "heev_pair.cuh"
+#include "heev_cta64.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
@@ -794,6 +795,11 @@ static int launch_nc(const LaunchCtx& c, bool gate) {
 }
 
 inline int padded_nc(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 12 ? 12 : (N <= 16 ? 16 : (N <= 24 ? 24 : 32)))); }
+
+// 32 < N <= 64, eigenvalues only: H (K1 output, [nm][N][N]) -> tridiag_cta64_kernel -> tql_small_kernel<64>.
+// scratch: >= nm * 128 doubles.  Returns the number of kernels launched or -1 (text in *info).
+int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
+                 std::string* info);
 
 // returns number of kernels launched or -1 on error (text in *info).  scratch: >= 32 * 2*NC*8 bytes.
 int launch_solve(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N,

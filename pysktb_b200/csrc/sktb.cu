@@ -396,6 +396,22 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
                                      (double*)W.S.p, sbytes, st, &g_kinfo);
         if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
         g_launches += rc;
+    } else if (!want_vecs && N > 32 && N <= 64) {
+        // K1 materialises H(k) (64 KB per k at N = 64), tridiag_cta64_kernel keeps it in registers, QL per lane
+        size_t perH = (size_t)N * N * sizeof(cplx);
+        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));
+        if (W.H.ensure(perH * chunk) || W.S.ensure((size_t)chunk * 128 * 8)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
+        if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
+        for (long long c0 = 0; c0 < nk; c0 += chunk) {
+            long long cnt = std::min(chunk, nk - c0);
+            const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
+            if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
+            int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
+            if (rc) return rc;
+            rc = small::launch_cta64((const cplx*)W.H.p, N, cnt, (double*)W.S.p, evals_d, ld, k_off + c0, p->d_fail, st, &g_kinfo);
+            if (rc < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        }
     } else {
         size_t perH = (size_t)N * N * sizeof(cplx);
         long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));

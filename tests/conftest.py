@@ -43,6 +43,9 @@ ORACLE_ONLY_SPECS = {
     "ce_partial_13": ("ce_partial", {"n_orb": 13}), "ce_partial_14": ("ce_partial", {"n_orb": 14}),
     "ce_partial_15": ("ce_partial", {"n_orb": 15}), "zigzag_13": ("zigzag_ribbon", {"n_chains": 13}),
     "zigzag_14": ("zigzag_ribbon", {"n_chains": 14}), "zigzag_16": ("zigzag_ribbon", {"n_chains": 16}),
+    # 32 < N <= 64: CTA-resident kernel, padded and full
+    "zigzag_17": ("zigzag_ribbon", {"n_chains": 17}), "zigzag_20": ("zigzag_ribbon", {"n_chains": 20}),
+    "zigzag_31": ("zigzag_ribbon", {"n_chains": 31}),
 }
 
 
