@@ -635,7 +635,8 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     }
     const bool gate = p->asym_bound > 0.5e-9;
     const bool use_small = n_rows == 0 && p->small_ok && small::supports(N);
-    size_t per_k = (size_t)N * 8 + (use_small ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4;
+    const bool use_cta64 = n_rows == 0 && !use_small && N > 32 && N <= 64;     // eigenvalues only, register-resident CTA kernel
+    size_t per_k = (size_t)N * 8 + (use_small ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? 1024 : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(WS_BUDGET / per_k)));
     const int LOR_GRID = 148 * 4;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
@@ -666,8 +667,15 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = n_rows; a.rows = d_rows;
                 a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * n_rows; a.vs_k = n_rows; a.vcol0 = 0;
             }
-            rc = launch_heev_generic(p, a, st);
-            if (rc) return rc;
+            if (use_cta64) {
+                if (p->ws[2].S.ensure((size_t)cnt * 128 * 8)) return fail("out of device memory (tridiagonal scratch)");
+                int rl = small::launch_cta64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo);
+                if (rl < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
+                g_launches += rl;
+            } else {
+                rc = launch_heev_generic(p, a, st);
+                if (rc) return rc;
+            }
         }
         if (gate) { any_flag_kernel<<<64, 256, 0, st>>>(flags, cnt, p->d_any); LAUNCHED(); }
         long long tiles = (cnt * N + SKTB_LOR_TILE - 1) / SKTB_LOR_TILE;

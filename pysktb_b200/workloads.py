@@ -39,6 +39,13 @@ def graphene_pz():
     )
 
 
+def cubic_s():
+    """One s orbital on a simple cubic lattice with the default SOC doubling (N = 2, soc_mat = 0): the second
+    case of the closed-form N = 2 kernel.  Not a reference example."""
+    return dict(name="cubic_s", lattice=np.eye(3).tolist(), a=3.0, atoms=[("X", [0, 0, 0], ["s"])], periodicity=None,
+                bond_cut={"XX": {"NN": 3.1}}, params={"X": {"e_s": 0.3}, "XX": {"V_sss": -0.7}}, soc=True)
+
+
 def sb_buckled(theta_deg=16.0):
     """C3 - buckled group-V p-orbitals + SOC (docs/source/examples/examples.ipynb cell 33). N=12."""
     th = np.deg2rad(theta_deg)
@@ -169,7 +176,7 @@ def d_soc_nonhermitian():
                 soc=True)
 
 
-ALL = {f.__name__: f for f in (cubic_sp3, graphene_pz, sb_buckled, ce_spdf_1atom, ce_partial, ce_spdf_2atom, ce_spf_example,
+ALL = {f.__name__: f for f in (cubic_sp3, cubic_s, graphene_pz, sb_buckled, ce_spdf_1atom, ce_partial, ce_spdf_2atom, ce_spf_example,
                                zigzag_ribbon, sp_chain, lowsym_spd, d_soc_nonhermitian)}
 
 

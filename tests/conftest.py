@@ -46,6 +46,7 @@ ORACLE_ONLY_SPECS = {
     # 32 < N <= 64: CTA-resident kernel, padded and full
     "zigzag_17": ("zigzag_ribbon", {"n_chains": 17}), "zigzag_20": ("zigzag_ribbon", {"n_chains": 20}),
     "zigzag_31": ("zigzag_ribbon", {"n_chains": 31}),
+    "cubic_s": ("cubic_s", {}),
 }
 
 

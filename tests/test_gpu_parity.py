@@ -195,7 +195,7 @@ def test_known_answers(tb):
                                      ("ce_partial_13", 37), ("ce_partial_14", 35), ("ce_partial_15", 33),
                                      ("zigzag_13", 34), ("zigzag_14", 36), ("zigzag_16", 67),
                                      ("zigzag_17", 9), ("zigzag_20", 150), ("zigzag_31", 21), ("C5_zigzag_32", 300),
-                                     ("C4_ce_spdf_2atom", 301), ("lowsym_spd", 149)])
+                                     ("C4_ce_spdf_2atom", 301), ("lowsym_spd", 149), ("cubic_s", 77)])
 def test_eigenvalues_vs_oracle_seeded(tb, name, nk):
     spec = spec_for(name)
     m = oracle_model(spec)
