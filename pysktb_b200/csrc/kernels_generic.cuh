@@ -307,8 +307,11 @@ __global__ void heev_generic_kernel(HeevArgs a) {
 // sums the per-CTA partials in a fixed order (deterministic, no atomics).
 // ---------------------------------------------------------------------------------------------------------
 #define SKTB_LOR_TILE 2048
-#define SKTB_LOR_EPT 4
-__global__ void lorentz_partial_kernel(const double* __restrict__ evals, long long ld, long long col0, long long count, int N,
+// EPT energies per thread, blockDim.x * EPT energies per pass (the host picks the smallest EPT that covers nE with
+// 128 threads).  Per Lorentzian: 1 DADD, 1 DFMA, hardware reciprocal seed + one Newton step (2 DFMA; relative
+// error ~6e-14, the DOS tolerance is 1e-8), 1 DFMA - no IEEE division, no branch.
+template <int EPT>
+__global__ void __launch_bounds__(128) lorentz_partial_kernel(const double* __restrict__ evals, long long ld, long long col0, long long count, int N,
                                        const cplx* __restrict__ vec, int n_rows, const int* __restrict__ grp_ptr,
                                        const int* __restrict__ grp_rows, int n_groups, const double* __restrict__ energies,
                                        int nE, int e_base, double eta, double* __restrict__ part) {
@@ -316,9 +319,9 @@ __global__ void lorentz_partial_kernel(const double* __restrict__ evals, long lo
     __shared__ double s_w[SKTB_LOR_TILE];
     const int g = blockIdx.y;
     const long long total = count * N;                  // flat (band, k) index: t = band*count + k
-    double E[SKTB_LOR_EPT], acc[SKTB_LOR_EPT];
+    double E[EPT], acc[EPT];
 #pragma unroll
-    for (int q = 0; q < SKTB_LOR_EPT; ++q) {
+    for (int q = 0; q < EPT; ++q) {
         int ei = e_base + threadIdx.x + q * blockDim.x;
         E[q] = ei < nE ? energies[ei] : 0.0;
         acc[q] = 0.0;
@@ -336,21 +339,26 @@ __global__ void lorentz_partial_kernel(const double* __restrict__ evals, long lo
                 const cplx* vv = vec + ((size_t)band * count + k) * n_rows;
                 for (int q = grp_ptr[g]; q < grp_ptr[g + 1]; ++q) { cplx u = vv[grp_rows[q]]; wgt = fma(u.x, u.x, wgt); wgt = fma(u.y, u.y, wgt); }
             }
-            s_w[t] = wgt;
+            s_w[t] = wgt * pref;
         }
         __syncthreads();
+#pragma unroll 4
         for (int t = 0; t < len; ++t) {
-            double ep = s_eps[t], wp = s_w[t] * pref;
+            const double ep = s_eps[t], wp = s_w[t];
 #pragma unroll
-            for (int q = 0; q < SKTB_LOR_EPT; ++q) {
-                double x = E[q] - ep;
-                acc[q] += wp / fma(x, x, eta2);
+            for (int q = 0; q < EPT; ++q) {
+                const double x = E[q] - ep;
+                const double den = fma(x, x, eta2);
+                double r;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+                r = fma(r, fma(-den, r, 1.0), r);
+                acc[q] = fma(wp, r, acc[q]);
             }
         }
     }
     const int ng = n_groups > 0 ? n_groups : 1;
 #pragma unroll
-    for (int q = 0; q < SKTB_LOR_EPT; ++q) {
+    for (int q = 0; q < EPT; ++q) {
         int ei = e_base + threadIdx.x + q * blockDim.x;
         if (ei < nE) part[((size_t)blockIdx.x * ng + g) * nE + ei] = acc[q];
     }

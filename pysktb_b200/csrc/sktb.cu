@@ -680,9 +680,11 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
         if (gate) { any_flag_kernel<<<64, 256, 0, st>>>(flags, cnt, p->d_any); LAUNCHED(); }
         long long tiles = (cnt * N + SKTB_LOR_TILE - 1) / SKTB_LOR_TILE;
         int gx = (int)std::min<long long>(tiles, LOR_GRID);
-        for (int e_base = 0; e_base < nE; e_base += 256 * SKTB_LOR_EPT) {
-            lorentz_partial_kernel<<<dim3(gx, ng), 256, 0, st>>>((const double*)p->wsE.p, cnt, 0, cnt, N, (const cplx*)p->wsVec.p, n_rows, d_gptr,
-                                                                 d_grows, n_groups, energies_d, nE, e_base, eta, (double*)p->wsPart.p);
+        const int ept = nE <= 128 ? 1 : (nE <= 256 ? 2 : 4);
+        for (int e_base = 0; e_base < nE; e_base += 128 * ept) {
+            auto kl = ept == 1 ? lorentz_partial_kernel<1> : (ept == 2 ? lorentz_partial_kernel<2> : lorentz_partial_kernel<4>);
+            kl<<<dim3(gx, ng), 128, 0, st>>>((const double*)p->wsE.p, cnt, 0, cnt, N, (const cplx*)p->wsVec.p, n_rows, d_gptr, d_grows, n_groups,
+                                             energies_d, nE, e_base, eta, (double*)p->wsPart.p);
             LAUNCHED();
         }
         lorentz_reduce_kernel<<<(ng * nE + 127) / 128, 128, 0, st>>>((const double*)p->wsPart.p, gx, ng * nE, out_d, 1);
