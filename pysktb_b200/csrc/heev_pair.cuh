@@ -32,6 +32,7 @@
 #pragma once
 
 constexpr int PAIR_WARPS = 4;
+constexpr int PAIR_VSTORE_CPLX = 32 * 32 + 32;      // reflectors [j][i] + tau[j] per k-point (eigenvector path)
 #ifndef SKTB_PAIR_S
 #define SKTB_PAIR_S 4
 #endif
@@ -41,6 +42,9 @@ constexpr int PAIR_WARPS = 4;
 struct PairBuf {
     cplx *V0, *V1, *P, *X, *alpha;   // V double-buffered by step parity
     double* D;                       // [LN] diagonal
+    cplx* vst = nullptr;             // global [32][32] reflector store of this matrix (eigenvector path) or NULL
+    cplx* taust = nullptr;           // global [32] tau
+    int voff = 0;                    // row / reflector offset of this (sub)matrix inside the 32 x 32 store
 };
 template <int LN> __host__ __device__ constexpr int pair_buf_cplx() { return 8 * LN + 2 + LN / 2; }   // V0 | V1 | P | X | alpha, pad | D
 
@@ -164,6 +168,14 @@ SKTB_D void pair_finish(PairCarry& c, const cplx (&z)[2], const cplx (&acol)[2],
     cplx* dst = L.h ? S.P : Vnext;
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) dst[s ? L.iB : L.iA] = L.h ? c.p[s] : c.v[s];
+    if (S.vst && jn < LN - 1) {      // eigenvector path: keep reflector jn (rows of the live slots) and tau; the no-op
+                                     // step LN-1 at the end of the last phase must not write (it would land in tau[])
+        if (L.h == 0) {
+#pragma unroll
+            for (int s = 2 - NS; s < 2; ++s) S.vst[(size_t)(jn + S.voff) * 32 + S.voff + (s ? L.iB : L.iA)] = c.v[s];
+        }
+        if (L.l == 0) S.taust[jn + S.voff] = tau;
+    }
     __syncwarp();
 }
 
@@ -366,7 +378,7 @@ SKTB_D void pair_build(cplx (&B)[2][16], const SmallArgs& a, const SmemView& s, 
 // scratch and the trailing 16x16 block (updated through step 15, column-major [q][i], 4 KB) into `blocks`.
 // FULL: run all 31 steps here (no tail kernel).
 template <bool SOC, int S, bool FULL>
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks) {
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks, cplx* __restrict__ vstore) {
     constexpr int NC = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = a.t.n_bonds;
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
     cplx* phs = myw + pair_buf_cplx<32>();
     for (int t = lane; t < pair_buf_cplx<32>(); t += 32) myw[t] = cmake(0.0, 0.0);
     __syncthreads();
-    const PairBuf S_ = pair_buf<32>(myw);
+    PairBuf S_ = pair_buf<32>(myw);
     const PairLane L = pair_lane<32>(lane);
 
 #pragma unroll 1
@@ -388,6 +400,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         long long kq = kcta + warp;
         const bool k_ok = kq < a.nk;
         if (!k_ok) kq = a.nk - 1;
+        if (vstore) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
         bond_phases<32>(a, s, kq, lane, phs);
         __syncwarp();
         cplx B[2][16];

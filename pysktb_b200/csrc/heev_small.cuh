@@ -554,6 +554,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
 
 #include "heev_pair.cuh"
 #include "heev_cta64.cuh"
+#include "heev_vec32.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
@@ -658,7 +659,7 @@ static int launch_pair(const LaunchCtx& c) {
     const size_t smemW = table_doubles(n, nb, N, SOC, false) * 8 + (size_t)PAIR_WARPS * (pair_buf_cplx<32>() + nb) * 16;
     const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
-    void (*kW)(SmallArgs, cplx*);
+    void (*kW)(SmallArgs, cplx*, cplx*);
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, true> : pair_wide32_kernel<SOC, 4, true>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, false> : pair_wide32_kernel<SOC, 4, false>;
     void (*kT)(const cplx*, double*, long long) = pair_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
@@ -702,7 +703,7 @@ static int launch_pair(const LaunchCtx& c) {
         a.flag_off = c.a.flag_off + c0;
         if (mode == 2 && ci >= nbuf) cudaStreamWaitEvent(sW, ps->evDone[b], 0);       // buffer b is free again
         gridW = (unsigned)std::max<long long>(1, std::min<long long>((cnt + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * occW));
-        kW<<<gridW, PAIR_WARPS * 32, smemW, sW>>>(a, blocks);
+        kW<<<gridW, PAIR_WARPS * 32, smemW, sW>>>(a, blocks, nullptr);
         ++launches;
         if (mode == 2) { cudaEventRecord(ps->evWide[b], sW); cudaStreamWaitEvent(sT, ps->evWide[b], 0); }
         if (mode != 0) {
@@ -799,6 +800,14 @@ inline int padded_nc(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 12 ? 12 : 
 // 32 < N <= 64, eigenvalues only: H (K1 output, [nm][N][N]) -> tridiag_cta64_kernel -> tql_small_kernel<64>.
 // scratch: >= nm * 128 doubles.  Returns the number of kernels launched or -1 (text in *info).
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
+                 std::string* info);
+
+// N <= 32 with eigenvectors (no gate): pair-layout tridiagonalisation keeping the reflectors -> vec32_kernel
+// (QL with accumulation, sort, back-transformation).  evecs: [N][ld][N] complex (reference layout [band, k, comp]).
+// scratch: >= nk * vec32_bytes_per_k() bytes.  Returns the number of kernels launched or -1 (text in *info).
+size_t vec32_bytes_per_k();
+int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N, double* evals,
+                 cplx* evecs, long long ld, long long col0, int* flags, long long flag_off, int* fail, void* scratch, cudaStream_t st,
                  std::string* info);
 
 // returns number of kernels launched or -1 on error (text in *info).  scratch: >= 32 * 2*NC*8 bytes.

@@ -396,6 +396,18 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
                                      (double*)W.S.p, sbytes, st, &g_kinfo);
         if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
         g_launches += rc;
+    } else if (want_vecs && p->small_ok && small::supports(N) && !(p->asym_bound > 0.5e-9)) {
+        // N <= 32 with eigenvectors: pair-layout tridiagonalisation keeping the reflectors + vec32_kernel
+        const size_t per_k = small::vec32_bytes_per_k();
+        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
+        if (W.RT.ensure(per_k * chunk)) return fail("out of device memory (reflector workspace %zu B)", per_k * chunk);
+        for (long long c0 = 0; c0 < nk; c0 += chunk) {
+            long long cnt = std::min(chunk, nk - c0);
+            int rc = small::launch_vec32(p->small_tab, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, first + c0, cnt, soc, N, evals_d, (cplx*)evecs_d, ld,
+                                         k_off + c0, flags_d, k_off + c0, p->d_fail, W.RT.p, st, &g_kinfo);
+            if (rc < 0) return fail("vec32 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        }
     } else if (!want_vecs && N > 32 && N <= 64) {
         // K1 materialises H(k) (64 KB per k at N = 64), tridiag_cta64_kernel keeps it in registers, QL per lane
         size_t perH = (size_t)N * N * sizeof(cplx);
