@@ -629,7 +629,11 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     const int ng = n_groups > 0 ? n_groups : 1;
     std::vector<int> rows, grp_rows;
     if (tracked_rows(p, N, n_groups, grp_ptr, grp_idx, &rows, &grp_rows)) return 1;
-    const int n_rows = (int)rows.size();
+    int n_rows = (int)rows.size();
+    const bool gate = p->asym_bound > 0.5e-9;
+    // N <= 32 with projections: full eigenvectors from the register path (vec32), weights read by row index
+    const bool use_vec32 = n_rows > 0 && p->small_ok && small::supports(N) && !gate;
+    if (use_vec32) { grp_rows.assign(grp_idx, grp_idx + grp_ptr[n_groups]); n_rows = N; }
     CK(cudaMemsetAsync(out_d, 0, (size_t)ng * nE * 8, st));
     CK(cudaMemsetAsync(p->d_any, 0, sizeof(int), st));
     if (k_count <= 0) { if (nonherm_any_h) *nonherm_any_h = 0; return 0; }
@@ -645,22 +649,28 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
         CK(cudaMemcpyAsync(d_grows, grp_rows.data(), grp_rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));   // host vectors go out of scope at return; keep it simple
     }
-    const bool gate = p->asym_bound > 0.5e-9;
     const bool use_small = n_rows == 0 && p->small_ok && small::supports(N);
     const bool use_cta64 = n_rows == 0 && !use_small && N > 32 && N <= 64;     // eigenvalues only, register-resident CTA kernel
-    size_t per_k = (size_t)N * 8 + (use_small ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? 1024 : 0);
+    size_t per_k = (size_t)N * 8 + ((use_small || use_vec32) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? 1024 : 0) +
+                   (use_vec32 ? small::vec32_bytes_per_k() : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(WS_BUDGET / per_k)));
     const int LOR_GRID = 148 * 4;
-    if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
-        (n_rows && (p->ws[2].RT.ensure((size_t)chunk * N * n_rows * 16) || p->wsVec.ensure((size_t)chunk * N * n_rows * 16))) ||
-        (!k_d && !use_small && p->ws[2].K.ensure((size_t)chunk * 24)) || (gate && p->wsFlag.ensure((size_t)chunk * 4)) ||
+    if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
+        (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k() : (size_t)chunk * N * n_rows * 16) ||
+                    p->wsVec.ensure((size_t)chunk * N * n_rows * 16))) ||
+        (!k_d && !use_small && !use_vec32 && p->ws[2].K.ensure((size_t)chunk * 24)) || (gate && p->wsFlag.ensure((size_t)chunk * 4)) ||
         p->wsPart.ensure((size_t)LOR_GRID * ng * nE * 8))
         return fail("out of device memory (dos workspaces)");
 
     for (long long c0 = 0; c0 < k_count; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)k_count - c0);
         int* flags = gate ? (int*)p->wsFlag.p : nullptr;
-        if (use_small) {
+        if (use_vec32) {
+            int rc = small::launch_vec32(p->small_tab, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, k_first + c0, cnt, soc, N, (double*)p->wsE.p,
+                                         (cplx*)p->wsVec.p, cnt, 0, flags, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
+            if (rc < 0) return fail("vec32 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        } else if (use_small) {
             size_t sbytes = small_scratch_bytes(N, cnt);
             if (p->ws[2].S.ensure(sbytes)) return fail("out of device memory (tridiagonal scratch)");
             int rc = small::launch_solve(p->small_tab, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, k_first + c0, cnt, soc, N, (double*)p->wsE.p, cnt, 0,
