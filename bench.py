@@ -182,6 +182,8 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _, ham = W.instantiate(spec, tb, tb.scaling, device=local)
     lib = _lib.lib()
@@ -275,12 +277,21 @@ def main():
     peak, pms = _lib.C.c_double(), _lib.C.c_double()
     _lib.check(lib.sktb_fp64_peak(local, _lib.C.byref(peak), _lib.C.byref(pms)))
     achieved = flops_per_k(N) * per_gpu_k / (kern_ms * 1e-3) / 1e12
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of the same launch shape
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tfile):
+        tj = json.load(open(tfile))
+        for key, rec in tj.items():
+            if key in ham.last_kernel_info() and rec.get("matrix_size") == N:
+                traffic = {"bytes_per_launch": rec["dram_bytes_per_launch"], "k_points_per_launch": rec["k_points_per_launch"],
+                           "kernel": key, "source": rec["source"]}
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
     hbm_ach = per_gpu_k * 8.0 * N / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "fp64", "kernel": ham.last_kernel_info(), "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value, "peak_source": "DFMA microbenchmark measured live on this device (MEASURED_PEAKS.json has no FP64 entry)",
-                "flops_per_unit": flops_per_k(N), "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms, "traffic": None,
+                "flops_per_unit": flops_per_k(N), "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms, "traffic": traffic,
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": 8 * N,
                         "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_file) else "fallback 6.65 TB/s"}}
     cpu = None
