@@ -33,7 +33,7 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     return 2;
 }
 
-size_t vec32_bytes_per_k() { return (size_t)64 * 8 + (size_t)PAIR_VSTORE_CPLX * 16; }
+size_t vec32_bytes_per_k() { return (size_t)64 * 8 + (size_t)PAIR_VSTORE_CPLX * 16 + 1024 * 8 + 32 * 4; }   // (d,e) | reflectors | Z | ranks
 
 int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N, double* evals,
                  cplx* evecs, long long ld, long long col0, int* flags, long long flag_off, int* fail, void* scratch, cudaStream_t st,
@@ -47,28 +47,33 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     a.scratch = reinterpret_cast<double*>(scratch); a.flags = flags; a.flag_off = flag_off;
     cplx* vstore = reinterpret_cast<cplx*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)nk * 64 * 8);
     const size_t smemW = table_doubles(n, nb, N, soc != 0, false) * 8 + (size_t)PAIR_WARPS * (pair_buf_cplx<32>() + nb) * 16;
-    const size_t smemV = (size_t)VEC32_WARPS * VEC32_SMEM_DOUBLES * 8;
+    const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
+    double* zstore = reinterpret_cast<double*>(vstore + (size_t)nk * PAIR_VSTORE_CPLX);
+    int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nk * 1024);
     void (*kW)(SmallArgs, cplx*, cplx*) = soc ? pair_wide32_kernel<true, 4, true> : pair_wide32_kernel<false, 4, true>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
     }
-    int dev = 0, sms = 148, occW = 0, occV = 0;
+    int dev = 0, sms = 148, occW = 0, occQ = 0, occV = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occW, kW, PAIR_WARPS * 32, smemW);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occV, vec32_kernel<0>, VEC32_WARPS * 32, smemV);
-    if (occW < 1 || occV < 1) { *info = "vec32 kernels do not fit (smem " + std::to_string(smemW) + ")"; return -1; }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, vecql32_kernel<0>, VECQL_WARPS * 32, smemQ);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occV, vecbt32_kernel<0>, VEC32_WARPS * 32, 0);
+    if (occW < 1 || occQ < 1 || occV < 1) { *info = "vec32 kernels do not fit (smem " + std::to_string(smemW) + ")"; return -1; }
     const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nk + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * occW));
     kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, nullptr, vstore);
     Vec32Args v{a.scratch, vstore, nk, N, evals, evecs, ld, col0, fail};
+    const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nk + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * occQ));
+    vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore);
     const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>((nk + VEC32_WARPS - 1) / VEC32_WARPS, (long long)sms * occV));
-    vec32_kernel<0><<<gridV, VEC32_WARPS * 32, smemV, st>>>(v);
+    vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, 0, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
-    char buf[256];
-    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,full,vec> grid=%u x %d thr smem=%zuB %d CTA/SM + vec32 grid=%u smem=%zuB %d CTA/SM; N=%d", soc, gridW,
-             PAIR_WARPS * 32, smemW, occW, gridV, smemV, occV, N);
+    char buf[320];
+    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,full,vec> grid=%u x %d thr smem=%zuB %d CTA/SM + vecql32 grid=%u smem=%zuB %d CTA/SM + vecbt32 grid=%u %d CTA/SM; N=%d",
+             soc, gridW, PAIR_WARPS * 32, smemW, occW, gridQ, smemQ, occQ, gridV, occV, N);
     *info = buf;
-    return 2;
+    return 3;
 }
 
 }  // namespace small

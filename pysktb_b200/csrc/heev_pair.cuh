@@ -377,9 +377,10 @@ SKTB_D void pair_build(cplx (&B)[2][16], const SmallArgs& a, const SmemView& s, 
 // WIDE kernel: K0 + K1 + steps 0..15 of the 32x32 tridiagonalisation.  Writes d[0..16], e[0..16] into the (d,e)
 // scratch and the trailing 16x16 block (updated through step 15, column-major [q][i], 4 KB) into `blocks`.
 // FULL: run all 31 steps here (no tail kernel).
-template <bool SOC, int S, bool FULL>
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks, cplx* __restrict__ vstore) {
+template <bool SOC, int S, bool FULL, int WW = PAIR_WARPS>
+__global__ void __launch_bounds__(WW * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks, cplx* __restrict__ vstore) {
     constexpr int NC = 32;
+    constexpr int PAIR_WARPS = WW;        // warps of this CTA (3: leaves registers for a co-resident tail / QL CTA)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = a.t.n_bonds;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

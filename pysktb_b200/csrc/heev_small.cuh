@@ -656,13 +656,17 @@ static int launch_pair(const LaunchCtx& c) {
     static const int mode = getenv("SKTB_PAIR_MODE") ? atoi(getenv("SKTB_PAIR_MODE")) : 2;
     static const int pair_s = getenv("SKTB_PAIR_S") ? atoi(getenv("SKTB_PAIR_S")) : SKTB_PAIR_S;
     const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
-    const size_t smemW = table_doubles(n, nb, N, SOC, false) * 8 + (size_t)PAIR_WARPS * (pair_buf_cplx<32>() + nb) * 16;
+    static const int wide_warps = getenv("SKTB_WIDE_WARPS") ? atoi(getenv("SKTB_WIDE_WARPS")) : PAIR_WARPS;
+    static const int tail_s = getenv("SKTB_TAIL_S") ? atoi(getenv("SKTB_TAIL_S")) : pair_s;
+    const int WWr = (wide_warps == 3 && mode != 0) ? 3 : PAIR_WARPS;
+    const size_t smemW = table_doubles(n, nb, N, SOC, false) * 8 + (size_t)WWr * (pair_buf_cplx<32>() + nb) * 16;
     const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
     void (*kW)(SmallArgs, cplx*, cplx*);
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, true> : pair_wide32_kernel<SOC, 4, true>;
+    else if (WWr == 3) kW = pair_wide32_kernel<SOC, 4, false, 3>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, false> : pair_wide32_kernel<SOC, 4, false>;
-    void (*kT)(const cplx*, double*, long long) = pair_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
+    void (*kT)(const cplx*, double*, long long) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
     auto kB = tql_small_kernel<NC, 32>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
@@ -671,7 +675,7 @@ static int launch_pair(const LaunchCtx& c) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemB) + ") failed"; return -1;
     }
     int occW = 0, occT = 0, occB = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occW, kW, PAIR_WARPS * 32, smemW);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occW, kW, WWr * 32, smemW);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, kT, PAIR_WARPS * 32, smemT);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
     if (occW < 1 || occT < 1 || occB < 1) { *c.info = "pair kernels do not fit (smem " + std::to_string(smemW) + ")"; return -1; }
@@ -702,8 +706,8 @@ static int launch_pair(const LaunchCtx& c) {
         a.first = c.a.first + c0; a.nk = cnt; a.scratch = de;
         a.flag_off = c.a.flag_off + c0;
         if (mode == 2 && ci >= nbuf) cudaStreamWaitEvent(sW, ps->evDone[b], 0);       // buffer b is free again
-        gridW = (unsigned)std::max<long long>(1, std::min<long long>((cnt + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * occW));
-        kW<<<gridW, PAIR_WARPS * 32, smemW, sW>>>(a, blocks, nullptr);
+        gridW = (unsigned)std::max<long long>(1, std::min<long long>((cnt + WWr - 1) / WWr, (long long)sms * std::min(occW, 2)));
+        kW<<<gridW, WWr * 32, smemW, sW>>>(a, blocks, nullptr);
         ++launches;
         if (mode == 2) { cudaEventRecord(ps->evWide[b], sW); cudaStreamWaitEvent(sT, ps->evWide[b], 0); }
         if (mode != 0) {
@@ -726,7 +730,7 @@ static int launch_pair(const LaunchCtx& c) {
     }
     char buf[400];
     snprintf(buf, sizeof buf, "pair_wide32<soc=%d,S=%d,mode=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + pair_tail16 grid=%u smem=%zuB + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
-             (int)SOC, pair_s, mode, gridW, PAIR_WARPS * 32, smemW, occW, gridT, smemT, gridB, smemB, occB, N, chunk);
+             (int)SOC, pair_s, mode, gridW, WWr * 32, smemW, occW, gridT, smemT, gridB, smemB, occB, N, chunk);
     *c.info = buf;
     return launches;
 }

@@ -1,4 +1,4 @@
-// K2b for N <= 32 with eigenvectors: one warp per matrix.
+// K2b for N <= 32 with eigenvectors: one warp per matrix, two kernels (QL with accumulation | back-transformation).
 //   in : (d, e) and the Householder reflectors v_j, tau_j kept by the pair-layout tridiagonalisation (heev_pair.cuh)
 //   1. implicit-shift QL on the real tridiagonal with the rotations accumulated into Z (lane r owns row r of Z, Z in
 //      shared memory column-major with stride 33: both the rotation update (fixed column, lanes = rows) and the
@@ -56,8 +56,11 @@ __device__ __forceinline__ void vec32_all_phases(cplx (&u)[32], const cplx* vst,
     vec32_backtransform4<0>(u, vst, taust, N);
 }
 
+// ---- kernel 1: QL with accumulation, few registers -> many warps per SM (the scalar recurrence is latency bound).
+//      Writes the sorted eigenvalues and Z (column n = eigenvector n of T, [32][32] doubles, 8 KB per k) + ranks.
+constexpr int VECQL_WARPS = 4;
 template <int UNUSED>
-__global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vec32_kernel(Vec32Args a) {
+__global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecql32_kernel(Vec32Args a, double* __restrict__ zstore, int* __restrict__ rankstore) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Z = reinterpret_cast<double*>(smem_raw) + (size_t)warp * VEC32_SMEM_DOUBLES;
@@ -66,14 +69,12 @@ __global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vec32_kernel(Vec32Args a)
     const int n = a.N;
     const double eps = 2.220446049250313e-16;
 #pragma unroll 1
-    for (long long kq = (long long)blockIdx.x * VEC32_WARPS + warp; kq < a.nk; kq += (long long)gridDim.x * VEC32_WARPS) {
-        // ---- load (d, e), Z = I ----
+    for (long long kq = (long long)blockIdx.x * VECQL_WARPS + warp; kq < a.nk; kq += (long long)gridDim.x * VECQL_WARPS) {
         d[lane] = a.de[(size_t)kq * 64 + lane];
         e[lane] = (lane < n - 1) ? a.de[(size_t)kq * 64 + 32 + lane] : 0.0;
 #pragma unroll 4
         for (int c = 0; c < 32; ++c) Z[c * VEC32_ZSTRIDE + lane] = (c == lane) ? 1.0 : 0.0;
         __syncwarp();
-        // ---- QL with accumulation (EISPACK tql2 / LAPACK dsteqr recurrences; every lane runs the scalar part) ----
         int bad = 0;
 #pragma unroll 1
         for (int l = 0; l < n; ++l) {
@@ -93,23 +94,24 @@ __global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vec32_kernel(Vec32Args a)
                 double s = 1.0, c = 1.0, p = 0.0;
                 bool under = false;
                 __syncwarp();
+                double dnext = d[m];                   // d[i+1] before this sweep touches it
 #pragma unroll 1
                 for (int i = m - 1; i >= l; --i) {
-                    const double ei = e[i];
+                    const double ei = e[i], di = d[i];
+                    const double z1 = Z[(i + 1) * VEC32_ZSTRIDE + lane], z0 = Z[i * VEC32_ZSTRIDE + lane];
                     const double f = s * ei, b = c * ei;
                     const double h2 = fma(f, f, g * g);
-                    if (h2 == 0.0) { e[i + 1] = 0.0; d[i + 1] -= p; e[m] = 0.0; under = true; break; }
-                    const double ir = rsqrt(h2);
+                    if (h2 == 0.0) { e[i + 1] = 0.0; d[i + 1] = dnext - p; e[m] = 0.0; under = true; break; }
+                    const double ir = pair_rsqrt(h2);
                     r = h2 * ir;
                     e[i + 1] = r;
                     s = f * ir; c = g * ir;
-                    g = d[i + 1] - p;
-                    r = fma(d[i] - g, s, 2.0 * c * b);
+                    g = dnext - p;
+                    r = fma(di - g, s, 2.0 * c * b);
                     p = s * r;
                     d[i + 1] = g + p;
                     g = fma(c, r, -b);
-                    // rotation of columns i, i+1 of Z (this lane's row)
-                    const double z1 = Z[(i + 1) * VEC32_ZSTRIDE + lane], z0 = Z[i * VEC32_ZSTRIDE + lane];
+                    dnext = di;
                     Z[(i + 1) * VEC32_ZSTRIDE + lane] = fma(s, z0, c * z1);
                     Z[i * VEC32_ZSTRIDE + lane] = fma(c, z0, -s * z1);
                 }
@@ -121,27 +123,40 @@ __global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vec32_kernel(Vec32Args a)
         }
         __syncwarp();
         if (bad && lane == 0) atomicAdd(a.fail, 1);
-        // ---- rank of eigenvalue `lane` (ascending, ties by index) ----
         const double mine = (lane < n) ? d[lane] : 0.0;
         int rank = 0;
         for (int q = 0; q < n; ++q) {
             const double o = d[q];
             rank += (o < mine || (o == mine && q < lane)) ? 1 : 0;
         }
-        // ---- back-transformation: lane = eigenvector ----
+        if (lane < n) a.evals[(long long)rank * a.ld + a.col0 + kq] = mine;
+        rankstore[(size_t)kq * 32 + lane] = rank;
+        double* zs = zstore + (size_t)kq * 1024;
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) zs[c * 32 + lane] = Z[lane * VEC32_ZSTRIDE + c];     // zs[comp][vector]: coalesced both ways
+        __syncwarp();
+    }
+}
+
+// ---- kernel 2: back-transformation, lane = eigenvector (128 registers of components)
+template <int UNUSED>
+__global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vecbt32_kernel(Vec32Args a, const double* __restrict__ zstore, const int* __restrict__ rankstore) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = a.N;
+#pragma unroll 1
+    for (long long kq = (long long)blockIdx.x * VEC32_WARPS + warp; kq < a.nk; kq += (long long)gridDim.x * VEC32_WARPS) {
+        const double* zs = zstore + (size_t)kq * 1024;
         cplx u[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) u[i] = cmake((lane < n && i < n) ? Z[lane * VEC32_ZSTRIDE + i] : 0.0, 0.0);
+        for (int i = 0; i < 32; ++i) u[i] = cmake((lane < n && i < n) ? zs[i * 32 + lane] : 0.0, 0.0);
+        const int rank = rankstore[(size_t)kq * 32 + lane];
         const cplx* vst = a.vstore + (size_t)kq * PAIR_VSTORE_CPLX;
         vec32_all_phases(u, vst, vst + 1024, n);
         if (lane < n) {
-            const long long slot = (long long)rank * a.ld + a.col0 + kq;
-            a.evals[slot] = mine;
-            cplx* out = a.evecs + (size_t)slot * n;
+            cplx* out = a.evecs + (size_t)((long long)rank * a.ld + a.col0 + kq) * n;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 if (i < n) out[i] = u[i];
         }
-        __syncwarp();
     }
 }
