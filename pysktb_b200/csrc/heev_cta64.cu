@@ -33,6 +33,48 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     return 2;
 }
 
+int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
+                  cudaStream_t st, std::string* info) {
+    if (N < 1 || N > 32) { *info = "launch_heev32: N out of range"; return -1; }
+    SmallArgs a{};
+    a.k = nullptr; a.mesh0 = a.mesh1 = a.mesh2 = 1; a.first = 0; a.nk = nm; a.N = N; a.soc = 0;
+    a.scratch = reinterpret_cast<double*>(scratch); a.flags = nullptr; a.flag_off = 0; a.Hsrc = H;
+    cplx* vstore = reinterpret_cast<cplx*>(reinterpret_cast<unsigned char*>(scratch) + (size_t)nm * 64 * 8);
+    double* zstore = reinterpret_cast<double*>(vstore + (size_t)nm * PAIR_VSTORE_CPLX);
+    int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nm * 1024);
+    const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16;
+    const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
+    const size_t smemB = (size_t)SMALL_WARPS * 2 * 32 * DSTRIDE * 8;
+    auto kW = pair_wide32_kernel<PAIR_SRC_LOAD, 4, true>;
+    auto kB = tql_small_kernel<32, 32>;
+    if (cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) { *info = "cudaFuncSetAttribute failed"; return -1; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nm + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 2));
+    kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, nullptr, evecs ? vstore : nullptr);
+    int launches = 1;
+    if (evecs) {
+        Vec32Args v{a.scratch, vstore, nm, N, evals, evecs, ld, col0, fail};
+        const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nm + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * 5));
+        vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore);
+        const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>((nm + VEC32_WARPS - 1) / VEC32_WARPS, (long long)sms * 2));
+        vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, 0, st>>>(v, zstore, rankstore);
+        launches += 2;
+    } else {
+        TqlArgs t{a.scratch, nm, N, evals, ld, col0, fail};
+        const unsigned gridB = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * 3));
+        kB<<<gridB, SMALL_WARPS * 32, smemB, st>>>(t);
+        launches += 1;
+    }
+    if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
+    char buf[200];
+    snprintf(buf, sizeof buf, "pair_wide32<load,full%s> grid=%u x %d thr + %s; N=%d", evecs ? ",vec" : "", gridW, PAIR_WARPS * 32,
+             evecs ? "vecql32 + vecbt32" : "tql_small", N);
+    *info = buf;
+    return launches;
+}
+
 size_t vec32_bytes_per_k() { return (size_t)64 * 8 + (size_t)PAIR_VSTORE_CPLX * 16 + 1024 * 8 + 32 * 4; }   // (d,e) | reflectors | Z | ranks
 
 int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N, double* evals,
@@ -50,7 +92,7 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
     double* zstore = reinterpret_cast<double*>(vstore + (size_t)nk * PAIR_VSTORE_CPLX);
     int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nk * 1024);
-    void (*kW)(SmallArgs, cplx*, cplx*) = soc ? pair_wide32_kernel<true, 4, true> : pair_wide32_kernel<false, 4, true>;
+    void (*kW)(SmallArgs, cplx*, cplx*) = soc ? pair_wide32_kernel<PAIR_SRC_SOC, 4, true> : pair_wide32_kernel<PAIR_SRC_NOSOC, 4, true>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
     }

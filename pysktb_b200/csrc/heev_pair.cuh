@@ -377,14 +377,37 @@ SKTB_D void pair_build(cplx (&B)[2][16], const SmallArgs& a, const SmemView& s, 
 // WIDE kernel: K0 + K1 + steps 0..15 of the 32x32 tridiagonalisation.  Writes d[0..16], e[0..16] into the (d,e)
 // scratch and the trailing 16x16 block (updated through step 15, column-major [q][i], 4 KB) into `blocks`.
 // FULL: run all 31 steps here (no tail kernel).
-template <bool SOC, int S, bool FULL, int WW = PAIR_WARPS>
-__global__ void __launch_bounds__(WW * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks, cplx* __restrict__ vstore) {
+// rows iA, iB x columns 2m + h of a caller-supplied matrix, zheevd(UPLO='L') reading (upper triangle = conj(lower))
+SKTB_D void pair_load(cplx (&B)[2][16], const cplx* __restrict__ H, const int N, const PairLane& L) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = s ? L.iB : L.iA;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int col = 2 * m + L.h;
+            cplx e = cmake(0.0, 0.0);
+            if (i < N && col < N) {
+                if (col < i) e = H[(size_t)i * N + col];
+                else if (col > i) e = cconj(H[(size_t)col * N + i]);
+                else e = cmake(H[(size_t)i * N + i].x, 0.0);
+            }
+            B[s][m] = e;
+        }
+    }
+}
+
+constexpr int PAIR_SRC_NOSOC = 0, PAIR_SRC_SOC = 1, PAIR_SRC_LOAD = 2;
+
+template <int SRC, int S, bool FULL>
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks, cplx* __restrict__ vstore) {
     constexpr int NC = 32;
-    constexpr int PAIR_WARPS = WW;        // warps of this CTA (3: leaves registers for a co-resident tail / QL CTA)
+    constexpr bool SOC = SRC == PAIR_SRC_SOC, LOAD = SRC == PAIR_SRC_LOAD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nb = a.t.n_bonds;
+    const int nb = LOAD ? 0 : a.t.n_bonds;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SmemView s = carve_and_load<SOC, false>(smem_raw, a);
+    SmemView s{};
+    if (LOAD) s.warp_base = reinterpret_cast<cplx*>(smem_raw);
+    else s = carve_and_load<SOC, false>(smem_raw, a);
     const size_t per_warp_cplx = (size_t)pair_buf_cplx<32>() + (size_t)nb;
     cplx* myw = s.warp_base + per_warp_cplx * warp;
     cplx* phs = myw + pair_buf_cplx<32>();
@@ -402,10 +425,13 @@ __global__ void __launch_bounds__(WW * 32, 2) pair_wide32_kernel(SmallArgs a, cp
         const bool k_ok = kq < a.nk;
         if (!k_ok) kq = a.nk - 1;
         if (vstore) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
-        bond_phases<32>(a, s, kq, lane, phs);
-        __syncwarp();
         cplx B[2][16];
-        pair_build<SOC>(B, a, s, phs, L);
+        if (LOAD) pair_load(B, a.Hsrc + (size_t)kq * a.N * a.N, a.N, L);
+        else {
+            bond_phases<32>(a, s, kq, lane, phs);
+            __syncwarp();
+            pair_build<SOC>(B, a, s, phs, L);
+        }
         if (a.flags && lane == 0 && k_ok) a.flags[a.flag_off + kq] = 0;
         PairCarry c;
         pair_prologue<32>(B, c, L, S_);

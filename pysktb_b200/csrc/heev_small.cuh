@@ -55,6 +55,7 @@ struct SmallArgs {
     int N, soc;
     double* scratch;            // [nk][2][NC]  (d | e) of every matrix
     int* flags; long long flag_off;
+    const cplx* Hsrc = nullptr; // pair kernels in LOAD mode (sktb_heev): [nk][N][N] row-major matrices instead of K0+K1
 };
 
 struct TqlArgs {
@@ -656,16 +657,17 @@ static int launch_pair(const LaunchCtx& c) {
     static const int mode = getenv("SKTB_PAIR_MODE") ? atoi(getenv("SKTB_PAIR_MODE")) : 2;
     static const int pair_s = getenv("SKTB_PAIR_S") ? atoi(getenv("SKTB_PAIR_S")) : SKTB_PAIR_S;
     const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
-    static const int wide_warps = getenv("SKTB_WIDE_WARPS") ? atoi(getenv("SKTB_WIDE_WARPS")) : PAIR_WARPS;
-    static const int tail_s = getenv("SKTB_TAIL_S") ? atoi(getenv("SKTB_TAIL_S")) : pair_s;
-    const int WWr = (wide_warps == 3 && mode != 0) ? 3 : PAIR_WARPS;
+    // (3-warp wide CTAs that leave registers for a co-resident tail/QL CTA, and 3 CTAs x 3 warps, were measured:
+    //  2.6e7 / 2.8e7 k/s against 3.4e7 for 2 x 4 warps at 255 registers - not kept)
+    static const int tail_s = getenv("SKTB_TAIL_S") ? atoi(getenv("SKTB_TAIL_S")) : 8;
+    constexpr int WWr = PAIR_WARPS;
     const size_t smemW = table_doubles(n, nb, N, SOC, false) * 8 + (size_t)WWr * (pair_buf_cplx<32>() + nb) * 16;
     const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
     void (*kW)(SmallArgs, cplx*, cplx*);
-    if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, true> : pair_wide32_kernel<SOC, 4, true>;
-    else if (WWr == 3) kW = pair_wide32_kernel<SOC, 4, false, 3>;
-    else kW = pair_s == 8 ? pair_wide32_kernel<SOC, 8, false> : pair_wide32_kernel<SOC, 4, false>;
+    constexpr int SRC = SOC ? PAIR_SRC_SOC : PAIR_SRC_NOSOC;
+    if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, true> : pair_wide32_kernel<SRC, 4, true>;
+    else kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, false> : pair_wide32_kernel<SRC, 4, false>;
     void (*kT)(const cplx*, double*, long long) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
     auto kB = tql_small_kernel<NC, 32>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
@@ -706,7 +708,7 @@ static int launch_pair(const LaunchCtx& c) {
         a.first = c.a.first + c0; a.nk = cnt; a.scratch = de;
         a.flag_off = c.a.flag_off + c0;
         if (mode == 2 && ci >= nbuf) cudaStreamWaitEvent(sW, ps->evDone[b], 0);       // buffer b is free again
-        gridW = (unsigned)std::max<long long>(1, std::min<long long>((cnt + WWr - 1) / WWr, (long long)sms * std::min(occW, 2)));
+        gridW = (unsigned)std::max<long long>(1, std::min<long long>((cnt + WWr - 1) / WWr, (long long)sms * occW));
         kW<<<gridW, WWr * 32, smemW, sW>>>(a, blocks, nullptr);
         ++launches;
         if (mode == 2) { cudaEventRecord(ps->evWide[b], sW); cudaStreamWaitEvent(sT, ps->evWide[b], 0); }
@@ -809,6 +811,10 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
 // N <= 32 with eigenvectors (no gate): pair-layout tridiagonalisation keeping the reflectors -> vec32_kernel
 // (QL with accumulation, sort, back-transformation).  evecs: [N][ld][N] complex (reference layout [band, k, comp]).
 // scratch: >= nk * vec32_bytes_per_k() bytes.  Returns the number of kernels launched or -1 (text in *info).
+// sktb_heev for N <= 32: caller-supplied matrices H [nm][N][N] (lower triangle read, input not modified) through the
+// pair kernels in LOAD mode; evecs may be NULL.  scratch: >= nm * vec32_bytes_per_k() bytes.
+int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
+                  cudaStream_t st, std::string* info);
 size_t vec32_bytes_per_k();
 int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N, double* evals,
                  cplx* evecs, long long ld, long long col0, int* flags, long long flag_off, int* fail, void* scratch, cudaStream_t st,

@@ -517,12 +517,32 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
     CK(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     size_t perH = (size_t)N * N * sizeof(cplx);
-    long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / perH)));
-    if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(perH * chunk))) return fail("out of device memory (heev workspace)");
     if (nonherm_d) {
         herm_gate_kernel<<<(unsigned)std::min<long long>(nm, 148LL * 8), 128, 0, st>>>((const cplx*)H_d, N, nm, nonherm_d);
         LAUNCHED();
     }
+    static const bool heev_generic_only = getenv("SKTB_HEEV_GENERIC") != nullptr && getenv("SKTB_HEEV_GENERIC")[0] == '1';
+    if (N <= 32 && !heev_generic_only) {                  // register-resident pair kernels, input read in place
+        const size_t per_k = small::vec32_bytes_per_k();
+        long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / per_k)));
+        if (p->ws[2].RT.ensure(per_k * chunk)) return fail("out of device memory (heev workspace)");
+        for (long long c0 = 0; c0 < nm; c0 += chunk) {
+            long long cnt = std::min(chunk, (long long)nm - c0);
+            int rc = small::launch_heev32((const cplx*)H_d + (size_t)c0 * N * N, N, cnt, evals_d, (cplx*)evecs_d, nm, c0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
+            if (rc < 0) return fail("heev32 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        }
+        return 0;
+    }
+    if (N <= 64 && !evecs_d && !heev_generic_only) {      // CTA-resident kernel, eigenvalues only
+        if (p->ws[2].S.ensure((size_t)nm * 128 * 8)) return fail("out of device memory (heev workspace)");
+        int rc = small::launch_cta64((const cplx*)H_d, N, nm, (double*)p->ws[2].S.p, evals_d, nm, 0, p->d_fail, st, &g_kinfo);
+        if (rc < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
+        g_launches += rc;
+        return 0;
+    }
+    long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / perH)));
+    if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(perH * chunk))) return fail("out of device memory (heev workspace)");
     for (long long c0 = 0; c0 < nm; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)nm - c0);
         CK(cudaMemcpyAsync(p->ws[2].H.p, (const cplx*)H_d + (size_t)c0 * N * N, perH * cnt, cudaMemcpyDeviceToDevice, st));

@@ -264,12 +264,16 @@ def test_heev_random_hermitian_vs_lapack(tb, N):
     from pysktb_b200 import _lib
     _, ham = ham_for(tb, "C1_cubic_sp3")
     r = np.random.default_rng(N)
-    nm = 5
+    nm = 9
     M = r.standard_normal((nm, N, N)) + 1j * r.standard_normal((nm, N, N))          # NOT Hermitian on purpose
     if N >= 8:
         M[1] = np.kron(M[1][: N // 2 + N % 2, : N // 2 + N % 2], np.eye(2))[:N, :N]  # exact degeneracies
         M[2] = np.diag(r.standard_normal(N))                                         # already diagonal
         M[3][N // 2:, : N // 2] = 0                                                  # decoupled blocks
+    M[5] = 0.0                                                                       # zero matrix
+    M[6] *= 1e-7                                                                     # tiny scale
+    M[7] *= 3e4                                                                      # large scale
+    M[8] = np.where(r.random((N, N)) < 0.15, M[8], 0.0) + 2.0 * np.eye(N)            # sparse, many trivial reflectors
     Md = torch.from_numpy(np.ascontiguousarray(M)).cuda()
     ev = torch.empty((N, nm), dtype=torch.float64, device="cuda")
     vec = torch.empty((N, nm, N), dtype=torch.complex128, device="cuda")
