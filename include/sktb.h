@@ -118,6 +118,18 @@ int sktb_spectral(sktb_plan* plan, const double* k_d, int64_t nk, int32_t soc, c
                   double eta, int32_t n_idx, const int32_t* idx, double* out_d, int32_t* nonherm_any_h,
                   void* stream);
 
+/* Hamiltonian.get_dos (hamiltonian.py:233-253): Gaussian-broadened DOS of a set of eigenvalues,
+ *   out[e] = sum_i exp(-(E_e - eps_i)^2 / (2 w^2)) / (pi w sqrt(2))      (the reference's own prefactor),
+ * evals_d [n] device (any layout, flat), energies_d [nE], out_d [nE] overwritten.  Deterministic (fixed-order sums). */
+int sktb_gauss_dos(sktb_plan* plan, const double* evals_d, int64_t n, const double* energies_d, int32_t nE, double w,
+                   double* out_d, void* stream);
+
+/* Band energy of Forces.get_total_energy (forces.py:381-395): sum over the k-points of the n_occ lowest
+ * eigenvalues, evals_d [N][ld] ascending per k (the layout sktb_solve / sktb_solve_mesh write), columns
+ * [0, nk).  out_d: one double, UN-normalised (caller multiplies by weight = 1/n_kpts and the spin factor).   */
+int sktb_band_energy(sktb_plan* plan, const double* evals_d, int64_t ld, int64_t nk, int32_t n_occ, double* out_d,
+                     void* stream);
+
 /* Measurement helpers (bench.py): sustained FP64 FMA throughput of the device in TFLOP/s (DFMA microbenchmark,
  * `ms` = duration of the timed launch), and the last solve's kernel configuration as text.                   */
 int sktb_fp64_peak(int device, double* tflops, double* ms);

@@ -140,9 +140,44 @@ def kmesh_fixture(ref):
     print("kmesh ok")
 
 
+def next_rows_fixture(ref):
+    """Hamiltonian.get_dos (Gaussian) and Forces.get_total_energy of the real reference."""
+    from pysktb.forces import Forces
+    out = {}
+    E = np.linspace(-4.0, 4.0, 33)
+    for name, spec, nk, ne in (("C1", W.cubic_sp3(), [3, 3, 3], 4), ("C3", W.sb_buckled(), [4, 3, 1], 6),
+                               ("C2", W.graphene_pz(), [5, 4, 1], 2), ("spchain", W.sp_chain(), [6, 1, 1], 1)):
+        st, ham = W.instantiate(spec, ref, ref.scaling)
+        # solve_k -> solve_kpath(parallel=1) would spawn loky workers that cannot import the reference shell
+        # (ref_loader): run the identical serial branch (parallel=0, hamiltonian.py:186-209) instead
+        orig = ham.solve_kpath
+        ham.solve_kpath = lambda k_list=None, eig_vectors=False, soc=True, parallel=0, _o=orig: _o(k_list, eig_vectors, soc, 0)
+        if spec["soc"]:                                       # get_dos always solves with soc (solve_k default)
+            out[name + "_gdos"] = np.asarray(quiet(ham.get_dos, E, w=0.15, nk=nk))
+            out[name + "_gdos_nk"] = np.array(nk)
+        f = Forces(ham)
+        tot = quiet(f.get_total_energy, ne, nk=nk, soc=spec["soc"])
+        out[name + "_etot"] = np.array(tot, dtype=float)
+        out[name + "_etot_args"] = np.array([ne] + nk)
+    r = np.random.default_rng(7)
+    ev = r.standard_normal(57) * 2
+    D = 0
+    for i in ev:                                              # the reference's loop on caller-supplied eigenvalues
+        D = D + np.exp(-((E - i) ** 2) / (2 * 0.2 ** 2)) / (np.pi * 0.2 * np.sqrt(2))
+    out["eig_in"] = ev
+    out["eig_gdos"] = D
+    out["energy"] = E
+    np.savez_compressed(os.path.join(OUT, "next_rows.npz"), **out)
+    print("next_rows", {k: v.shape for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
+    if "--next-rows-only" in sys.argv:
+        next_rows_fixture(ref)
+        return
+    next_rows_fixture(ref)
     sk_fixture(ref)
     kmesh_fixture(ref)
     E = np.linspace

@@ -346,3 +346,32 @@ def lorentz_dos(evals, energies, eta):
     """evals [N, nk] -> dos [nE] (already divided by nk)."""
     E = np.asarray(energies)[:, None, None]
     return ((eta / np.pi) / ((E - evals[None]) ** 2 + eta * eta)).sum(axis=(1, 2)) / evals.shape[1]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rows: Hamiltonian.get_dos (Gaussian) and the band energy of Forces.get_total_energy
+# ---------------------------------------------------------------------------------------------------------
+def gauss_dos(evals, energy, w):
+    """hamiltonian.py:249-252: D(E) = sum_i exp(-(E - e_i)^2 / (2 w^2)) / (pi w sqrt(2))."""
+    e = np.asarray(evals, dtype=float).reshape(-1)
+    E = np.asarray(energy, dtype=float)
+    return np.exp(-((E[..., None] - e) ** 2) / (2 * w ** 2)).sum(axis=-1) / (np.pi * w * np.sqrt(2))
+
+
+def get_dos(model, energy, w=1e-2, nk=(20, 20, 20)):
+    """hamiltonian.py:233-253 with eig=None: endpoint-included linspace mesh, kx outer / kz inner, soc=True."""
+    kx, ky, kz = (np.linspace(0, 1, int(n)) for n in nk)
+    ks = [[i, j, k] for i in kx for j in ky for k in kz]
+    return gauss_dos(model.solve_kpath(ks, soc=True), energy, w)
+
+
+def total_energy_band(model, n_electrons, nk=(10, 10, 10), soc=True):
+    """forces.py:76-81, 381-395: mesh linspace(endpoint=False), sum of the lowest n_occ eigenvalues, weight 1/n_k,
+    factor 2 without soc."""
+    kx, ky, kz = (np.linspace(0, 1, int(n), endpoint=False) for n in nk)
+    ks = [[x, y, z] for x in kx for y in ky for z in kz]
+    ev = model.solve_kpath(ks, soc=soc)
+    n_occ = n_electrons if soc else n_electrons // 2
+    n_occ = min(n_occ, ev.shape[0])
+    return (1.0 if soc else 2.0) * ev[:n_occ].sum() / len(ks)
+

@@ -19,8 +19,9 @@ from .scaling import (ScalingLaw, Constant, Harrison, PowerLaw, Exponential, GSP
 from .hamiltonian import Hamiltonian
 from .greens import GreensFunction, SurfaceGreensFunction
 from . import dist
+from .forces import Forces
 
 __version__ = "0.1.0"
-__all__ = ["Structure", "Atom", "Lattice", "System", "Hamiltonian", "GreensFunction", "SurfaceGreensFunction",
+__all__ = ["Structure", "Atom", "Lattice", "System", "Hamiltonian", "GreensFunction", "SurfaceGreensFunction", "Forces",
            "ScalingLaw", "Constant", "Harrison", "PowerLaw", "Exponential", "GSP", "Polynomial", "Tabulated",
            "Custom", "ensure_scaling", "dist"]

@@ -364,6 +364,59 @@ __global__ void __launch_bounds__(128) lorentz_partial_kernel(const double* __re
     }
 }
 
+// Hamiltonian.get_dos: Gaussian broadening, same tiling as the Lorentzian kernel (threads own energies).
+template <int EPT>
+__global__ void __launch_bounds__(128) gauss_partial_kernel(const double* __restrict__ evals, long long n, const double* __restrict__ energies,
+                                                             int nE, int e_base, double w, double* __restrict__ part) {
+    __shared__ double s_eps[SKTB_LOR_TILE];
+    double E[EPT], acc[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        int ei = e_base + threadIdx.x + q * blockDim.x;
+        E[q] = ei < nE ? energies[ei] : 0.0;
+        acc[q] = 0.0;
+    }
+    const double inv2w2 = 1.0 / (2.0 * w * w);
+    for (long long t0 = (long long)blockIdx.x * SKTB_LOR_TILE; t0 < n; t0 += (long long)gridDim.x * SKTB_LOR_TILE) {
+        int len = (int)min((long long)SKTB_LOR_TILE, n - t0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < len; t += blockDim.x) s_eps[t] = evals[t0 + t];
+        __syncthreads();
+        for (int t = 0; t < len; ++t) {
+            const double ep = s_eps[t];
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) { const double x = E[q] - ep; acc[q] += exp(-(x * x) * inv2w2); }
+        }
+    }
+    const double pref = 1.0 / (3.141592653589793 * w * 1.4142135623730951);
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        int ei = e_base + threadIdx.x + q * blockDim.x;
+        if (ei < nE) part[(size_t)blockIdx.x * nE + ei] = acc[q] * pref;
+    }
+}
+
+// sum of the n_occ lowest bands over nk columns: per-CTA partial (fixed order), then one reducing CTA
+__global__ void __launch_bounds__(256) band_energy_partial_kernel(const double* __restrict__ evals, long long ld, long long nk, int n_occ,
+                                                                  double* __restrict__ part) {
+    __shared__ double scratch[64];
+    double s = 0.0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += (long long)gridDim.x * blockDim.x) {
+        double sk = 0.0;
+        for (int b = 0; b < n_occ; ++b) sk += evals[(long long)b * ld + k];
+        s += sk;
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void band_energy_reduce_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += part[i];
+        out[0] = s;
+    }
+}
+
 // out[g][e] (+)= sum_cta part[cta][g][e]
 __global__ void lorentz_reduce_kernel(const double* __restrict__ part, int n_cta, int ng_nE, double* __restrict__ out, int accumulate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

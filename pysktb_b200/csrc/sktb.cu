@@ -795,6 +795,49 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Gaussian get_dos, band energy
+// ------------------------------------------------------------------------------------------------------
+extern "C" int sktb_gauss_dos(sktb_plan* p, const double* evals_d, int64_t n, const double* energies_d, int32_t nE, double w, double* out_d,
+                              void* stream) {
+    if (!p || !energies_d || !out_d) return fail("null argument");
+    if (nE <= 0) return 0;
+    if (!(w > 0.0)) return fail("gaussian width must be positive");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(out_d, 0, (size_t)nE * 8, st));
+    if (n <= 0) return 0;
+    if (!evals_d) return fail("null argument");
+    const int LOR_GRID = 148 * 4;
+    const int gx = (int)std::min<long long>((n + SKTB_LOR_TILE - 1) / SKTB_LOR_TILE, LOR_GRID);
+    if (p->wsPart.ensure((size_t)LOR_GRID * nE * 8)) return fail("out of device memory (dos partials)");
+    const int ept = nE <= 128 ? 1 : (nE <= 256 ? 2 : 4);
+    for (int e_base = 0; e_base < nE; e_base += 128 * ept) {
+        auto kg = ept == 1 ? gauss_partial_kernel<1> : (ept == 2 ? gauss_partial_kernel<2> : gauss_partial_kernel<4>);
+        kg<<<gx, 128, 0, st>>>(evals_d, n, energies_d, nE, e_base, w, (double*)p->wsPart.p);
+        LAUNCHED();
+    }
+    lorentz_reduce_kernel<<<(nE + 127) / 128, 128, 0, st>>>((const double*)p->wsPart.p, gx, nE, out_d, 0);
+    LAUNCHED();
+    return 0;
+}
+
+extern "C" int sktb_band_energy(sktb_plan* p, const double* evals_d, int64_t ld, int64_t nk, int32_t n_occ, double* out_d, void* stream) {
+    if (!p || !out_d) return fail("null argument");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(out_d, 0, 8, st));
+    if (nk <= 0 || n_occ <= 0) return 0;
+    if (!evals_d) return fail("null argument");
+    const int grid = (int)std::min<long long>((nk + 255) / 256, 148 * 4);
+    if (p->wsPart.ensure((size_t)grid * 8)) return fail("out of device memory");
+    band_energy_partial_kernel<<<grid, 256, 0, st>>>(evals_d, ld, nk, n_occ, (double*)p->wsPart.p);
+    LAUNCHED();
+    band_energy_reduce_kernel<<<1, 32, 0, st>>>((const double*)p->wsPart.p, grid, out_d);
+    LAUNCHED();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // measurement helper
 // ------------------------------------------------------------------------------------------------------
 extern "C" int sktb_fp64_peak(int device, double* tflops, double* ms_out) {

@@ -317,6 +317,40 @@ class Hamiltonian(object):
                 raise Exception(_NOT_HERMITIAN)
         return out
 
+    def get_dos(self, energy, eig=None, w=1e-2, nk=[20, 20, 20]):
+        """Gaussian-broadened DOS (hamiltonian.py:233-253): eigenvalues on the endpoint-INCLUDED mesh
+        `linspace(0, 1, nk[i])` (kx outer, kz inner) through `solve_kpath` (soc=True as in `solve_k`), or the
+        caller's `eig`; sum_i exp(-(E - e_i)^2 / (2 w^2)) / (pi w sqrt(2)) on the device (sktb_gauss_dos)."""
+        torch = _torch()
+        energy = np.asarray(energy, dtype=float)
+        with torch.cuda.device(self._device):
+            if eig is None:
+                kx, ky, kz = (np.linspace(0, 1, int(n)) for n in nk)
+                mesh = np.stack(np.meshgrid(kx, ky, kz, indexing="ij"), axis=-1).reshape(-1, 3)
+                kd = torch.from_numpy(np.ascontiguousarray(mesh)).cuda()
+                N = self._dim(True)
+                ev = torch.empty((N, len(mesh)), dtype=torch.float64, device="cuda")
+                gate = self.asym_bound > 0.5e-9
+                fl = torch.zeros(len(mesh), dtype=torch.int32, device="cuda") if gate else None
+                _lib.check(_lib.lib().sktb_solve(self._plan, kd.data_ptr(), len(mesh), 1, ev.data_ptr(), None, len(mesh), 0,
+                                                 fl.data_ptr() if gate else None, self._stream()))
+                if gate and bool(fl.any().item()):
+                    raise Exception(_NOT_HERMITIAN)
+            else:
+                ev = torch.from_numpy(np.ascontiguousarray(np.asarray(eig, dtype=float).reshape(-1))).cuda()
+            Ed = torch.from_numpy(np.ascontiguousarray(energy.reshape(-1))).cuda()
+            out = torch.empty(Ed.numel(), dtype=torch.float64, device="cuda")
+            _lib.check(_lib.lib().sktb_gauss_dos(self._plan, ev.data_ptr(), ev.numel(), Ed.data_ptr(), Ed.numel(), float(w),
+                                                 out.data_ptr(), self._stream()))
+            res = out.cpu().numpy().reshape(energy.shape)
+        return res
+
+    @staticmethod
+    def kproj_weights(vecs, index):
+        """Projection weights of `plot_kproj` (hamiltonian.py:347-351): ||vecs[band, k, index]||_2, shape (band, k)."""
+        v = np.asarray(vecs)[:, :, list(index)]
+        return np.sqrt((np.abs(v) ** 2).sum(axis=-1))
+
     def clean_eig(self, eigen_val, eig=None):
         eigen_val = np.array(np.asarray(eigen_val).real, dtype=float)
         order = eigen_val.argsort()

@@ -350,3 +350,30 @@ def test_dos_properties_large_mesh(tb):
     ld = gf.ldos(E[::16], nk=[96, 96, 1], eta=0.1, soc=False)
     np.testing.assert_allclose(ld.sum(axis=0), gf.dos(E[::16], nk=[96, 96, 1], eta=0.1, soc=False), rtol=1e-10)
     np.testing.assert_allclose(ld[0], ld[1], rtol=1e-9)     # sublattice symmetry
+
+
+# ---------------------------------------------------------------------------------------------------
+# Hamiltonian.get_dos (Gaussian, sktb_gauss_dos) and Forces.get_total_energy (sktb_band_energy)
+# ---------------------------------------------------------------------------------------------------
+def test_next_rows_vs_reference_golden(tb):
+    g = golden("next_rows")
+    E = g["energy"]
+    _, ham = ham_for(tb, "C1_cubic_sp3")
+    np.testing.assert_allclose(ham.get_dos(E, eig=g["eig_in"], w=0.2), g["eig_gdos"], rtol=1e-11, atol=1e-300)
+    for tag, name in {"C1": "C1_cubic_sp3", "C3": "C3_sb_buckled", "C2": "C2_graphene_pz", "spchain": "sp_chain"}.items():
+        spec = spec_for(name)
+        _, h = ham_for(tb, name)
+        ne, nk = int(g[tag + "_etot_args"][0]), [int(x) for x in g[tag + "_etot_args"][1:]]
+        tot, band, rep = tb.Forces(h).get_total_energy(ne, nk=nk, soc=spec["soc"])
+        assert abs(band - g[tag + "_etot"][1]) < 1e-10 and rep == 0.0 and abs(tot - g[tag + "_etot"][0]) < 1e-10
+        if tag + "_gdos" in g:
+            d = h.get_dos(E, w=0.15, nk=[int(x) for x in g[tag + "_gdos_nk"]])
+            np.testing.assert_allclose(d, g[tag + "_gdos"], rtol=1e-8, atol=1e-12)
+    # larger mesh: oracle Gaussian on device eigenvalues, band energy against a numpy sum
+    ev = h.solve_kmesh([7, 5, 3])
+    Ew = np.linspace(-1, 1, 300)
+    from oracle import sktb_oracle as O
+    np.testing.assert_allclose(h.get_dos(Ew, eig=ev.cpu().numpy(), w=0.07), O.gauss_dos(ev.cpu().numpy(), Ew, 0.07), rtol=1e-10, atol=1e-12)
+    v = np.abs(np.random.default_rng(0).standard_normal((4, 3, 6)) + 1j)
+    assert np.allclose(tb.Hamiltonian.kproj_weights(v, [1, 4]), np.linalg.norm(v[:, :, [1, 4]], axis=-1))
+

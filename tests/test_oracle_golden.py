@@ -106,3 +106,25 @@ def test_lorentz_closed_form_equals_reference_dos():
         m = oracle_model(spec_for(name))
         ev = m.solve_kpath(list(m.kmesh(list(g["dos_nk"]))), soc=bool(g["soc"]))
         np.testing.assert_allclose(lorentz_dos(ev, g["dos_E"], float(g["dos_eta"])), g["dos"], rtol=1e-10)
+
+
+# Gaussian get_dos and Forces.get_total_energy of the real reference (tests/golden/next_rows.npz)
+NEXT_MODELS = {"C1": "C1_cubic_sp3", "C3": "C3_sb_buckled", "C2": "C2_graphene_pz", "spchain": "sp_chain"}
+
+
+def test_next_rows_oracle_vs_reference():
+    from oracle import sktb_oracle as O
+    g = golden("next_rows")
+    E = g["energy"]
+    np.testing.assert_allclose(O.gauss_dos(g["eig_in"], E, 0.2), g["eig_gdos"], rtol=1e-12, atol=1e-300)
+    for tag, name in NEXT_MODELS.items():
+        spec = spec_for(name)
+        m = oracle_model(spec)
+        ne, nk = int(g[tag + "_etot_args"][0]), [int(x) for x in g[tag + "_etot_args"][1:]]
+        e_band = O.total_energy_band(m, ne, nk=nk, soc=spec["soc"])
+        assert abs(e_band - g[tag + "_etot"][1]) < 1e-10, (tag, e_band, g[tag + "_etot"])
+        assert g[tag + "_etot"][2] == 0.0                                    # no repulsive potential in these models
+        if tag + "_gdos" in g:
+            d = O.get_dos(m, E, w=0.15, nk=[int(x) for x in g[tag + "_gdos_nk"]])
+            np.testing.assert_allclose(d, g[tag + "_gdos"], rtol=1e-9, atol=1e-12)
+
