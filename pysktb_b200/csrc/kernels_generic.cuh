@@ -144,7 +144,8 @@ __global__ void heev_generic_kernel(HeevArgs a) {
     double* scratch = sn + N;                     // 64
     cplx* v = reinterpret_cast<cplx*>(scratch + 64);
     cplx* w = v + N;
-    cplx* sA = w + N;                             // N*N when SMEM_A
+    cplx* v2 = w + N;
+    cplx* sA = v2 + N;                            // N*N when SMEM_A
     __shared__ int s_lo, s_hi, s_done;
     const int n_rows = a.n_rows;
 
@@ -166,6 +167,108 @@ __global__ void heev_generic_kernel(HeevArgs a) {
         }
         __syncthreads();
 
+        if (N <= T && N >= 2) {
+            // ---- one column per thread: look-ahead formulation (one read+write pass over the trailing matrix per
+            //      step instead of a mat-vec pass plus an update pass).  Thread i owns column i of the mirrored
+            //      matrix, so y_i = sum_k A[i][k] v_k = sum_k conj(C[k][i]) v_k needs no cross-thread reduction:
+            //      the mat-vec of reflector j+1 is accumulated while reflector j's rank-2 update streams by.
+            const int i = tid;
+            const bool mine = i < N;
+            cplx vi = cmake(0.0, 0.0), wi = cmake(0.0, 0.0), tau = cmake(0.0, 0.0);
+            // prologue: reflector 0 from column 0, plain mat-vec
+            {
+                cplx x = (mine && i >= 1) ? cconj(A[i]) : cmake(0.0, 0.0);
+                double xn = block_sum((i > 1) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
+                if (i == 1) { scratch[40] = x.x; scratch[41] = x.y; }
+                if (i == 0) d[0] = A[0].x;
+                __syncthreads();
+                cplx alpha = cmake(scratch[40], scratch[41]);
+                double beta; cplx scale;
+                householder(alpha, xn, beta, tau, scale);
+                if (i == 0) e[0] = beta;
+                vi = (i == 1) ? cmake(1.0, 0.0) : ((mine && i > 1) ? cmul(x, scale) : cmake(0.0, 0.0));
+                if (mine) v[i] = vi;
+                __syncthreads();
+                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                if (mine && i >= 1) {
+                    int k = 1;
+                    for (; k + 1 < N; k += 2) { cfmac(acc, A[(size_t)k * N + i], v[k]); cfmac(acc2, A[(size_t)(k + 1) * N + i], v[k + 1]); }
+                    if (k < N) cfmac(acc, A[(size_t)k * N + i], v[k]);
+                }
+                cplx p = (mine && i >= 1) ? cmul(tau, cadd(acc, acc2)) : cmake(0.0, 0.0);
+                cplx dl = cmake(0.0, 0.0);
+                cfmac(dl, p, vi);
+                cplx dot = block_sum(dl, scratch);
+                cplx a2 = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dot);
+                wi = p; cfma(wi, a2, vi);
+                if (mine) w[i] = wi;
+                __syncthreads();
+            }
+            for (int j = 0; j + 1 < N; ++j) {
+                // (1) row j+1 of the update -> the next pivot column (entries x'_i = conj(C[j+1][i]), i > j+1)
+                cplx x = cmake(0.0, 0.0);
+                if (mine && i >= j + 1) {
+                    cplx c = A[(size_t)(j + 1) * N + i];
+                    cfmsc(c, vi, w[j + 1]);
+                    cfmsc(c, wi, v[j + 1]);
+                    A[(size_t)(j + 1) * N + i] = c;
+                    if (i == j + 1) d[j + 1] = c.x;
+                    x = cconj(c);
+                }
+                // row tracking with reflector j (tracked rows of Q): R <- R H_j
+                for (int r = tid; r < n_rows; r += T) {
+                    cplx sdot = cmake(0.0, 0.0);
+                    for (int q = j + 1; q < N; ++q) cfma(sdot, RT[(size_t)q * n_rows + r], v[q]);
+                    cplx ts = cmul(tau, sdot);
+                    for (int q = j + 1; q < N; ++q) {
+                        cplx xx = RT[(size_t)q * n_rows + r];
+                        cplx vc = cconj(v[q]);
+                        cfms(xx, ts, vc);
+                        RT[(size_t)q * n_rows + r] = xx;
+                    }
+                }
+                if (j + 2 >= N) break;                                    // column N-1 is the last diagonal entry
+                double xn = block_sum((mine && i > j + 2) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
+                if (i == j + 2) { scratch[40] = x.x; scratch[41] = x.y; }
+                __syncthreads();
+                cplx alpha = cmake(scratch[40], scratch[41]);
+                double beta; cplx tau2, scale;
+                householder(alpha, xn, beta, tau2, scale);
+                if (i == 0) e[j + 1] = beta;
+                cplx v2i = (i == j + 2) ? cmake(1.0, 0.0) : ((mine && i > j + 2) ? cmul(x, scale) : cmake(0.0, 0.0));
+                if (mine) v2[i] = v2i;
+                __syncthreads();
+                // (2) rows k >= j+2: update and accumulate the next mat-vec in the same pass
+                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                if (mine && i >= j + 2) {
+                    int k = j + 2;
+#pragma unroll 2
+                    for (; k + 1 < N; k += 2) {
+                        cplx c0 = A[(size_t)k * N + i], c1 = A[(size_t)(k + 1) * N + i];
+                        cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
+                        cfmsc(c1, vi, w[k + 1]); cfmsc(c1, wi, v[k + 1]);
+                        A[(size_t)k * N + i] = c0; A[(size_t)(k + 1) * N + i] = c1;
+                        cfmac(acc, c0, v2[k]); cfmac(acc2, c1, v2[k + 1]);
+                    }
+                    if (k < N) {
+                        cplx c0 = A[(size_t)k * N + i];
+                        cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
+                        A[(size_t)k * N + i] = c0;
+                        cfmac(acc, c0, v2[k]);
+                    }
+                }
+                cplx p = (mine && i >= j + 2) ? cmul(tau2, cadd(acc, acc2)) : cmake(0.0, 0.0);
+                cplx dl = cmake(0.0, 0.0);
+                cfmac(dl, p, v2i);
+                cplx dot = block_sum(dl, scratch);                        // (syncs: every thread is done reading v, w)
+                cplx a2 = cmul(cmake(-0.5 * tau2.x, -0.5 * tau2.y), dot);
+                vi = v2i; tau = tau2;
+                wi = p; cfma(wi, a2, vi);
+                if (mine) { v[i] = vi; w[i] = wi; }
+                __syncthreads();
+            }
+            __syncthreads();
+        } else
         for (int j = 0; j + 1 < N; ++j) {
             const cplx* Aj = A + (size_t)j * N;
             double part = 0.0;

@@ -341,7 +341,7 @@ static int launch_hk(sktb_plan* p, const double* k_d, long long nk, int soc, cpl
 static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     const int N = a.N;
     int T = std::min(1024, std::max(32, (N + 31) / 32 * 32));
-    size_t aux = ((size_t)4 * N + 64) * sizeof(double) + (size_t)2 * N * sizeof(cplx);
+    size_t aux = ((size_t)4 * N + 64) * sizeof(double) + (size_t)3 * N * sizeof(cplx);
     size_t withA = aux + (size_t)N * N * sizeof(cplx);
     bool smemA = withA <= 200 * 1024;
     size_t smem = smemA ? withA : aux;
