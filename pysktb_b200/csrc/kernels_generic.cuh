@@ -242,15 +242,18 @@ __global__ void heev_generic_kernel(HeevArgs a) {
                 cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
                 if (mine && i >= j + 2) {
                     int k = j + 2;
-#pragma unroll 2
-                    for (; k + 1 < N; k += 2) {
-                        cplx c0 = A[(size_t)k * N + i], c1 = A[(size_t)(k + 1) * N + i];
+                    for (; k + 3 < N; k += 4) {                            // four independent 16 B loads in flight per thread
+                        cplx* Ak = A + (size_t)k * N + i;
+                        cplx c0 = Ak[0], c1 = Ak[N], c2 = Ak[2 * (size_t)N], c3 = Ak[3 * (size_t)N];
                         cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
                         cfmsc(c1, vi, w[k + 1]); cfmsc(c1, wi, v[k + 1]);
-                        A[(size_t)k * N + i] = c0; A[(size_t)(k + 1) * N + i] = c1;
+                        cfmsc(c2, vi, w[k + 2]); cfmsc(c2, wi, v[k + 2]);
+                        cfmsc(c3, vi, w[k + 3]); cfmsc(c3, wi, v[k + 3]);
+                        Ak[0] = c0; Ak[N] = c1; Ak[2 * (size_t)N] = c2; Ak[3 * (size_t)N] = c3;
                         cfmac(acc, c0, v2[k]); cfmac(acc2, c1, v2[k + 1]);
+                        cfmac(acc, c2, v2[k + 2]); cfmac(acc2, c3, v2[k + 3]);
                     }
-                    if (k < N) {
+                    for (; k < N; ++k) {
                         cplx c0 = A[(size_t)k * N + i];
                         cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
                         A[(size_t)k * N + i] = c0;
@@ -320,7 +323,58 @@ __global__ void heev_generic_kernel(HeevArgs a) {
         __syncthreads();
 
         // ---- tridiagonal QL ----
-        if (n_rows == 0) {
+        bool sorted_by_construction = false;
+        if (n_rows == 0 && N <= T && N > 48) {
+            // eigenvalues only, one eigenvalue per thread: bisection on the Sturm count (LAPACK dstebz recurrence
+            // q_i = d_i - x - e_{i-1}^2 / q_{i-1} with the pivmin safeguard) instead of a serial QL on one thread.
+            // Thread n brackets the n-th smallest eigenvalue, so the result is ascending without a sort.
+            double* e2 = cs;                                              // cs / sn are free here
+            double lo_b = 1e300, hi_b = -1e300, emax = 0.0;
+            if (tid < N) {
+                const double el = tid > 0 ? fabs(e[tid - 1]) : 0.0, er = tid < N - 1 ? fabs(e[tid]) : 0.0;
+                lo_b = d[tid] - el - er; hi_b = d[tid] + el + er;
+                e2[tid] = tid < N - 1 ? e[tid] * e[tid] : 0.0;
+                emax = fmax(fabs(d[tid]), fmax(el, er));
+            }
+            // block min / max through the sum helper's scratch (three passes keep the helper simple)
+            __syncthreads();
+            for (int o = 16; o > 0; o >>= 1) {
+                lo_b = fmin(lo_b, __shfl_xor_sync(0xffffffffu, lo_b, o));
+                hi_b = fmax(hi_b, __shfl_xor_sync(0xffffffffu, hi_b, o));
+                emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+            }
+            if ((tid & 31) == 0) { scratch[tid >> 5] = lo_b; scratch[32 + (tid >> 5)] = hi_b; sn[tid >> 5] = emax; }
+            __syncthreads();
+            const int nw = (T + 31) >> 5;
+            double gl = 1e300, gu = -1e300, tn = 0.0;
+            for (int q = 0; q < nw; ++q) { gl = fmin(gl, scratch[q]); gu = fmax(gu, scratch[32 + q]); tn = fmax(tn, sn[q]); }
+            const double eps = 2.220446049250313e-16;
+            const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, tn * tn), 1e-290);
+            gl -= 2.0 * eps * tn * N + 2.0 * pivmin; gu += 2.0 * eps * tn * N + 2.0 * pivmin;
+            double lam = 0.0;
+            if (tid < N) {
+                double lo = gl, hi = gu;
+                for (int it = 0; it < 128; ++it) {
+                    const double x = 0.5 * (lo + hi);
+                    if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
+                    int cnt = 0;
+                    double q = d[0] - x;
+                    if (fabs(q) < pivmin) q = -pivmin;
+                    cnt += q < 0.0;
+                    for (int r = 1; r < N; ++r) {
+                        q = d[r] - x - e2[r - 1] / q;
+                        if (fabs(q) < pivmin) q = -pivmin;
+                        cnt += q < 0.0;
+                    }
+                    if (cnt > tid) hi = x; else lo = x;
+                }
+                lam = 0.5 * (lo + hi);
+            }
+            __syncthreads();
+            if (tid < N) d[tid] = lam;
+            __syncthreads();
+            sorted_by_construction = true;
+        } else if (n_rows == 0) {
             if (tid == 0) { if (tql_values(d, e, N, 1)) atomicAdd(a.fail, 1); }
             __syncthreads();
         } else {
@@ -386,8 +440,9 @@ __global__ void heev_generic_kernel(HeevArgs a) {
         // ---- ascending rank sort + output ----
         for (int i = tid; i < N; i += T) {
             double di = d[i];
-            int rank = 0;
-            for (int q = 0; q < N; ++q) { double dq = d[q]; rank += (dq < di) || (dq == di && q < i); }
+            int rank = sorted_by_construction ? i : 0;
+            if (!sorted_by_construction)
+                for (int q = 0; q < N; ++q) { double dq = d[q]; rank += (dq < di) || (dq == di && q < i); }
             a.evals[(long long)rank * a.ld + a.col0 + mat] = di;
             e[i] = (double)rank;                   // e is free now: keep the permutation
         }
