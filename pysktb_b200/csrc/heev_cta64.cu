@@ -33,6 +33,38 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     return 2;
 }
 
+size_t vec64_bytes_per_k() { return (size_t)128 * 8 + (size_t)C64_VSTORE_CPLX * 16 + 4096 * 8 + 64 * 4; }   // (d,e) | reflectors | Z | ranks
+
+int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
+                 cudaStream_t st, std::string* info) {
+    if (N <= 32 || N > 64 || !evecs) { *info = "launch_vec64: bad arguments"; return -1; }
+    double* de = reinterpret_cast<double*>(scratch);
+    cplx* vstore = reinterpret_cast<cplx*>(de + (size_t)nm * 128);
+    double* zstore = reinterpret_cast<double*>(vstore + (size_t)nm * C64_VSTORE_CPLX);
+    int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nm * 4096);
+    const size_t smemQ = (size_t)VEC64_SMEM_DOUBLES * 8;
+    int dev = 0, sms = 148, occA = 0, occQ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<0>, C64_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, vecql64_kernel<0>, 32, smemQ);
+    if (occA < 1 || occQ < 1) { *info = "vec64 kernels do not fit"; return -1; }
+    C64Args a{H, N, nm, de, vstore};
+    const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
+    tridiag_cta64_kernel<0><<<gridA, C64_THREADS, 0, st>>>(a);
+    Vec64Args v{de, vstore, nm, N, evals, evecs, ld, col0, fail};
+    const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occQ));
+    vecql64_kernel<0><<<gridQ, 32, smemQ, st>>>(v, zstore, rankstore);
+    const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * 2));
+    vecbt64_kernel<0><<<gridV, 128, 0, st>>>(v, zstore, rankstore);
+    if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
+    char buf[256];
+    snprintf(buf, sizeof buf, "tridiag_cta64<vec> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d", gridA, C64_THREADS,
+             occA, gridQ, smemQ, occQ, gridV, N);
+    *info = buf;
+    return 3;
+}
+
 int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
                   cudaStream_t st, std::string* info) {
     if (N < 1 || N > 32) { *info = "launch_heev32: N out of range"; return -1; }

@@ -21,7 +21,10 @@ constexpr int C64_SMEM_CPLX = 4 * 128 + 2 + 4 * 64 + 32 + 32;   // V | P | X | s
 struct C64Smem {
     cplx *V, *P, *X, *alpha, *yp;
     double *D, *E;
+    cplx* vst = nullptr;     // global [64][64] reflector store of this matrix (eigenvector path) or NULL
+    cplx* taust = nullptr;   // global [64]
 };
+constexpr int C64_VSTORE_CPLX = 64 * 64 + 64;
 SKTB_D C64Smem c64_smem(cplx* base) {
     C64Smem s;
     s.V = base; s.P = base + 128; s.X = base + 256; s.alpha = base + 512; s.yp = base + 514;
@@ -92,6 +95,14 @@ SKTB_D void c64_finish(PairCarry& c, const cplx (&ypart)[2], const cplx (&xo)[2]
         for (int s = 2 - NS; s < 2; ++s) dst[s ? L.iB : L.iA] = L.h ? c.p[s] : c.v[s];
     }
     if (L.h == 2 && L.r == 0) S.E[jn] = beta;
+    if (S.vst && jn < 63) {          // eigenvector path: keep reflector jn and tau (warp 3 is otherwise idle here)
+        if (L.h == 3) {
+#pragma unroll
+            for (int s = 2 - NS; s < 2; ++s) S.vst[(size_t)jn * 64 + (s ? L.iB : L.iA)] = c.v[s];
+            if (NS == 1) S.vst[(size_t)jn * 64 + L.iA] = cmake(0.0, 0.0);      // retired rows: every entry of the store is defined
+            if (L.r == 0) S.taust[jn] = tau;
+        }
+    }
     __syncthreads();
 }
 
@@ -184,6 +195,7 @@ struct C64Args {
     const cplx* H;          // [nm][N][N] row-major (K1 output)
     int N; long long nm;
     double* scratch;        // [nm][2][64]  (d | e)
+    cplx* vstore = nullptr; // [nm][C64_VSTORE_CPLX] reflectors + tau (eigenvector path) or NULL
 };
 
 template <int UNUSED>
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
     const int t = threadIdx.x;
     C64Lane L;
     L.r = t & 31; L.h = t >> 5; L.iA = L.r; L.iB = 63 - L.r;
-    const C64Smem S = c64_smem(smem);
+    C64Smem S = c64_smem(smem);
     for (int q = t; q < C64_SMEM_CPLX; q += C64_THREADS) smem[q] = cmake(0.0, 0.0);
     __syncthreads();
     const int N = a.N;
@@ -200,6 +212,7 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
     for (long long km = blockIdx.x; km < a.nm; km += gridDim.x) {
         // ---- load rows iA, iB x columns 4m + h with zheevd(UPLO='L') semantics: upper triangle = conj(lower) ----
         const cplx* H = a.H + (size_t)km * N * N;
+        if (a.vstore) { S.vst = a.vstore + (size_t)km * C64_VSTORE_CPLX; S.taust = S.vst + 4096; }
         cplx B[2][16];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {

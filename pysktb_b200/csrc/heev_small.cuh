@@ -556,6 +556,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
 #include "heev_pair.cuh"
 #include "heev_cta64.cuh"
 #include "heev_vec32.cuh"
+#include "heev_vec64.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
@@ -811,6 +812,12 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
 // N <= 32 with eigenvectors (no gate): pair-layout tridiagonalisation keeping the reflectors -> vec32_kernel
 // (QL with accumulation, sort, back-transformation).  evecs: [N][ld][N] complex (reference layout [band, k, comp]).
 // scratch: >= nk * vec32_bytes_per_k() bytes.  Returns the number of kernels launched or -1 (text in *info).
+// 32 < N <= 64 with eigenvectors: H [nm][N][N] (K1 output or caller matrices, not modified) -> tridiag_cta64 keeping the
+// reflectors -> vecql64 -> vecbt64.  scratch: >= nm * vec64_bytes_per_k() bytes.  evecs [N][ld][N].
+size_t vec64_bytes_per_k();
+int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
+                 cudaStream_t st, std::string* info);
+
 // sktb_heev for N <= 32: caller-supplied matrices H [nm][N][N] (lower triangle read, input not modified) through the
 // pair kernels in LOAD mode; evecs may be NULL.  scratch: >= nm * vec32_bytes_per_k() bytes.
 int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,

@@ -408,6 +408,22 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
             if (rc < 0) return fail("vec32 launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
         }
+    } else if (want_vecs && N > 32 && N <= 64) {
+        // K1 -> tridiag_cta64 keeping the reflectors -> vecql64 -> vecbt64
+        const size_t perH = (size_t)N * N * sizeof(cplx), per_k = perH + small::vec64_bytes_per_k() + 24;
+        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
+        if (W.H.ensure(perH * chunk) || W.RT.ensure(small::vec64_bytes_per_k() * chunk)) return fail("out of device memory (vec64 workspaces)");
+        if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
+        for (long long c0 = 0; c0 < nk; c0 += chunk) {
+            long long cnt = std::min(chunk, nk - c0);
+            const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
+            if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
+            int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
+            if (rc) return rc;
+            rc = small::launch_vec64((const cplx*)W.H.p, N, cnt, evals_d, (cplx*)evecs_d, ld, k_off + c0, p->d_fail, W.RT.p, st, &g_kinfo);
+            if (rc < 0) return fail("vec64 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        }
     } else if (!want_vecs && N > 32 && N <= 64) {
         // K1 materialises H(k) (64 KB per k at N = 64), tridiag_cta64_kernel keeps it in registers, QL per lane
         size_t perH = (size_t)N * N * sizeof(cplx);
@@ -534,6 +550,18 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
         }
         return 0;
     }
+    if (N <= 64 && evecs_d && !heev_generic_only) {       // CTA-resident kernel keeping the reflectors + vec64
+        const size_t per_k = small::vec64_bytes_per_k();
+        long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / per_k)));
+        if (p->ws[2].RT.ensure(per_k * chunk)) return fail("out of device memory (heev workspace)");
+        for (long long c0 = 0; c0 < nm; c0 += chunk) {
+            long long cnt = std::min(chunk, (long long)nm - c0);
+            int rc = small::launch_vec64((const cplx*)H_d + (size_t)c0 * N * N, N, cnt, evals_d, (cplx*)evecs_d, nm, c0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
+            if (rc < 0) return fail("vec64 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        }
+        return 0;
+    }
     if (N <= 64 && !evecs_d && !heev_generic_only) {      // CTA-resident kernel, eigenvalues only
         if (p->ws[2].S.ensure((size_t)nm * 128 * 8)) return fail("out of device memory (heev workspace)");
         int rc = small::launch_cta64((const cplx*)H_d, N, nm, (double*)p->ws[2].S.p, evals_d, nm, 0, p->d_fail, st, &g_kinfo);
@@ -653,7 +681,8 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     const bool gate = p->asym_bound > 0.5e-9;
     // N <= 32 with projections: full eigenvectors from the register path (vec32), weights read by row index
     const bool use_vec32 = n_rows > 0 && p->small_ok && small::supports(N) && !gate;
-    if (use_vec32) { grp_rows.assign(grp_idx, grp_idx + grp_ptr[n_groups]); n_rows = N; }
+    const bool use_vec64 = n_rows > 0 && N > 32 && N <= 64;        // full eigenvectors from tridiag_cta64 + vec64
+    if (use_vec32 || use_vec64) { grp_rows.assign(grp_idx, grp_idx + grp_ptr[n_groups]); n_rows = N; }
     CK(cudaMemsetAsync(out_d, 0, (size_t)ng * nE * 8, st));
     CK(cudaMemsetAsync(p->d_any, 0, sizeof(int), st));
     if (k_count <= 0) { if (nonherm_any_h) *nonherm_any_h = 0; return 0; }
@@ -672,11 +701,12 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     const bool use_small = n_rows == 0 && p->small_ok && small::supports(N);
     const bool use_cta64 = n_rows == 0 && !use_small && N > 32 && N <= 64;     // eigenvalues only, register-resident CTA kernel
     size_t per_k = (size_t)N * 8 + ((use_small || use_vec32) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? 1024 : 0) +
-                   (use_vec32 ? small::vec32_bytes_per_k() : 0);
+                   (use_vec32 ? small::vec32_bytes_per_k() : 0) + (use_vec64 ? small::vec64_bytes_per_k() : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(WS_BUDGET / per_k)));
     const int LOR_GRID = 148 * 4;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
-        (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k() : (size_t)chunk * N * n_rows * 16) ||
+        (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k()
+                                                 : (use_vec64 ? (size_t)chunk * small::vec64_bytes_per_k() : (size_t)chunk * N * n_rows * 16)) ||
                     p->wsVec.ensure((size_t)chunk * N * n_rows * 16))) ||
         (!k_d && !use_small && !use_vec32 && p->ws[2].K.ensure((size_t)chunk * 24)) || (gate && p->wsFlag.ensure((size_t)chunk * 4)) ||
         p->wsPart.ensure((size_t)LOR_GRID * ng * nE * 8))
@@ -709,7 +739,11 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = n_rows; a.rows = d_rows;
                 a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * n_rows; a.vs_k = n_rows; a.vcol0 = 0;
             }
-            if (use_cta64) {
+            if (use_vec64) {
+                int rl = small::launch_vec64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
+                if (rl < 0) return fail("vec64 launch failed: %s", g_kinfo.c_str());
+                g_launches += rl;
+            } else if (use_cta64) {
                 if (p->ws[2].S.ensure((size_t)cnt * 128 * 8)) return fail("out of device memory (tridiagonal scratch)");
                 int rl = small::launch_cta64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo);
                 if (rl < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
