@@ -585,9 +585,11 @@ __global__ void lorentz_reduce_kernel(const double* __restrict__ part, int n_cta
 }
 
 // A(k,E) maps: out[k][e] = sum_band w(band,k) L(E_e - eps(band,k)); one CTA per k.
+// vec: [band][count][n_rows]; sel == NULL: the weight sums all n_rows stored rows (tracked-row layout), else the n_sel
+// entries sel[q] of full eigenvectors (n_rows = N).
 __global__ void spectral_map_kernel(const double* __restrict__ evals, long long ld, long long col0, long long count, int N,
-                                    const cplx* __restrict__ vec, int n_rows, const double* __restrict__ energies, int nE,
-                                    double eta, double* __restrict__ out, long long out_k0) {
+                                    const cplx* __restrict__ vec, int n_rows, const int* __restrict__ sel, int n_sel,
+                                    const double* __restrict__ energies, int nE, double eta, double* __restrict__ out, long long out_k0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_eps = reinterpret_cast<double*>(smem_raw);
     double* s_w = s_eps + N;
@@ -600,14 +602,21 @@ __global__ void spectral_map_kernel(const double* __restrict__ evals, long long 
             if (n_rows > 0) {
                 wgt = 0.0;
                 const cplx* vv = vec + ((size_t)b * count + k) * n_rows;
-                for (int q = 0; q < n_rows; ++q) { cplx u = vv[q]; wgt = fma(u.x, u.x, wgt); wgt = fma(u.y, u.y, wgt); }
+                const int nq = sel ? n_sel : n_rows;
+                for (int q = 0; q < nq; ++q) { cplx u = vv[sel ? sel[q] : q]; wgt = fma(u.x, u.x, wgt); wgt = fma(u.y, u.y, wgt); }
             }
             s_w[b] = wgt * pref;
         }
         __syncthreads();
         for (int ei = threadIdx.x; ei < nE; ei += blockDim.x) {
             double E = energies[ei], acc = 0.0;
-            for (int b = 0; b < N; ++b) { double x = E - s_eps[b]; acc += s_w[b] / fma(x, x, eta2); }
+            for (int b = 0; b < N; ++b) {
+                const double x = E - s_eps[b], den = fma(x, x, eta2);
+                double r;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+                r = fma(r, fma(-den, r, 1.0), r);
+                acc = fma(s_w[b], r, acc);
+            }
             out[(out_k0 + k) * nE + ei] = acc;
         }
     }

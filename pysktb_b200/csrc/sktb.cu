@@ -796,30 +796,63 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
     }
     const bool gate = p->asym_bound > 0.5e-9;
     CK(cudaMemsetAsync(p->d_any, 0, sizeof(int), st));
-    size_t per_k = (size_t)N * 8 + (size_t)N * N * 16 + (size_t)N * nr * 32 + 4;
+    // solver choice: register-resident paths (full eigenvectors when a projection is asked for), else generic row tracking
+    const bool small_path = p->small_ok && small::supports(N) && !gate;
+    const bool mid_path = N > 32 && N <= 64;
+    const bool full_vec = nr > 0 && (small_path || mid_path);
+    const int vstride = full_vec ? N : nr;
+    size_t per_k = (size_t)N * 8 + ((small_path) ? 0 : (size_t)N * N * 16) + (size_t)N * vstride * 32 + 4 +
+                   (small_path ? (nr ? small::vec32_bytes_per_k() : 1024) : 0) + (mid_path ? small::vec64_bytes_per_k() : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
-    if (p->wsE.ensure((size_t)chunk * N * 8) || p->ws[2].H.ensure((size_t)chunk * N * N * 16) ||
-        (nr && (p->ws[2].RT.ensure((size_t)chunk * N * nr * 16) || p->wsVec.ensure((size_t)chunk * N * nr * 16))) ||
+    if (p->wsE.ensure((size_t)chunk * N * 8) || (!small_path && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
+        (nr && p->wsVec.ensure((size_t)chunk * N * vstride * 16)) ||
+        (nr && p->ws[2].RT.ensure(small_path ? (size_t)chunk * small::vec32_bytes_per_k()
+                                             : (mid_path ? (size_t)chunk * small::vec64_bytes_per_k() : (size_t)chunk * N * nr * 16))) ||
         (gate && p->wsFlag.ensure((size_t)chunk * 4)))
         return fail("out of device memory (spectral workspaces)");
     for (long long c0 = 0; c0 < nk; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)nk - c0);
         int* flags = gate ? (int*)p->wsFlag.p : nullptr;
-        int rc = launch_hk(p, k_d + 3 * c0, cnt, soc, (cplx*)p->ws[2].H.p, flags, 0, st);
-        if (rc) return rc;
-        HeevArgs a{};
-        a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
-        a.evals = (double*)p->wsE.p; a.ld = cnt; a.col0 = 0;
-        if (nr) {
-            a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = nr; a.rows = d_rows;
-            a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * nr; a.vs_k = nr; a.vcol0 = 0;
+        if (small_path) {
+            int rc;
+            if (nr) rc = small::launch_vec32(p->small_tab, k_d + 3 * c0, nullptr, 0, cnt, soc, N, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, flags, 0,
+                                             p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
+            else {
+                size_t sbytes = small_scratch_bytes(N, cnt);
+                if (p->ws[2].S.ensure(sbytes)) return fail("out of device memory (tridiagonal scratch)");
+                rc = small::launch_solve(p->small_tab, k_d + 3 * c0, nullptr, 0, cnt, soc, N, (double*)p->wsE.p, cnt, 0, flags, 0, p->d_fail,
+                                         (double*)p->ws[2].S.p, sbytes, st, &g_kinfo);
+            }
+            if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        } else {
+            int rc = launch_hk(p, k_d + 3 * c0, cnt, soc, (cplx*)p->ws[2].H.p, flags, 0, st);
+            if (rc) return rc;
+            if (mid_path) {
+                int rl;
+                if (nr) rl = small::launch_vec64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
+                else {
+                    if (p->ws[2].S.ensure((size_t)cnt * 128 * 8)) return fail("out of device memory (tridiagonal scratch)");
+                    rl = small::launch_cta64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo);
+                }
+                if (rl < 0) return fail("mid-path launch failed: %s", g_kinfo.c_str());
+                g_launches += rl;
+            } else {
+                HeevArgs a{};
+                a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
+                a.evals = (double*)p->wsE.p; a.ld = cnt; a.col0 = 0;
+                if (nr) {
+                    a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = nr; a.rows = d_rows;
+                    a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * nr; a.vs_k = nr; a.vcol0 = 0;
+                }
+                rc = launch_heev_generic(p, a, st);
+                if (rc) return rc;
+            }
         }
-        rc = launch_heev_generic(p, a, st);
-        if (rc) return rc;
         if (gate) { any_flag_kernel<<<64, 256, 0, st>>>(flags, cnt, p->d_any); LAUNCHED(); }
         unsigned grid = (unsigned)std::min<long long>(cnt, 148LL * 8);
-        spectral_map_kernel<<<grid, 128, (size_t)2 * N * 8, st>>>((const double*)p->wsE.p, cnt, 0, cnt, N, (const cplx*)p->wsVec.p, nr, energies_d, nE, eta,
-                                                                out_d, c0);
+        spectral_map_kernel<<<grid, 128, (size_t)2 * N * 8, st>>>((const double*)p->wsE.p, cnt, 0, cnt, N, (const cplx*)p->wsVec.p, vstride,
+                                                                full_vec ? d_rows : nullptr, nr, energies_d, nE, eta, out_d, c0);
         LAUNCHED();
     }
     CK(cudaMemcpyAsync(p->h_pinned, p->d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
