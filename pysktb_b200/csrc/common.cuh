@@ -137,8 +137,19 @@ SKTB_D cplx block_sum(cplx v, double* scratch) {
 
 // k-mesh point of flat index idx (greens.py:104-109): true IEEE divisions, no reciprocal multiply.
 SKTB_HD void kmesh_point(long long idx, int n0, int n1, int n2, double& kx, double& ky, double& kz) {
-    long long l = idx % n2, t = idx / n2;
-    long long j = t % n1, i = t / n1;
+    long long l, j, i;
+    if ((unsigned long long)idx <= 0xffffffffULL) {          // 32-bit index arithmetic whenever the flat index fits (64-bit
+        const unsigned u = (unsigned)idx;                     // integer division costs ~100 instructions per k-point)
+        const unsigned t32 = u / (unsigned)n2;
+        l = u - t32 * (unsigned)n2;
+        const unsigned i32 = t32 / (unsigned)n1;
+        j = t32 - i32 * (unsigned)n1;
+        i = i32;
+    } else {
+        l = idx % n2;
+        const long long t = idx / n2;
+        j = t % n1; i = t / n1;
+    }
     double d0 = (double)(n0 > 1 ? n0 : 1), d1 = (double)(n1 > 1 ? n1 : 1), d2 = (double)(n2 > 1 ? n2 : 1);
 #ifdef __CUDA_ARCH__
     kx = __ddiv_rn((double)i, d0); ky = __ddiv_rn((double)j, d1); kz = __ddiv_rn((double)l, d2);

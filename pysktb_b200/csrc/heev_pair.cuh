@@ -464,7 +464,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const c
     const PairLane L = pair_lane<16>(lane);
     const long long n_pairs = (nk + 1) / 2;
 #pragma unroll 1
-    for (long long pr = (long long)blockIdx.x * PAIR_WARPS + warp; pr < n_pairs; pr += (long long)gridDim.x * PAIR_WARPS) {
+    for (long long pcta = (long long)blockIdx.x * PAIR_WARPS; pcta < n_pairs; pcta += (long long)gridDim.x * PAIR_WARPS) {
+#if SKTB_SMALL_SYNC
+        __syncthreads();          // keep the CTA's warps on the same stretch of the instruction stream (L1.5 I-cache is 32 KB)
+#endif
+        const long long pr = pcta + warp;
         long long kq = 2 * pr + g;
         const bool k_ok = kq < nk;
         if (!k_ok) kq = nk - 1;
