@@ -77,7 +77,7 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16;
     const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * 32 * DSTRIDE * 8;
-    auto kW = pair_wide32_kernel<PAIR_SRC_LOAD, 4, true>;
+    void (*kW)(SmallArgs, cplx*, cplx*) = evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, false>;
     auto kB = tql_small_kernel<32, 32>;
     if (cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) { *info = "cudaFuncSetAttribute failed"; return -1; }
     int dev = 0, sms = 148;
@@ -124,7 +124,7 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
     double* zstore = reinterpret_cast<double*>(vstore + (size_t)nk * PAIR_VSTORE_CPLX);
     int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nk * 1024);
-    void (*kW)(SmallArgs, cplx*, cplx*) = soc ? pair_wide32_kernel<PAIR_SRC_SOC, 4, true> : pair_wide32_kernel<PAIR_SRC_NOSOC, 4, true>;
+    void (*kW)(SmallArgs, cplx*, cplx*) = soc ? pair_wide32_kernel<PAIR_SRC_SOC, 4, true, true> : pair_wide32_kernel<PAIR_SRC_NOSOC, 4, true, true>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
     }

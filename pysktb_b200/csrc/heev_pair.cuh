@@ -102,15 +102,20 @@ SKTB_D double pair_rsum(double v) {
 
 // zlarfg, branch-free (straight-line code, so that ptxas can schedule this scalar chain under the update loop)
 SKTB_D void pair_larfg(const cplx alpha, const double xn, double& beta, cplx& tau, cplx& scale) {
+    // The reciprocal square root / reciprocal run on every path (inputs replaced by 1, results multiplied by a 0/1
+    // mask when the reflector is trivial): a result that is only *selected* lets ptxas branch around the chain, and
+    // that branch would end the basic block in the middle of the update loop this chain is meant to hide under.
     const bool trivial = (xn == 0.0) && (alpha.y == 0.0);
+    const double live = trivial ? 0.0 : 1.0;
     const double n2 = fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xn));
-    const double inrm = trivial ? 0.0 : pair_rsqrt(n2);
+    const double inrm = pair_rsqrt(trivial ? 1.0 : n2) * live;
     const double sgn = alpha.x >= 0.0 ? -1.0 : 1.0;
     beta = trivial ? alpha.x : sgn * (n2 * inrm);
     const double ib = sgn * inrm;
     tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
     const double dx = alpha.x - beta, dy = alpha.y;
-    const double id = trivial ? 0.0 : pair_rcp(fma(dx, dx, dy * dy));
+    const double den = fma(dx, dx, dy * dy);
+    const double id = pair_rcp(trivial ? 1.0 : den) * live;
     scale = cmake(dx * id, -dy * id);
 }
 
@@ -136,7 +141,7 @@ SKTB_D void pair_publish(const cplx (&x)[2], const int jn, const bool owner, con
 }
 
 // reflector of step jn from the published column + y = A v partial sums z -> new carry; publishes v (parity 0) / p (parity 1)
-template <int LN, int NS>
+template <int LN, int NS, bool VEC>
 SKTB_D void pair_finish(PairCarry& c, const cplx (&z)[2], const cplx (&acol)[2], const bool a_here, const cplx (&xo)[2], const cplx alpha,
                         const double xn, const int jn, const PairLane& L, const PairBuf& S, cplx* Vnext) {
     double beta; cplx tau, scale;
@@ -168,7 +173,7 @@ SKTB_D void pair_finish(PairCarry& c, const cplx (&z)[2], const cplx (&acol)[2],
     cplx* dst = L.h ? S.P : Vnext;
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) dst[s ? L.iB : L.iA] = L.h ? c.p[s] : c.v[s];
-    if (S.vst && jn < LN - 1) {      // eigenvector path: keep reflector jn (rows of the live slots) and tau; the no-op
+    if (VEC && jn < LN - 1) {      // eigenvector path: keep reflector jn (rows of the live slots) and tau; the no-op
                                      // step LN-1 at the end of the last phase must not write (it would land in tau[])
         if (L.h == 0) {
 #pragma unroll
@@ -182,7 +187,7 @@ SKTB_D void pair_finish(PairCarry& c, const cplx (&z)[2], const cplx (&acol)[2],
 // One Householder step j.  EVEN: j == base (pivot column in register 0 of parity-0 lanes, next pivot in register 0
 // of parity-1 lanes); ODD: j == base + 1 (register 0 dead, next pivot in register 1 of parity-0 lanes) and every
 // result is written one register down (the window rotation).  HALF = live registers per slot, NS = live slots.
-template <int LN, int HALF, int NS, bool EVEN>
+template <int LN, int HALF, int NS, bool EVEN, bool VEC>
 SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const PairLane& L, const PairBuf& S) {
     constexpr int ME = EVEN ? 0 : 1;          // register of the next pivot column
     constexpr int SH = EVEN ? 0 : 1;          // destination shift
@@ -248,11 +253,11 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
     // column jn+1 (where v' = 1): EVEN -> register 1 of parity-0 lanes; ODD -> old register 1 (now 0) of parity-1 lanes
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) acol[s] = EVEN ? B[s][1] : B[s][0];
-    pair_finish<LN, NS>(c, z, acol, L.h == (EVEN ? 0 : 1), xo, alpha, xn, jn, L, S, EVEN ? S.V1 : S.V0);
+    pair_finish<LN, NS, VEC>(c, z, acol, L.h == (EVEN ? 0 : 1), xo, alpha, xn, jn, L, S, EVEN ? S.V1 : S.V0);
 }
 
 // pivot column 0 (register 0 of parity-0 lanes) and the plain mat-vec for reflector 0
-template <int LN>
+template <int LN, bool VEC>
 SKTB_D void pair_prologue(cplx (&B)[2][LN / 2], PairCarry& c, const PairLane& L, const PairBuf& S) {
     cplx x[2] = {B[0][0], B[1][0]};
     pair_publish<2>(x, 0, L.h == 0, L, S);
@@ -276,21 +281,21 @@ SKTB_D void pair_prologue(cplx (&B)[2][LN / 2], PairCarry& c, const PairLane& L,
     }
     acol[0] = B[0][0]; acol[1] = B[1][0];                 // column 1 = register 0 of parity-1 lanes
     c.eval = 0.0;
-    pair_finish<LN, 2>(c, z, acol, L.h == 1, xo, alpha, xn, 0, L, S, S.V0);
+    pair_finish<LN, 2, VEC>(c, z, acol, L.h == 1, xo, alpha, xn, 0, L, S, S.V0);
 }
 
 // phases of S steps: window HALF registers, then HALF - S/2, ... down to (excluding) HEND; slot A is dead once
 // HALF <= LN/4 (step >= LN/2)
-template <int LN, int HALF, int HEND, int S>
+template <int LN, int HALF, int HEND, int S, bool VEC>
 SKTB_D void pair_phases(cplx (&B)[2][LN / 2], PairCarry& c, int& j, const PairLane& L, const PairBuf& S_) {
     constexpr int NS = HALF > LN / 4 ? 2 : 1;
 #pragma unroll 1
     for (int it = 0; it < S / 2; ++it) {
-        pair_step<LN, HALF, NS, true>(B, c, j, L, S_);
-        pair_step<LN, HALF, NS, false>(B, c, j + 1, L, S_);      // (the step LN-1 of the last phase is a harmless no-op)
+        pair_step<LN, HALF, NS, true, VEC>(B, c, j, L, S_);
+        pair_step<LN, HALF, NS, false, VEC>(B, c, j + 1, L, S_);      // (the step LN-1 of the last phase is a harmless no-op)
         j += 2;
     }
-    if constexpr (HALF - S / 2 > HEND) pair_phases<LN, HALF - S / 2, HEND, S>(B, c, j, L, S_);
+    if constexpr (HALF - S / 2 > HEND) pair_phases<LN, HALF - S / 2, HEND, S, VEC>(B, c, j, L, S_);
 }
 
 // K1 in the pair layout: rows iA, iB x columns 2m + h of the mirrored-lower H(k).  Branch-free: table offsets of
@@ -398,7 +403,7 @@ SKTB_D void pair_load(cplx (&B)[2][16], const cplx* __restrict__ H, const int N,
 
 constexpr int PAIR_SRC_NOSOC = 0, PAIR_SRC_SOC = 1, PAIR_SRC_LOAD = 2;
 
-template <int SRC, int S, bool FULL>
+template <int SRC, int S, bool FULL, bool VEC = false>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallArgs a, cplx* __restrict__ blocks, cplx* __restrict__ vstore) {
     constexpr int NC = 32;
     constexpr bool SOC = SRC == PAIR_SRC_SOC, LOAD = SRC == PAIR_SRC_LOAD;
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         long long kq = kcta + warp;
         const bool k_ok = kq < a.nk;
         if (!k_ok) kq = a.nk - 1;
-        if (vstore) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
+        if (VEC) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
         cplx B[2][16];
         if (LOAD) pair_load(B, a.Hsrc + (size_t)kq * a.N * a.N, a.N, L);
         else {
@@ -434,9 +439,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         }
         if (a.flags && lane == 0 && k_ok) a.flags[a.flag_off + kq] = 0;
         PairCarry c;
-        pair_prologue<32>(B, c, L, S_);
+        pair_prologue<32, VEC>(B, c, L, S_);
         int j = 0;
-        pair_phases<32, 16, FULL ? 0 : 8, S>(B, c, j, L, S_);
+        pair_phases<32, 16, FULL ? 0 : 8, S, VEC>(B, c, j, L, S_);
         if (k_ok) {
             double* out = a.scratch + (size_t)kq * (2 * NC);
             out[lane] = S_.D[lane]; out[NC + lane] = c.eval;
@@ -480,9 +485,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const c
             B[1][m] = blk[(2 * m + L.h) * 16 + L.iB];
         }
         PairCarry c;
-        pair_prologue<16>(B, c, L, S_);
+        pair_prologue<16, false>(B, c, L, S_);
         int j = 0;
-        pair_phases<16, 8, 0, S>(B, c, j, L, S_);
+        pair_phases<16, 8, 0, S, false>(B, c, j, L, S_);
         if (k_ok) {
             double* out = scratch + (size_t)kq * (2 * NC);
             out[16 + L.l] = S_.D[L.l]; out[NC + 16 + L.l] = c.eval;
