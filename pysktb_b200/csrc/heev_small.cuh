@@ -530,12 +530,18 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
     for (long long batch = gwarp; batch < n_batches; batch += nwarps) {
         const long long kbase = batch * 32;
         const int cnt = (int)min((long long)32, a.nk - kbase);
-#pragma unroll 4
-        for (int m = 0; m < 32; ++m) {
-            const double* src = a.scratch + (size_t)(kbase + min(m, cnt - 1)) * (2 * NC);
-            for (int t = lane; t < 2 * NC; t += 32) {
-                double v = src[t];
-                if (t < NC) dbuf[t * DSTRIDE + m] = v; else ebuf[(t - NC) * DSTRIDE + m] = v;
+        {   // every lane fetches ITS matrix: NC independent 16-byte loads in flight per lane, stored straight into the
+            // lane's own (conflict-free, odd-stride) column - no cross-lane transposition, no load->store dependence chain
+            const double2* src = reinterpret_cast<const double2*>(a.scratch + (size_t)(kbase + min(lane, cnt - 1)) * (2 * NC));
+#pragma unroll
+            for (int t = 0; t < NC / 2; ++t) {
+                const double2 v = src[t];
+                dbuf[(2 * t) * DSTRIDE + lane] = v.x; dbuf[(2 * t + 1) * DSTRIDE + lane] = v.y;
+            }
+#pragma unroll
+            for (int t = 0; t < NC / 2; ++t) {
+                const double2 v = src[NC / 2 + t];
+                ebuf[(2 * t) * DSTRIDE + lane] = v.x; ebuf[(2 * t + 1) * DSTRIDE + lane] = v.y;
             }
         }
         __syncwarp();
