@@ -182,8 +182,9 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]               # keep stdout to the one JSON line: at VERSION and WARN level NCCL
+                                                        # prints its version banner to stdout on the first communicator
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _, ham = W.instantiate(spec, tb, tb.scaling, device=local)
     lib = _lib.lib()
