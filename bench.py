@@ -185,7 +185,19 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             del os.environ["NCCL_DEBUG"]               # keep stdout to the one JSON line: at VERSION and WARN level NCCL
                                                         # prints its version banner to stdout on the first communicator
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to stdout when the first communicator is created (depending on the box's
+        # NCCL_DEBUG): route fd 1 to stderr until the communicator exists, so that stdout carries only the JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     _, ham = W.instantiate(spec, tb, tb.scaling, device=local)
     lib = _lib.lib()
 
