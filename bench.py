@@ -241,6 +241,7 @@ def main():
     ms = float(t_ms.item())
     value = per_gpu_k * world / (ms * 1e-3)
     checksum = float(out[:, :: max(1, count // 4096)].sum().item())
+    ql_failures = ham.ql_failures()                                  # matrices whose QL did not converge (must be 0)
 
     # ---- e2e through the public API with host buffers -------------------------------------------------
     e2e = None
@@ -314,7 +315,7 @@ def main():
     line = {"metric": "k-points/sec (H(k)+eigh)", "value": value, "unit": "k-points/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum}
+            "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum, "ql_failures": ql_failures}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -284,6 +284,7 @@ class Hamiltonian(object):
                                               vecs.ctypes.data if eig_vectors else None, _lib.C.byref(bad)))
         if bad.value:
             raise Exception(_NOT_HERMITIAN)
+        self._check_convergence()
         return (vals, vecs) if eig_vectors else vals
 
     def solve_k(self, k_point=None, eig_vectors=False):
@@ -357,6 +358,19 @@ class Hamiltonian(object):
         if eig is not None:
             return eigen_val[order], eig[order]
         return eigen_val[order]
+
+    def ql_failures(self):
+        """Number of matrices whose tridiagonal QL hit its iteration limit since the plan was created (synchronises).
+        numpy raises LinAlgError in that situation (hamiltonian.py:119 -> zheevd INFO > 0); see `_check_convergence`."""
+        n = _lib.C.c_int32(0)
+        _lib.check(_lib.lib().sktb_ql_failures(self._plan, _lib.C.byref(n)))
+        return int(n.value)
+
+    def _check_convergence(self):
+        n = self.ql_failures()
+        if n > getattr(self, "_ql_seen", 0):
+            self._ql_seen = n
+            raise np.linalg.LinAlgError("Eigenvalues did not converge")
 
     def last_kernel_info(self):
         return _lib.lib().sktb_last_kernel_info().decode()

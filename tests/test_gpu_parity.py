@@ -386,6 +386,7 @@ def test_large_mesh_multi_chunk_pipeline(tb):
     # host front end (sktb_solve_host: chunked H2D / solve / D2H on two streams over the same internal pipeline), all k
     host = ham.solve_kpath(np.ascontiguousarray(kk))
     assert np.array_equal(host, ev.cpu().numpy())
+    assert ham.ql_failures() == 0
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -412,4 +413,10 @@ def test_next_rows_vs_reference_golden(tb):
     np.testing.assert_allclose(h.get_dos(Ew, eig=ev.cpu().numpy(), w=0.07), O.gauss_dos(ev.cpu().numpy(), Ew, 0.07), rtol=1e-10, atol=1e-12)
     v = np.abs(np.random.default_rng(0).standard_normal((4, 3, 6)) + 1j)
     assert np.allclose(tb.Hamiltonian.kproj_weights(v, [1, 4]), np.linalg.norm(v[:, :, [1, 4]], axis=-1))
+
+
+def test_zz_no_ql_failures(tb):
+    """Runs last (file order): none of the eigensolves issued by this module hit the QL iteration limit."""
+    for name, (_, ham) in _ham_cache.items():
+        assert ham.ql_failures() == 0, name
 
