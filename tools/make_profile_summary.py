@@ -7,11 +7,11 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
 out, title, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
 lines = [f"# {title}", ""]
 for rep in reps:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else rep
-    lines += [f"## {kname}", "", f"source report: `{rep}` (scratch, not committed)", "", "| metric | value | unit |", "|---|---:|---|"]
+    lines += [f"## {kname}", "", f"source: `{rep}` (raw metric table of one `ncu --set full` launch; scratch, not committed)", "", "| metric | value | unit |", "|---|---:|---|"]
     for h, u, v in zip(hdr, units, vals):
         if h in KEYS or ('issue_stalled' in h and 'per_issue_active' in h and v and float(v) > 0.05):
             lines.append(f"| {h} | {v} | {u} |")
