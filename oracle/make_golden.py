@@ -159,6 +159,15 @@ def next_rows_fixture(ref):
         tot = quiet(f.get_total_energy, ne, nk=nk, soc=spec["soc"])
         out[name + "_etot"] = np.array(tot, dtype=float)
         out[name + "_etot_args"] = np.array([ne] + nk)
+    # Hamiltonian.total_energy -> utils/energitics.get_totalenergy (ARPACK per k, fanned out with joblib: run the same
+    # calls serially - loky workers cannot import the reference shell)
+    from pysktb.utils import energitics
+    energitics.Parallel = lambda n_jobs=None: (lambda it: [f(*a, **kw) for f, a, kw in it])
+    for name, spec, args in (("C1", W.cubic_sp3(), dict(filled_band=3, nk=3, dim=3)), ("C3", W.sb_buckled(), dict(filled_band=0, nk=4, dim=2)),
+                             ("spchain", W.sp_chain(), dict(filled_band=0, nk=7, dim=1))):   # (N = 2 models: ARPACK needs k < N - 1, the reference raises)
+        st, ham = W.instantiate(spec, ref, ref.scaling)
+        out[name + "_emean"] = np.array(quiet(energitics.get_totalenergy, ham, soc=spec["soc"], **args))
+        out[name + "_emean_args"] = np.array([args["filled_band"], args["nk"], args["dim"]])
     r = np.random.default_rng(7)
     ev = r.standard_normal(57) * 2
     D = 0

@@ -375,3 +375,19 @@ def total_energy_band(model, n_electrons, nk=(10, 10, 10), soc=True):
     n_occ = min(n_occ, ev.shape[0])
     return (1.0 if soc else 2.0) * ev[:n_occ].sum() / len(ks)
 
+
+def total_energy_mean(model, filled_band=0, nk=10, dim=3, soc=True):
+    """hamiltonian.py:319-323 -> utils/energitics.py:26-63: mean of the lowest `neig` eigenvalues (neig = filled_band or
+    int(N/2)) over the endpoint-included mesh linspace(0,1,nk)^dim.  (The reference obtains them with ARPACK eigsh
+    'SR' on the full matrix; for Hermitian H(k) these are the lowest eigenvalues.)"""
+    x = np.linspace(0, 1, int(nk))
+    if dim == 3:
+        ks = [[a, b, c] for a in x for b in x for c in x]
+    elif dim == 2:
+        ks = [[a, b, 0.0] for a in x for b in x]
+    else:
+        ks = [[a, 0.0, 0.0] for a in x]
+    ev = model.solve_kpath(ks, soc=soc)
+    neig = int(filled_band) if filled_band else int(ev.shape[0] / 2)
+    return float(ev[:neig].mean())
+

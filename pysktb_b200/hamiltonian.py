@@ -346,6 +346,40 @@ class Hamiltonian(object):
             res = out.cpu().numpy().reshape(energy.shape)
         return res
 
+    def total_energy(self, filled_band=0, nk=10, dim=3, soc=True):
+        """Mean of the `filled_band` lowest eigenvalues (default: half filling, N // 2) over the endpoint-included mesh
+        linspace(0, 1, nk)^dim (hamiltonian.py:319-323 -> utils/energitics.py:26-63, which asks ARPACK for the lowest
+        eigenvalues per k).  All eigenvalues come from the device solver; the partial sum is reduced on the device
+        (sktb_band_energy).  'Caution for metallic systems: the Fermi level is not calculated' applies as in the reference."""
+        torch = _torch()
+        soc = bool(soc == True)  # noqa: E712
+        x = np.linspace(0, 1, int(nk))
+        if dim == 3:
+            mesh = np.stack(np.meshgrid(x, x, x, indexing="ij"), axis=-1).reshape(-1, 3)
+        elif dim == 2:
+            mesh = np.concatenate([np.stack(np.meshgrid(x, x, indexing="ij"), axis=-1).reshape(-1, 2), np.zeros((int(nk) ** 2, 1))], axis=1)
+        elif dim == 1:
+            mesh = np.concatenate([x.reshape(-1, 1), np.zeros((int(nk), 2))], axis=1)
+        else:
+            raise ValueError("dim must be 1, 2 or 3")
+        N = self._dim(soc)
+        neig = int(filled_band) if filled_band else int(N / 2)
+        neig = max(1, min(neig, N))
+        with torch.cuda.device(self._device):
+            kd = torch.from_numpy(np.ascontiguousarray(mesh)).cuda()
+            ev = torch.empty((N, len(mesh)), dtype=torch.float64, device="cuda")
+            gate = self.asym_bound > 0.5e-9
+            fl = torch.zeros(len(mesh), dtype=torch.int32, device="cuda") if gate else None
+            lib = _lib.lib()
+            _lib.check(lib.sktb_solve(self._plan, kd.data_ptr(), len(mesh), int(soc), ev.data_ptr(), None, len(mesh), 0,
+                                      fl.data_ptr() if gate else None, self._stream()))
+            out = torch.zeros(1, dtype=torch.float64, device="cuda")
+            _lib.check(lib.sktb_band_energy(self._plan, ev.data_ptr(), len(mesh), len(mesh), neig, out.data_ptr(), self._stream()))
+            if gate and bool(fl.any().item()):
+                raise Exception(_NOT_HERMITIAN)
+            total = float(out.cpu()[0])
+        return total / (len(mesh) * neig)
+
     @staticmethod
     def kproj_weights(vecs, index):
         """Projection weights of `plot_kproj` (hamiltonian.py:347-351): ||vecs[band, k, index]||_2, shape (band, k)."""

@@ -406,6 +406,9 @@ def test_next_rows_vs_reference_golden(tb):
         if tag + "_gdos" in g:
             d = h.get_dos(E, w=0.15, nk=[int(x) for x in g[tag + "_gdos_nk"]])
             np.testing.assert_allclose(d, g[tag + "_gdos"], rtol=1e-8, atol=1e-12)
+        if tag + "_emean" in g:
+            fb, nk1, dim = (int(x) for x in g[tag + "_emean_args"])
+            assert abs(h.total_energy(filled_band=fb, nk=nk1, dim=dim, soc=spec["soc"]) - float(g[tag + "_emean"])) < 1e-9
     # larger mesh: oracle Gaussian on device eigenvalues, band energy against a numpy sum
     ev = h.solve_kmesh([7, 5, 3])
     Ew = np.linspace(-1, 1, 300)

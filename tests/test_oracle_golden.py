@@ -127,4 +127,7 @@ def test_next_rows_oracle_vs_reference():
         if tag + "_gdos" in g:
             d = O.get_dos(m, E, w=0.15, nk=[int(x) for x in g[tag + "_gdos_nk"]])
             np.testing.assert_allclose(d, g[tag + "_gdos"], rtol=1e-9, atol=1e-12)
+        if tag + "_emean" in g:                                              # Hamiltonian.total_energy (ARPACK in the reference)
+            fb, nk1, dim = (int(x) for x in g[tag + "_emean_args"])
+            assert abs(O.total_energy_mean(m, fb, nk1, dim, soc=spec["soc"]) - float(g[tag + "_emean"])) < 1e-9
 
