@@ -418,6 +418,18 @@ def test_next_rows_vs_reference_golden(tb):
     assert np.allclose(tb.Hamiltonian.kproj_weights(v, [1, 4]), np.linalg.norm(v[:, :, [1, 4]], axis=-1))
 
 
+def test_ldos_multi_chunk_sums_to_dos(tb):
+    """Eigenvector-based LDOS over several workspace chunks (T: ~60 000 k per chunk, 48^3 = 110 592 k; C4: ~18 000 k per
+    chunk, 28^3 = 21 952 k): the projections on all orbitals of all atoms must add up to the eigenvalue-only DOS."""
+    E = np.linspace(-3.5, 3.5, 57)
+    for name, nk in (("T_ce_spdf_1atom", [48, 48, 48]), ("C4_ce_spdf_2atom", [28, 28, 28])):
+        st, ham = ham_for(tb, name)
+        gf = tb.GreensFunction(ham)
+        ld = gf.ldos(E, atom_indices=list(range(len(st.atoms))), nk=nk, eta=0.05)
+        dos = gf.dos(E, nk=nk, eta=0.05)
+        np.testing.assert_allclose(ld.sum(axis=0), dos, rtol=1e-9)
+
+
 def test_zz_no_ql_failures(tb):
     """Runs last (file order): none of the eigensolves issued by this module hit the QL iteration limit."""
     for name, (_, ham) in _ham_cache.items():
