@@ -33,6 +33,28 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     return 2;
 }
 
+// QL with accumulation for N <= 32: record-and-replay (tqlrec32 + vecapply32, vecql32 only for flagged overflows), or the
+// all-in-one vecql32 when SKTB_VEC_LIST=0.  Region layout after the ranks: lists | dfinal | flags.
+static int launch_vecql32_family(const Vec32Args& v, long long nm, double* zstore, int* rankstore, int sms, cudaStream_t st) {
+    static const bool use_list = !(getenv("SKTB_VEC_LIST") && getenv("SKTB_VEC_LIST")[0] == '0');
+    const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
+    const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nm + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * 5));
+    if (!use_list) {
+        vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore, nullptr);
+        return 1;
+    }
+    double2* lists = reinterpret_cast<double2*>(rankstore + (size_t)nm * 32);
+    double* dfinal = reinterpret_cast<double*>(lists + (size_t)nm * VECREC_CAP);
+    int* flags = reinterpret_cast<int*>(dfinal + (size_t)nm * 32);
+    const size_t smemR = (size_t)SMALL_WARPS * 2 * 32 * DSTRIDE * 8;
+    cudaFuncSetAttribute(tqlrec32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR);
+    const unsigned gridR = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * 3));
+    tqlrec32_kernel<0><<<gridR, SMALL_WARPS * 32, smemR, st>>>(v, dfinal, lists, flags);
+    vecapply32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, dfinal, lists, flags, zstore, rankstore);
+    vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore, flags);
+    return 3;
+}
+
 size_t vec64_bytes_per_k() { return (size_t)128 * 8 + (size_t)C64_VSTORE_CPLX * 16 + 4096 * 8 + 64 * 4; }   // (d,e) | reflectors | Z | ranks
 
 int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
@@ -88,11 +110,10 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     int launches = 1;
     if (evecs) {
         Vec32Args v{a.scratch, vstore, nm, N, evals, evecs, ld, col0, fail};
-        const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nm + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * 5));
-        vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore);
+        launches += launch_vecql32_family(v, nm, zstore, rankstore, sms, st);
         const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>((nm + VEC32_WARPS - 1) / VEC32_WARPS, (long long)sms * 2));
         vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, 0, st>>>(v, zstore, rankstore);
-        launches += 2;
+        launches += 1;
     } else {
         TqlArgs t{a.scratch, nm, N, evals, ld, col0, fail};
         const unsigned gridB = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * 3));
@@ -107,7 +128,7 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     return launches;
 }
 
-size_t vec32_bytes_per_k() { return (size_t)64 * 8 + (size_t)PAIR_VSTORE_CPLX * 16 + 1024 * 8 + 32 * 4; }   // (d,e) | reflectors | Z | ranks
+size_t vec32_bytes_per_k() { return (size_t)64 * 8 + (size_t)PAIR_VSTORE_CPLX * 16 + 1024 * 8 + 32 * 4 + (size_t)VECREC_CAP * 16 + 32 * 8 + 16; }   // (d,e) | reflectors | Z | ranks | rotation list | d final | flag
 
 int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N, double* evals,
                  cplx* evecs, long long ld, long long col0, int* flags, long long flag_off, int* fail, void* scratch, cudaStream_t st,
@@ -139,7 +160,7 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, nullptr, vstore);
     Vec32Args v{a.scratch, vstore, nk, N, evals, evecs, ld, col0, fail};
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nk + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * occQ));
-    vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore);
+    const int nq = launch_vecql32_family(v, nk, zstore, rankstore, sms, st);
     const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>((nk + VEC32_WARPS - 1) / VEC32_WARPS, (long long)sms * occV));
     vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, 0, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }

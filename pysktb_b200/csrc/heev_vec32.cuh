@@ -60,7 +60,8 @@ __device__ __forceinline__ void vec32_all_phases(cplx (&u)[32], const cplx* vst,
 //      Writes the sorted eigenvalues and Z (column n = eigenvector n of T, [32][32] doubles, 8 KB per k) + ranks.
 constexpr int VECQL_WARPS = 4;
 template <int UNUSED>
-__global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecql32_kernel(Vec32Args a, double* __restrict__ zstore, int* __restrict__ rankstore) {
+__global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecql32_kernel(Vec32Args a, double* __restrict__ zstore, int* __restrict__ rankstore,
+                                                                       const int* __restrict__ only_flagged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Z = reinterpret_cast<double*>(smem_raw) + (size_t)warp * VEC32_SMEM_DOUBLES;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecql32_kernel(Vec32Args 
     const double eps = 2.220446049250313e-16;
 #pragma unroll 1
     for (long long kq = (long long)blockIdx.x * VECQL_WARPS + warp; kq < a.nk; kq += (long long)gridDim.x * VECQL_WARPS) {
+        if (only_flagged && !only_flagged[kq]) continue;              // fallback pass after tqlrec32 / vecapply32
         d[lane] = a.de[(size_t)kq * 64 + lane];
         e[lane] = (lane < n - 1) ? a.de[(size_t)kq * 64 + 32 + lane] : 0.0;
 #pragma unroll 4
@@ -160,3 +162,177 @@ __global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vecbt32_kernel(Vec32Args 
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// QL with accumulation without repeating the scalar recurrence on 32 lanes (vecql32 spends its FP64 issue slots on
+// that):  tqlrec32 runs the eigenvalue-only QL of tql_small (one matrix per LANE) and records every rotation
+// (c, s) sweep by sweep in a per-matrix list in global memory;  vecapply32 (one matrix per WARP, lane = row of Z)
+// replays the list on Z in shared memory: 1 broadcast load, 1 LDS, 1 STS and 4 FP64 per rotation.
+// List format (16-byte entries): sweep header {m, count} followed by count rotations {c, s} for i = m-1, m-2, ...;
+// terminator {-1, 0}.  A matrix whose list would overflow VECREC_CAP is flagged and redone by vecql32_kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int VECREC_CAP = 2048;
+
+SKTB_D int tql_lane_rec(double* d, double* e, int n, double2* list, int& ovf) {
+    const double eps = 2.220446049250313e-16;
+#define D_(i) d[(i) * DSTRIDE]
+#define E_(i) e[(i) * DSTRIDE]
+    E_(n - 1) = 0.0;
+    int fail = 0, l = 0, iter = 0, pos = 0;
+    bool rec = true;
+    int m = tql_scan(d, e, 0, n);
+    while (true) {
+        if (m == l || iter > 80) {
+            if (m != l) fail = 1;
+            ++l; iter = 0;
+            if (l >= n) break;
+            m = tql_scan(d, e, l, n);
+            continue;
+        }
+        ++iter;
+        if (rec && pos + (m - l) + 2 > VECREC_CAP) { rec = false; ovf = 1; }
+        const int hp = pos;
+        if (rec) ++pos;
+        double el = E_(l), dl = D_(l);
+        double g = (D_(l + 1) - dl) / (2.0 * el);
+        double r = sqrt(fma(g, g, 1.0));
+        g = D_(m) - dl + el / (g + (g >= 0.0 ? r : -r));
+        double s = 1.0, c = 1.0, p = 0.0;
+        bool under = false;
+        double di1 = D_(m);
+        double dnext = 0.0;
+        int mb = m;
+        int done = 0;
+        for (int i = m - 1; i >= l; --i) {
+            double ei = E_(i), di = D_(i);
+            double f = s * ei, b = c * ei;
+            double h2 = fma(f, f, g * g);
+            if (h2 == 0.0) { E_(i + 1) = 0.0; D_(i + 1) = di1 - p; E_(m) = 0.0; under = true; break; }
+            double ir = rsqrt(h2);
+            r = h2 * ir;
+            s = f * ir; c = g * ir;
+            if (rec) list[pos++] = make_double2(c, s);
+            ++done;
+            g = di1 - p;
+            double rr = fma(di - g, s, 2.0 * c * b);
+            p = s * rr;
+            double dnew = g + p;
+            D_(i + 1) = dnew;
+            double an = fabs(dnew);
+            if (i + 1 < m) {
+                E_(i + 1) = r;
+                if (r <= eps * (an + dnext)) mb = i + 1;
+            }
+            dnext = an;
+            g = fma(c, rr, -b);
+            di1 = di;
+        }
+        if (rec) list[hp] = make_double2((double)m, (double)done);
+        if (under) { m = tql_scan(d, e, l, n); continue; }
+        double dl_new = di1 - p;
+        D_(l) = dl_new; E_(l) = g; E_(m) = 0.0;
+        if (fabs(g) <= eps * (fabs(dl_new) + dnext)) { ++l; iter = 0; }
+        m = mb;
+    }
+    if (rec) list[pos] = make_double2(-1.0, 0.0);
+#undef D_
+#undef E_
+    return fail;
+}
+
+// one tridiagonal matrix per lane (as tql_small_kernel); writes the final (unsorted) d, the rotation list, the flag
+template <int UNUSED>
+__global__ void __launch_bounds__(SMALL_WARPS * 32) tqlrec32_kernel(Vec32Args a, double* __restrict__ dfinal, double2* __restrict__ lists,
+                                                                     int* __restrict__ ovf_flag) {
+    constexpr int NC = 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* dbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * NC * DSTRIDE;
+    double* ebuf = dbuf + NC * DSTRIDE;
+    const long long n_batches = (a.nk + 31) / 32;
+    const long long gwarp = (long long)blockIdx.x * SMALL_WARPS + warp, nwarps = (long long)gridDim.x * SMALL_WARPS;
+#pragma unroll 1
+    for (long long batch = gwarp; batch < n_batches; batch += nwarps) {
+        const long long kbase = batch * 32;
+        const int cnt = (int)min((long long)32, a.nk - kbase);
+        const long long kq = kbase + min(lane, cnt - 1);
+        {
+            const double2* src = reinterpret_cast<const double2*>(a.de + (size_t)kq * (2 * NC));
+#pragma unroll
+            for (int t = 0; t < NC / 2; ++t) {
+                const double2 v = src[t];
+                dbuf[(2 * t) * DSTRIDE + lane] = v.x; dbuf[(2 * t + 1) * DSTRIDE + lane] = v.y;
+            }
+#pragma unroll
+            for (int t = 0; t < NC / 2; ++t) {
+                const double2 v = src[NC / 2 + t];
+                ebuf[(2 * t) * DSTRIDE + lane] = v.x; ebuf[(2 * t + 1) * DSTRIDE + lane] = v.y;
+            }
+        }
+        __syncwarp();
+        int ovf = 0;
+        double2* list = lists + (size_t)kq * VECREC_CAP;
+        const int bad = tql_lane_rec(dbuf + lane, ebuf + lane, a.N, list, ovf);
+        if (bad) atomicAdd(a.fail, 1);
+        if (lane < cnt) {
+            ovf_flag[kq] = ovf;
+#pragma unroll 4
+            for (int q = 0; q < NC; ++q) dfinal[(size_t)kq * NC + q] = dbuf[q * DSTRIDE + lane];
+        }
+        __syncwarp();
+    }
+}
+
+// one matrix per warp, lane = row of Z: replay the rotation list, then ranks / eigenvalues / Z^T exactly as vecql32
+template <int UNUSED>
+__global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecapply32_kernel(Vec32Args a, const double* __restrict__ dfinal, const double2* __restrict__ lists,
+                                                                          const int* __restrict__ ovf_flag, double* __restrict__ zstore,
+                                                                          int* __restrict__ rankstore) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Z = reinterpret_cast<double*>(smem_raw) + (size_t)warp * VEC32_SMEM_DOUBLES;
+    double* d = Z + 32 * VEC32_ZSTRIDE;
+    const int n = a.N;
+#pragma unroll 1
+    for (long long kq = (long long)blockIdx.x * VECQL_WARPS + warp; kq < a.nk; kq += (long long)gridDim.x * VECQL_WARPS) {
+        if (ovf_flag[kq]) continue;                                   // redone by vecql32_kernel
+        d[lane] = dfinal[(size_t)kq * 32 + lane];
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) Z[c * VEC32_ZSTRIDE + lane] = (c == lane) ? 1.0 : 0.0;
+        __syncwarp();
+        const double2* list = lists + (size_t)kq * VECREC_CAP;
+        int pos = 0;
+#pragma unroll 1
+        while (true) {
+            const double2 hdr = list[pos];
+            const int m = (int)hdr.x, count = (int)hdr.y;
+            if (m < 0) break;
+            ++pos;
+            double up = Z[m * VEC32_ZSTRIDE + lane];                  // running value of column i+1
+#pragma unroll 4
+            for (int t = 0; t < count; ++t) {
+                const double2 cs = list[pos + t];
+                const int i = m - 1 - t;
+                const double g = Z[i * VEC32_ZSTRIDE + lane];
+                Z[(i + 1) * VEC32_ZSTRIDE + lane] = fma(cs.y, g, cs.x * up);
+                up = fma(cs.x, g, -cs.y * up);
+            }
+            if (count > 0) Z[(m - count) * VEC32_ZSTRIDE + lane] = up;
+            pos += count;
+        }
+        __syncwarp();
+        const double mine = (lane < n) ? d[lane] : 0.0;
+        int rank = 0;
+        for (int q = 0; q < n; ++q) {
+            const double o = d[q];
+            rank += (o < mine || (o == mine && q < lane)) ? 1 : 0;
+        }
+        if (lane < n) a.evals[(long long)rank * a.ld + a.col0 + kq] = mine;
+        rankstore[(size_t)kq * 32 + lane] = rank;
+        double* zs = zstore + (size_t)kq * 1024;
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) zs[c * 32 + lane] = Z[lane * VEC32_ZSTRIDE + c];
+        __syncwarp();
+    }
+}
+
