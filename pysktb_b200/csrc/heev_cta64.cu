@@ -35,6 +35,12 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
 
 // QL with accumulation for N <= 32: record-and-replay (tqlrec32 + vecapply32, vecql32 only for flagged overflows), or the
 // all-in-one vecql32 when SKTB_VEC_LIST=0.  Region layout after the ranks: lists | dfinal | flags.
+static const size_t smemBT = (size_t)VEC32_WARPS * PAIR_VSTORE_CPLX * 16;      // vecbt32: reflectors of one matrix per warp
+static bool vecbt32_smem_ok() {
+    static const bool ok = cudaFuncSetAttribute(vecbt32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBT) == cudaSuccess;
+    return ok;
+}
+
 static int launch_vecql32_family(const Vec32Args& v, long long nm, double* zstore, int* rankstore, int sms, cudaStream_t st) {
     static const bool use_list = !(getenv("SKTB_VEC_LIST") && getenv("SKTB_VEC_LIST")[0] == '0');
     const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
@@ -110,9 +116,10 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     int launches = 1;
     if (evecs) {
         Vec32Args v{a.scratch, vstore, nm, N, evals, evecs, ld, col0, fail};
+        if (!vecbt32_smem_ok()) { *info = "cudaFuncSetAttribute(vecbt32) failed"; return -1; }
         launches += launch_vecql32_family(v, nm, zstore, rankstore, sms, st);
         const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>((nm + VEC32_WARPS - 1) / VEC32_WARPS, (long long)sms * 2));
-        vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, 0, st>>>(v, zstore, rankstore);
+        vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, smemBT, st>>>(v, zstore, rankstore);
         launches += 1;
     } else {
         TqlArgs t{a.scratch, nm, N, evals, ld, col0, fail};
@@ -154,7 +161,8 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occW, kW, PAIR_WARPS * 32, smemW);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, vecql32_kernel<0>, VECQL_WARPS * 32, smemQ);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occV, vecbt32_kernel<0>, VEC32_WARPS * 32, 0);
+    if (!vecbt32_smem_ok()) { *info = "cudaFuncSetAttribute(vecbt32) failed"; return -1; }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occV, vecbt32_kernel<0>, VEC32_WARPS * 32, smemBT);
     if (occW < 1 || occQ < 1 || occV < 1) { *info = "vec32 kernels do not fit (smem " + std::to_string(smemW) + ")"; return -1; }
     const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nk + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * occW));
     kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, nullptr, vstore);
@@ -162,7 +170,7 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nk + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * occQ));
     const int nq = launch_vecql32_family(v, nk, zstore, rankstore, sms, st);
     const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>((nk + VEC32_WARPS - 1) / VEC32_WARPS, (long long)sms * occV));
-    vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, 0, st>>>(v, zstore, rankstore);
+    vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, smemBT, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[320];
     snprintf(buf, sizeof buf, "pair_wide32<soc=%d,full,vec> grid=%u x %d thr smem=%zuB %d CTA/SM + vecql32 grid=%u smem=%zuB %d CTA/SM + vecbt32 grid=%u %d CTA/SM; N=%d",

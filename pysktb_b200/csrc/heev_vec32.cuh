@@ -16,7 +16,7 @@
 
 constexpr int VEC32_ZSTRIDE = 33;
 constexpr int VEC32_WARPS = 4;
-constexpr int VEC32_SMEM_DOUBLES = 32 * VEC32_ZSTRIDE + 64;      // Z | d | e   per warp
+constexpr int VEC32_SMEM_DOUBLES = 32 * VEC32_ZSTRIDE + 32 + 128;      // Z | d | e (vecql32) or rotation windows [2][32] x 16 B (vecapply32)   per warp
 
 struct Vec32Args {
     const double* de;        // [nk][2][32]
@@ -143,17 +143,23 @@ __global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecql32_kernel(Vec32Args 
 // ---- kernel 2: back-transformation, lane = eigenvector (128 registers of components)
 template <int UNUSED>
 __global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vecbt32_kernel(Vec32Args a, const double* __restrict__ zstore, const int* __restrict__ rankstore) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    cplx* vsm = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * PAIR_VSTORE_CPLX;     // this warp's reflectors + tau (16.5 KB)
     const int n = a.N;
 #pragma unroll 1
     for (long long kq = (long long)blockIdx.x * VEC32_WARPS + warp; kq < a.nk; kq += (long long)gridDim.x * VEC32_WARPS) {
+        const cplx* vst = a.vstore + (size_t)kq * PAIR_VSTORE_CPLX;
+        __syncwarp();
+#pragma unroll 11
+        for (int t = 0; t < PAIR_VSTORE_CPLX / 32; ++t) vsm[t * 32 + lane] = vst[t * 32 + lane];   // coalesced, 33 loads in flight
         const double* zs = zstore + (size_t)kq * 1024;
         cplx u[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) u[i] = cmake((lane < n && i < n) ? zs[i * 32 + lane] : 0.0, 0.0);
         const int rank = rankstore[(size_t)kq * 32 + lane];
-        const cplx* vst = a.vstore + (size_t)kq * PAIR_VSTORE_CPLX;
-        vec32_all_phases(u, vst, vst + 1024, n);
+        __syncwarp();
+        vec32_all_phases(u, vsm, vsm + 1024, n);
         if (lane < n) {
             cplx* out = a.evecs + (size_t)((long long)rank * a.ld + a.col0 + kq) * n;
 #pragma unroll
@@ -300,25 +306,33 @@ __global__ void __launch_bounds__(VECQL_WARPS * 32, 5) vecapply32_kernel(Vec32Ar
 #pragma unroll 4
         for (int c = 0; c < 32; ++c) Z[c * VEC32_ZSTRIDE + lane] = (c == lane) ? 1.0 : 0.0;
         __syncwarp();
+        // A sweep is a header plus at most 31 rotations: one coalesced 512-byte window (entry pos + lane per lane) holds
+        // it.  The window of the NEXT sweep is requested as soon as this sweep's header is known and lands in the other
+        // half of the double buffer while the rotations below run from shared memory (broadcast reads).
         const double2* list = lists + (size_t)kq * VECREC_CAP;
-        int pos = 0;
+        double2* win = reinterpret_cast<double2*>(d + 32);            // [2][32] entries behind d
+        int pos = 0, cur = 0;
+        double2 pre = list[min(pos + lane, VECREC_CAP - 1)];
 #pragma unroll 1
         while (true) {
-            const double2 hdr = list[pos];
+            win[cur * 32 + lane] = pre;
+            __syncwarp();
+            const double2 hdr = win[cur * 32];
             const int m = (int)hdr.x, count = (int)hdr.y;
             if (m < 0) break;
-            ++pos;
+            pos += 1 + count;
+            pre = list[min(pos + lane, VECREC_CAP - 1)];              // prefetch the next window
             double up = Z[m * VEC32_ZSTRIDE + lane];                  // running value of column i+1
 #pragma unroll 4
             for (int t = 0; t < count; ++t) {
-                const double2 cs = list[pos + t];
+                const double2 cs = win[cur * 32 + 1 + t];
                 const int i = m - 1 - t;
                 const double g = Z[i * VEC32_ZSTRIDE + lane];
                 Z[(i + 1) * VEC32_ZSTRIDE + lane] = fma(cs.y, g, cs.x * up);
                 up = fma(cs.x, g, -cs.y * up);
             }
             if (count > 0) Z[(m - count) * VEC32_ZSTRIDE + lane] = up;
-            pos += count;
+            cur ^= 1;
         }
         __syncwarp();
         const double mine = (lane < n) ? d[lane] : 0.0;
