@@ -53,15 +53,15 @@ static int launch_vecql32_family(const Vec32Args& v, long long nm, double* zstor
     double* dfinal = reinterpret_cast<double*>(lists + (size_t)nm * VECREC_CAP);
     int* flags = reinterpret_cast<int*>(dfinal + (size_t)nm * 32);
     const size_t smemR = (size_t)SMALL_WARPS * 2 * 32 * DSTRIDE * 8;
-    cudaFuncSetAttribute(tqlrec32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR);
+    cudaFuncSetAttribute(tqlrec_kernel<32, VECREC_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR);
     const unsigned gridR = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * 3));
-    tqlrec32_kernel<0><<<gridR, SMALL_WARPS * 32, smemR, st>>>(v, dfinal, lists, flags);
+    tqlrec_kernel<32, VECREC_CAP><<<gridR, SMALL_WARPS * 32, smemR, st>>>(TqlRecArgs{v.de, nm, v.N, v.fail}, dfinal, lists, flags);
     vecapply32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, dfinal, lists, flags, zstore, rankstore);
     vecql32_kernel<0><<<gridQ, VECQL_WARPS * 32, smemQ, st>>>(v, zstore, rankstore, flags);
     return 3;
 }
 
-size_t vec64_bytes_per_k() { return (size_t)128 * 8 + (size_t)C64_VSTORE_CPLX * 16 + 4096 * 8 + 64 * 4; }   // (d,e) | reflectors | Z | ranks
+size_t vec64_bytes_per_k() { return (size_t)128 * 8 + (size_t)C64_VSTORE_CPLX * 16 + 4096 * 8 + 64 * 4 + (size_t)VECREC64_CAP * 16 + 64 * 8 + 16; }   // (d,e) | reflectors | Z | ranks | rotation list | d final | flag
 
 int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
                  cudaStream_t st, std::string* info) {
@@ -82,7 +82,23 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     tridiag_cta64_kernel<0><<<gridA, C64_THREADS, 0, st>>>(a);
     Vec64Args v{de, vstore, nm, N, evals, evecs, ld, col0, fail};
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occQ));
-    vecql64_kernel<0><<<gridQ, 32, smemQ, st>>>(v, zstore, rankstore);
+    static const bool use_list = !(getenv("SKTB_VEC_LIST") && getenv("SKTB_VEC_LIST")[0] == '0');
+    int nql = 1;
+    if (!use_list) vecql64_kernel<0><<<gridQ, 32, smemQ, st>>>(v, zstore, rankstore, nullptr);
+    else {
+        double2* lists = reinterpret_cast<double2*>(rankstore + (size_t)nm * 64);
+        double* dfinal = reinterpret_cast<double*>(lists + (size_t)nm * VECREC64_CAP);
+        int* flags = reinterpret_cast<int*>(dfinal + (size_t)nm * 64);
+        const size_t smemR = (size_t)SMALL_WARPS * 2 * 64 * DSTRIDE * 8, smemP = (size_t)VECAPPLY64_SMEM_DOUBLES * 8;
+        if (cudaFuncSetAttribute(tqlrec_kernel<64, VECREC64_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR) != cudaSuccess) {
+            *info = "cudaFuncSetAttribute(tqlrec64) failed"; return -1;
+        }
+        const unsigned gridR = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms));
+        tqlrec_kernel<64, VECREC64_CAP><<<gridR, SMALL_WARPS * 32, smemR, st>>>(TqlRecArgs{de, nm, N, fail}, dfinal, lists, flags);
+        vecapply64_kernel<0><<<gridQ, 32, smemP, st>>>(v, dfinal, lists, flags, zstore, rankstore);
+        vecql64_kernel<0><<<gridQ, 32, smemQ, st>>>(v, zstore, rankstore, flags);
+        nql = 3;
+    }
     const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * 2));
     vecbt64_kernel<0><<<gridV, 128, 0, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
@@ -90,7 +106,7 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     snprintf(buf, sizeof buf, "tridiag_cta64<vec> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d", gridA, C64_THREADS,
              occA, gridQ, smemQ, occQ, gridV, N);
     *info = buf;
-    return 3;
+    return 2 + nql;
 }
 
 int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,

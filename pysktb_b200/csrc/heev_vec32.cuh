@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(VEC32_WARPS * 32, 2) vecbt32_kernel(Vec32Args 
 // ---------------------------------------------------------------------------------------------------------
 constexpr int VECREC_CAP = 2048;
 
-SKTB_D int tql_lane_rec(double* d, double* e, int n, double2* list, int& ovf) {
+SKTB_D int tql_lane_rec(double* d, double* e, int n, double2* list, const int cap, int& ovf) {
     const double eps = 2.220446049250313e-16;
 #define D_(i) d[(i) * DSTRIDE]
 #define E_(i) e[(i) * DSTRIDE]
@@ -196,7 +196,7 @@ SKTB_D int tql_lane_rec(double* d, double* e, int n, double2* list, int& ovf) {
             continue;
         }
         ++iter;
-        if (rec && pos + (m - l) + 2 > VECREC_CAP) { rec = false; ovf = 1; }
+        if (rec && pos + (m - l) + 2 > cap) { rec = false; ovf = 1; }
         const int hp = pos;
         if (rec) ++pos;
         double el = E_(l), dl = D_(l);
@@ -247,10 +247,12 @@ SKTB_D int tql_lane_rec(double* d, double* e, int n, double2* list, int& ovf) {
 }
 
 // one tridiagonal matrix per lane (as tql_small_kernel); writes the final (unsorted) d, the rotation list, the flag
-template <int UNUSED>
-__global__ void __launch_bounds__(SMALL_WARPS * 32) tqlrec32_kernel(Vec32Args a, double* __restrict__ dfinal, double2* __restrict__ lists,
-                                                                     int* __restrict__ ovf_flag) {
-    constexpr int NC = 32;
+struct TqlRecArgs {
+    const double* de; long long nk; int N; int* fail;     // (d, e) scratch [nk][2][NC]
+};
+template <int NC, int CAP>
+__global__ void __launch_bounds__(SMALL_WARPS * 32) tqlrec_kernel(TqlRecArgs a, double* __restrict__ dfinal, double2* __restrict__ lists,
+                                                                   int* __restrict__ ovf_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* dbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * NC * DSTRIDE;
@@ -277,8 +279,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tqlrec32_kernel(Vec32Args a,
         }
         __syncwarp();
         int ovf = 0;
-        double2* list = lists + (size_t)kq * VECREC_CAP;
-        const int bad = tql_lane_rec(dbuf + lane, ebuf + lane, a.N, list, ovf);
+        double2* list = lists + (size_t)kq * CAP;
+        const int bad = tql_lane_rec(dbuf + lane, ebuf + lane, a.N, list, CAP, ovf);
         if (bad) atomicAdd(a.fail, 1);
         if (lane < cnt) {
             ovf_flag[kq] = ovf;

@@ -19,7 +19,8 @@ struct Vec64Args {
 };
 
 template <int UNUSED>
-__global__ void __launch_bounds__(32) vecql64_kernel(Vec64Args a, double* __restrict__ zstore, int* __restrict__ rankstore) {
+__global__ void __launch_bounds__(32) vecql64_kernel(Vec64Args a, double* __restrict__ zstore, int* __restrict__ rankstore,
+                                                      const int* __restrict__ only_flagged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     double* Z = reinterpret_cast<double*>(smem_raw);
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(32) vecql64_kernel(Vec64Args a, double* __rest
     const double eps = 2.220446049250313e-16;
 #pragma unroll 1
     for (long long kq = blockIdx.x; kq < a.nk; kq += gridDim.x) {
+        if (only_flagged && !only_flagged[kq]) continue;
         for (int t = lane; t < 64; t += 32) {
             d[t] = a.de[(size_t)kq * 128 + t];
             e[t] = (t < n - 1) ? a.de[(size_t)kq * 128 + 64 + t] : 0.0;
@@ -160,3 +162,73 @@ __global__ void __launch_bounds__(128, 2) vecbt64_kernel(Vec64Args a, const doub
         }
     }
 }
+
+// Record-and-replay QL for 32 < N <= 64 (see heev_vec32.cuh): tqlrec_kernel<64, VECREC64_CAP> records, this kernel
+// replays on Z (one matrix per warp, lane r owns rows r and r+32; a sweep = header + at most 63 rotations = one
+// 64-entry window, double-buffered); flagged overflows are redone by vecql64_kernel.
+constexpr int VECREC64_CAP = 8192;
+constexpr int VECAPPLY64_SMEM_DOUBLES = 64 * VEC64_ZSTRIDE + 64 + 2 * 64 * 2;      // Z | d | windows [2][64] x 16 B
+
+template <int UNUSED>
+__global__ void __launch_bounds__(32) vecapply64_kernel(Vec64Args a, const double* __restrict__ dfinal, const double2* __restrict__ lists,
+                                                         const int* __restrict__ ovf_flag, double* __restrict__ zstore, int* __restrict__ rankstore) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    double* Z = reinterpret_cast<double*>(smem_raw);
+    double* d = Z + 64 * VEC64_ZSTRIDE;
+    double2* win = reinterpret_cast<double2*>(d + 64);
+    const int n = a.N;
+#pragma unroll 1
+    for (long long kq = blockIdx.x; kq < a.nk; kq += gridDim.x) {
+        if (ovf_flag[kq]) continue;
+        d[lane] = dfinal[(size_t)kq * 64 + lane]; d[lane + 32] = dfinal[(size_t)kq * 64 + lane + 32];
+#pragma unroll 4
+        for (int c = 0; c < 64; ++c) { Z[c * VEC64_ZSTRIDE + lane] = (c == lane) ? 1.0 : 0.0; Z[c * VEC64_ZSTRIDE + lane + 32] = (c == lane + 32) ? 1.0 : 0.0; }
+        __syncwarp();
+        const double2* list = lists + (size_t)kq * VECREC64_CAP;
+        int pos = 0, cur = 0;
+        double2 pre0 = list[min(pos + lane, VECREC64_CAP - 1)], pre1 = list[min(pos + lane + 32, VECREC64_CAP - 1)];
+#pragma unroll 1
+        while (true) {
+            win[cur * 64 + lane] = pre0; win[cur * 64 + lane + 32] = pre1;
+            __syncwarp();
+            const double2 hdr = win[cur * 64];
+            const int m = (int)hdr.x, count = (int)hdr.y;
+            if (m < 0) break;
+            pos += 1 + count;
+            pre0 = list[min(pos + lane, VECREC64_CAP - 1)]; pre1 = list[min(pos + lane + 32, VECREC64_CAP - 1)];
+            double upa = Z[m * VEC64_ZSTRIDE + lane], upb = Z[m * VEC64_ZSTRIDE + lane + 32];
+#pragma unroll 4
+            for (int t = 0; t < count; ++t) {
+                const double2 cs = win[cur * 64 + 1 + t];
+                const int i = m - 1 - t;
+                const double ga = Z[i * VEC64_ZSTRIDE + lane], gb = Z[i * VEC64_ZSTRIDE + lane + 32];
+                Z[(i + 1) * VEC64_ZSTRIDE + lane] = fma(cs.y, ga, cs.x * upa);
+                Z[(i + 1) * VEC64_ZSTRIDE + lane + 32] = fma(cs.y, gb, cs.x * upb);
+                upa = fma(cs.x, ga, -cs.y * upa);
+                upb = fma(cs.x, gb, -cs.y * upb);
+            }
+            if (count > 0) { Z[(m - count) * VEC64_ZSTRIDE + lane] = upa; Z[(m - count) * VEC64_ZSTRIDE + lane + 32] = upb; }
+            cur ^= 1;
+        }
+        __syncwarp();
+        for (int t = lane; t < 64; t += 32) {
+            const double mine = (t < n) ? d[t] : 0.0;
+            int rank = 0;
+            for (int q = 0; q < n; ++q) {
+                const double o = d[q];
+                rank += (o < mine || (o == mine && q < t)) ? 1 : 0;
+            }
+            if (t < n) a.evals[(long long)rank * a.ld + a.col0 + kq] = mine;
+            rankstore[(size_t)kq * 64 + t] = rank;
+        }
+        double* zs = zstore + (size_t)kq * 4096;
+#pragma unroll 2
+        for (int c = 0; c < 64; ++c) {
+            zs[c * 64 + lane] = Z[lane * VEC64_ZSTRIDE + c];
+            zs[c * 64 + lane + 32] = Z[(lane + 32) * VEC64_ZSTRIDE + c];
+        }
+        __syncwarp();
+    }
+}
+
