@@ -100,7 +100,11 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
         nql = 3;
     }
     const unsigned gridV = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * 2));
-    vecbt64_kernel<0><<<gridV, 128, 0, st>>>(v, zstore, rankstore);
+    const size_t smemV64 = (size_t)C64_VSTORE_CPLX * 16;
+    if (cudaFuncSetAttribute(vecbt64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV64) != cudaSuccess) {
+        *info = "cudaFuncSetAttribute(vecbt64) failed"; return -1;
+    }
+    vecbt64_kernel<0><<<gridV, 128, smemV64, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[256];
     snprintf(buf, sizeof buf, "tridiag_cta64<vec> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d", gridA, C64_THREADS,

@@ -135,25 +135,31 @@ SKTB_D void vec64_backtransform4(cplx (&u)[32], const cplx* __restrict__ vst, co
 
 template <int UNUSED>
 __global__ void __launch_bounds__(128, 2) vecbt64_kernel(Vec64Args a, const double* __restrict__ zstore, const int* __restrict__ rankstore) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* vsm = reinterpret_cast<cplx*>(smem_raw);                      // this matrix's reflectors + tau (65 KB), staged coalesced
     const int t = threadIdx.x, nvec = t >> 1, h = t & 1;
     const int n = a.N;
 #pragma unroll 1
     for (long long kq = blockIdx.x; kq < a.nk; kq += gridDim.x) {
+        const cplx* vst = a.vstore + (size_t)kq * C64_VSTORE_CPLX;
+        __syncthreads();
+#pragma unroll 8
+        for (int q = t; q < C64_VSTORE_CPLX; q += 128) vsm[q] = vst[q];
         const double* zs = zstore + (size_t)kq * 4096;
         cplx u[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) u[i] = cmake((nvec < n && 32 * h + i < n) ? zs[(32 * h + i) * 64 + nvec] : 0.0, 0.0);
         const int rank = rankstore[(size_t)kq * 64 + nvec];
-        const cplx* vst = a.vstore + (size_t)kq * C64_VSTORE_CPLX;
-        const cplx* taust = vst + 4096;
-        vec64_backtransform4<60>(u, vst, taust, n, h); vec64_backtransform4<56>(u, vst, taust, n, h);
-        vec64_backtransform4<52>(u, vst, taust, n, h); vec64_backtransform4<48>(u, vst, taust, n, h);
-        vec64_backtransform4<44>(u, vst, taust, n, h); vec64_backtransform4<40>(u, vst, taust, n, h);
-        vec64_backtransform4<36>(u, vst, taust, n, h); vec64_backtransform4<32>(u, vst, taust, n, h);
-        vec64_backtransform4<28>(u, vst, taust, n, h); vec64_backtransform4<24>(u, vst, taust, n, h);
-        vec64_backtransform4<20>(u, vst, taust, n, h); vec64_backtransform4<16>(u, vst, taust, n, h);
-        vec64_backtransform4<12>(u, vst, taust, n, h); vec64_backtransform4<8>(u, vst, taust, n, h);
-        vec64_backtransform4<4>(u, vst, taust, n, h); vec64_backtransform4<0>(u, vst, taust, n, h);
+        __syncthreads();
+        const cplx* taust = vsm + 4096;
+        vec64_backtransform4<60>(u, vsm, taust, n, h); vec64_backtransform4<56>(u, vsm, taust, n, h);
+        vec64_backtransform4<52>(u, vsm, taust, n, h); vec64_backtransform4<48>(u, vsm, taust, n, h);
+        vec64_backtransform4<44>(u, vsm, taust, n, h); vec64_backtransform4<40>(u, vsm, taust, n, h);
+        vec64_backtransform4<36>(u, vsm, taust, n, h); vec64_backtransform4<32>(u, vsm, taust, n, h);
+        vec64_backtransform4<28>(u, vsm, taust, n, h); vec64_backtransform4<24>(u, vsm, taust, n, h);
+        vec64_backtransform4<20>(u, vsm, taust, n, h); vec64_backtransform4<16>(u, vsm, taust, n, h);
+        vec64_backtransform4<12>(u, vsm, taust, n, h); vec64_backtransform4<8>(u, vsm, taust, n, h);
+        vec64_backtransform4<4>(u, vsm, taust, n, h); vec64_backtransform4<0>(u, vsm, taust, n, h);
         if (nvec < n) {
             cplx* out = a.evecs + (size_t)((long long)rank * a.ld + a.col0 + kq) * n + 32 * h;
 #pragma unroll
