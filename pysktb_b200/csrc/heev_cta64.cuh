@@ -214,18 +214,20 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
         const cplx* H = a.H + (size_t)km * N * N;
         if (a.vstore) { S.vst = a.vstore + (size_t)km * C64_VSTORE_CPLX; S.taust = S.vst + 4096; }
         cplx B[2][16];
+        // branch-free: the address of the lower-triangle element is clamped, all 32 loads are independent and in flight
+        // together; conjugation / real diagonal / zero padding are applied to the loaded value
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int i = s ? L.iB : L.iA;
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 const int col = 4 * m + L.h;
-                cplx e = cmake(0.0, 0.0);
-                if (i < N && col < N) {
-                    if (col < i) e = H[(size_t)i * N + col];
-                    else if (col > i) e = cconj(H[(size_t)col * N + i]);
-                    else e = cmake(H[(size_t)i * N + i].x, 0.0);
-                }
+                const bool ok = i < N && col < N;
+                const int hi = ok ? max(i, col) : 0, lo = ok ? min(i, col) : 0;
+                cplx e = H[(size_t)hi * N + lo];
+                if (col > i) e.y = -e.y;
+                if (col == i) e.y = 0.0;
+                if (!ok) e = cmake(0.0, 0.0);
                 B[s][m] = e;
             }
         }

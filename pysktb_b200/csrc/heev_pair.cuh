@@ -388,14 +388,14 @@ SKTB_D void pair_load(cplx (&B)[2][16], const cplx* __restrict__ H, const int N,
     for (int s = 0; s < 2; ++s) {
         const int i = s ? L.iB : L.iA;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
+        for (int m = 0; m < 16; ++m) {                    // branch-free (clamped address): 32 independent loads
             const int col = 2 * m + L.h;
-            cplx e = cmake(0.0, 0.0);
-            if (i < N && col < N) {
-                if (col < i) e = H[(size_t)i * N + col];
-                else if (col > i) e = cconj(H[(size_t)col * N + i]);
-                else e = cmake(H[(size_t)i * N + i].x, 0.0);
-            }
+            const bool ok = i < N && col < N;
+            const int hi = ok ? max(i, col) : 0, lo = ok ? min(i, col) : 0;
+            cplx e = H[(size_t)hi * N + lo];
+            if (col > i) e.y = -e.y;
+            if (col == i) e.y = 0.0;
+            if (!ok) e = cmake(0.0, 0.0);
             B[s][m] = e;
         }
     }
