@@ -4,10 +4,16 @@
 namespace sktb {
 namespace small {
 
+size_t cta64_bytes_per_k() { return (size_t)128 * 8 + (size_t)1024 * 16 + (size_t)256 * 16; }      // (d,e)[2][64] | 32x32 block | 16x16 block
+
+// Eigenvalues for 32 < N <= 64: tridiag_cta64 (steps 0..31, four warps per matrix) -> trailing 32 x 32 block ->
+// pair_wide32<LOAD> (steps 32..47, one warp per matrix) -> pair_tail16 (steps 48..62, two matrices per warp) -> tql<64>.
+// SKTB_CTA64_SPLIT=0: all 63 steps in tridiag_cta64.
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
                  std::string* info) {
     constexpr int NC = 64;
     if (N <= 32 || N > 64) { *info = "launch_cta64: N out of range"; return -1; }
+    static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
     auto kB = tql_small_kernel<NC, 64>;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
     if (cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) {
@@ -16,25 +22,40 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     int dev = 0, sms = 148, occA = 0, occB = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<0>, C64_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false>, C64_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
     if (occA < 1 || occB < 1) { *info = "cta64 kernels do not fit"; return -1; }
-    C64Args a{H, N, nm, scratch};
+    double* de = scratch;
+    cplx* blk32 = reinterpret_cast<cplx*>(scratch + (size_t)nm * 128);
+    cplx* blk16 = blk32 + (size_t)nm * 1024;
+    C64Args a{H, N, nm, de, nullptr, split ? blk32 : nullptr};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
-    tridiag_cta64_kernel<0><<<gridA, C64_THREADS, 0, st>>>(a);
-    TqlArgs t{scratch, nm, N, evals, ld, col0, fail};
+    int launches = 2;
+    if (split) {
+        tridiag_cta64_kernel<true><<<gridA, C64_THREADS, 0, st>>>(a);
+        SmallArgs w{};
+        w.k = nullptr; w.mesh0 = w.mesh1 = w.mesh2 = 1; w.first = 0; w.nk = nm; w.N = N - 32; w.soc = 0;
+        w.scratch = de; w.flags = nullptr; w.flag_off = 0; w.Hsrc = blk32; w.Hld = 32; w.out_stride = 128; w.d_off = 32; w.e_off = 96;
+        const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16, smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
+        const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nm + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 2));
+        pair_wide32_kernel<PAIR_SRC_LOAD, 4, false, false><<<gridW, PAIR_WARPS * 32, smemW, st>>>(w, blk16, nullptr);
+        const unsigned gridT = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
+        pair_tail16_kernel<8><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, de, nm, 128, 32, 96);
+        launches = 4;
+    } else {
+        tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);
+    }
+    TqlArgs t{de, nm, N, evals, ld, col0, fail};
     const unsigned gridB = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * occB));
     kB<<<gridB, SMALL_WARPS * 32, smemB, st>>>(t);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
-    char buf[256];
-    snprintf(buf, sizeof buf, "hk + tridiag_cta64 grid=%u x %d thr %d CTA/SM + tql_small<64> grid=%u smem=%zuB %d CTA/SM; N=%d", gridA, C64_THREADS, occA,
-             gridB, smemB, occB, N);
+    char buf[320];
+    snprintf(buf, sizeof buf, "hk + tridiag_cta64%s grid=%u x %d thr %d CTA/SM%s + tql_small<64> grid=%u smem=%zuB %d CTA/SM; N=%d", split ? "<split>" : "",
+             gridA, C64_THREADS, occA, split ? " + pair_wide32<load> + pair_tail16" : "", gridB, smemB, occB, N);
     *info = buf;
-    return 2;
+    return launches;
 }
 
-// QL with accumulation for N <= 32: record-and-replay (tqlrec32 + vecapply32, vecql32 only for flagged overflows), or the
-// all-in-one vecql32 when SKTB_VEC_LIST=0.  Region layout after the ranks: lists | dfinal | flags.
 static const size_t smemBT = (size_t)VEC32_WARPS * PAIR_VSTORE_CPLX * 16;      // vecbt32: reflectors of one matrix per warp
 static bool vecbt32_smem_ok() {
     static const bool ok = cudaFuncSetAttribute(vecbt32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBT) == cudaSuccess;
@@ -74,12 +95,12 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     int dev = 0, sms = 148, occA = 0, occQ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<0>, C64_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false>, C64_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, vecql64_kernel<0>, 32, smemQ);
     if (occA < 1 || occQ < 1) { *info = "vec64 kernels do not fit"; return -1; }
-    C64Args a{H, N, nm, de, vstore};
+    C64Args a{H, N, nm, de, vstore, nullptr};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
-    tridiag_cta64_kernel<0><<<gridA, C64_THREADS, 0, st>>>(a);
+    tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);
     Vec64Args v{de, vstore, nm, N, evals, evecs, ld, col0, fail};
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occQ));
     static const bool use_list = !(getenv("SKTB_VEC_LIST") && getenv("SKTB_VEC_LIST")[0] == '0');

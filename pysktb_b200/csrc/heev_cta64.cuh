@@ -173,7 +173,8 @@ SKTB_D void c64_step(cplx (&B)[2][16], PairCarry& c, const int j, const C64Lane&
     c64_finish<NS>(c, ypart, xo, beta, tau, scale, jn, L, S);
 }
 
-template <int HALF>
+// SPLIT: stop after the two-slot phases (steps 0..31); the trailing 32 x 32 block goes to the N <= 32 kernels
+template <int HALF, bool SPLIT>
 SKTB_D void c64_phases(cplx (&B)[2][16], PairCarry& c, int& j, const C64Lane& L, const C64Smem& S) {
     constexpr int NS = HALF > 8 ? 2 : 1;
 #pragma unroll 1
@@ -188,7 +189,7 @@ SKTB_D void c64_phases(cplx (&B)[2][16], PairCarry& c, int& j, const C64Lane& L,
             B[s][HALF - 1] = cmake(0.0, 0.0);
         }
     }
-    if constexpr (HALF > 2) c64_phases<HALF - 2>(B, c, j, L, S);
+    if constexpr (HALF > 2 && !(SPLIT && HALF - 2 <= 8)) c64_phases<HALF - 2, SPLIT>(B, c, j, L, S);
 }
 
 struct C64Args {
@@ -196,9 +197,10 @@ struct C64Args {
     int N; long long nm;
     double* scratch;        // [nm][2][64]  (d | e)
     cplx* vstore = nullptr; // [nm][C64_VSTORE_CPLX] reflectors + tau (eigenvector path) or NULL
+    cplx* blocks = nullptr; // SPLIT: [nm][32][32] trailing block after step 31 (row-major, full rows)
 };
 
-template <int UNUSED>
+template <bool SPLIT>
 __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a) {
     __shared__ __align__(16) cplx smem[C64_SMEM_CPLX];
     const int t = threadIdx.x;
@@ -258,10 +260,15 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
             c64_finish<2>(c, ypart, xo, beta, tau, scale, 0, L, S);
         }
         int j = 0;
-        c64_phases<16>(B, c, j, L, S);
+        c64_phases<16, SPLIT>(B, c, j, L, S);
         if (t < 64) {
             double* out = a.scratch + (size_t)km * 128;
-            out[t] = S.D[t]; out[64 + t] = S.E[t];
+            if (!SPLIT || t < 32) { out[t] = S.D[t]; out[64 + t] = S.E[t]; }       // SPLIT: d[0..31], e[0..31]; the rest comes from the 32-wide kernels
+        }
+        if (SPLIT) {    // slot B = rows 32..63; registers 0..7 hold columns 32 + 4m + h (base = 32 after 32 steps)
+            cplx* blk = a.blocks + (size_t)km * 1024 + (size_t)(31 - L.r) * 32 + L.h;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) blk[4 * m] = B[1][m];
         }
         __syncthreads();
     }

@@ -383,7 +383,7 @@ SKTB_D void pair_build(cplx (&B)[2][16], const SmallArgs& a, const SmemView& s, 
 // scratch and the trailing 16x16 block (updated through step 15, column-major [q][i], 4 KB) into `blocks`.
 // FULL: run all 31 steps here (no tail kernel).
 // rows iA, iB x columns 2m + h of a caller-supplied matrix, zheevd(UPLO='L') reading (upper triangle = conj(lower))
-SKTB_D void pair_load(cplx (&B)[2][16], const cplx* __restrict__ H, const int N, const PairLane& L) {
+SKTB_D void pair_load(cplx (&B)[2][16], const cplx* __restrict__ H, const int N, const int ldh, const PairLane& L) {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int i = s ? L.iB : L.iA;
@@ -392,7 +392,7 @@ SKTB_D void pair_load(cplx (&B)[2][16], const cplx* __restrict__ H, const int N,
             const int col = 2 * m + L.h;
             const bool ok = i < N && col < N;
             const int hi = ok ? max(i, col) : 0, lo = ok ? min(i, col) : 0;
-            cplx e = H[(size_t)hi * N + lo];
+            cplx e = H[(size_t)hi * ldh + lo];
             if (col > i) e.y = -e.y;
             if (col == i) e.y = 0.0;
             if (!ok) e = cmake(0.0, 0.0);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         if (!k_ok) kq = a.nk - 1;
         if (VEC) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
         cplx B[2][16];
-        if (LOAD) pair_load(B, a.Hsrc + (size_t)kq * a.N * a.N, a.N, L);
+        if (LOAD) pair_load(B, a.Hsrc + (size_t)kq * (a.Hld ? a.Hld * a.Hld : a.N * a.N), a.N, a.Hld ? a.Hld : a.N, L);
         else {
             bond_phases<32>(a, s, kq, lane, phs);
             __syncwarp();
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         int j = 0;
         pair_phases<32, 16, FULL ? 0 : 8, S, VEC>(B, c, j, L, S_);
         if (k_ok) {
-            double* out = a.scratch + (size_t)kq * (2 * NC);
-            out[lane] = S_.D[lane]; out[NC + lane] = c.eval;
+            double* out = a.scratch + (size_t)kq * (a.out_stride ? a.out_stride : 2 * NC);
+            out[a.d_off + lane] = S_.D[lane]; out[(a.out_stride ? a.e_off : NC) + lane] = c.eval;
             if (!FULL) {
                 cplx* blk = blocks + (size_t)kq * 256 + (15 - L.r);
 #pragma unroll
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
 // TAIL kernel: tridiagonalisation of the trailing 16x16 blocks (steps 16..30), two matrices per warp, d[16..31] and
 // e[16..30] into the (d,e) scratch.  Few registers: co-resides with the wide kernel of the next chunk.
 template <int S>
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const cplx* __restrict__ blocks, double* __restrict__ scratch, long long nk) {
-    constexpr int NC = 32;
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const cplx* __restrict__ blocks, double* __restrict__ scratch, long long nk,
+                                                                          int out_stride, int d_off, int e_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 4;
     cplx* myw = reinterpret_cast<cplx*>(smem_raw) + (size_t)(2 * warp + g) * pair_buf_cplx<16>();
@@ -489,8 +489,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const c
         int j = 0;
         pair_phases<16, 8, 0, S, false>(B, c, j, L, S_);
         if (k_ok) {
-            double* out = scratch + (size_t)kq * (2 * NC);
-            out[16 + L.l] = S_.D[L.l]; out[NC + 16 + L.l] = c.eval;
+            double* out = scratch + (size_t)kq * out_stride;
+            out[d_off + 16 + L.l] = S_.D[L.l]; out[e_off + 16 + L.l] = c.eval;
         }
         __syncwarp();
     }

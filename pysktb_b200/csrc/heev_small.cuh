@@ -56,6 +56,8 @@ struct SmallArgs {
     double* scratch;            // [nk][2][NC]  (d | e) of every matrix
     int* flags; long long flag_off;
     const cplx* Hsrc = nullptr; // pair kernels in LOAD mode (sktb_heev): [nk][N][N] row-major matrices instead of K0+K1
+    int Hld = 0;                // LOAD mode: leading dimension / matrix stride of Hsrc (0 -> N); tridiag_cta64's 32 x 32 blocks use 32
+    int out_stride = 0, d_off = 0, e_off = 0;   // pair kernels: (d,e) record layout, 0 -> [2][32] per k; the cta64 split writes into [2][64] at 32
 };
 
 struct TqlArgs {
@@ -675,7 +677,7 @@ static int launch_pair(const LaunchCtx& c) {
     constexpr int SRC = SOC ? PAIR_SRC_SOC : PAIR_SRC_NOSOC;
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, true> : pair_wide32_kernel<SRC, 4, true>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, false> : pair_wide32_kernel<SRC, 4, false>;
-    void (*kT)(const cplx*, double*, long long) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
+    void (*kT)(const cplx*, double*, long long, int, int, int) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
     auto kB = tql_small_kernel<NC, 32>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
@@ -721,7 +723,7 @@ static int launch_pair(const LaunchCtx& c) {
         if (mode == 2) { cudaEventRecord(ps->evWide[b], sW); cudaStreamWaitEvent(sT, ps->evWide[b], 0); }
         if (mode != 0) {
             gridT = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
-            kT<<<gridT, PAIR_WARPS * 32, smemT, sT>>>(blocks, de, cnt);
+            kT<<<gridT, PAIR_WARPS * 32, smemT, sT>>>(blocks, de, cnt, 2 * NC, 0, NC);
             ++launches;
         }
         TqlArgs t{de, cnt, N, c.evals, c.ld, c.col0 + c0, c.fail};
@@ -811,7 +813,8 @@ static int launch_nc(const LaunchCtx& c, bool gate) {
 inline int padded_nc(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 12 ? 12 : (N <= 16 ? 16 : (N <= 24 ? 24 : 32)))); }
 
 // 32 < N <= 64, eigenvalues only: H (K1 output, [nm][N][N]) -> tridiag_cta64_kernel -> tql_small_kernel<64>.
-// scratch: >= nm * 128 doubles.  Returns the number of kernels launched or -1 (text in *info).
+// scratch: >= nm * cta64_bytes_per_k() bytes.  Returns the number of kernels launched or -1 (text in *info).
+size_t cta64_bytes_per_k();
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
                  std::string* info);
 

@@ -429,7 +429,7 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
         // K1 materialises H(k) (64 KB per k at N = 64), tridiag_cta64_kernel keeps it in registers, QL per lane
         size_t perH = (size_t)N * N * sizeof(cplx);
         long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));
-        if (W.H.ensure(perH * chunk) || W.S.ensure((size_t)chunk * 128 * 8)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
+        if (W.H.ensure(perH * chunk) || W.S.ensure((size_t)chunk * small::cta64_bytes_per_k())) return fail("out of device memory (H workspace %zu B)", perH * chunk);
         if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
         for (long long c0 = 0; c0 < nk; c0 += chunk) {
             long long cnt = std::min(chunk, nk - c0);
@@ -564,7 +564,7 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
         return 0;
     }
     if (N <= 64 && !evecs_d && !heev_generic_only) {      // CTA-resident kernel, eigenvalues only
-        if (p->ws[2].S.ensure((size_t)nm * 128 * 8)) return fail("out of device memory (heev workspace)");
+        if (p->ws[2].S.ensure((size_t)nm * small::cta64_bytes_per_k())) return fail("out of device memory (heev workspace)");
         int rc = small::launch_cta64((const cplx*)H_d, N, nm, (double*)p->ws[2].S.p, evals_d, nm, 0, p->d_fail, st, &g_kinfo);
         if (rc < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
         g_launches += rc;
@@ -745,7 +745,7 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 if (rl < 0) return fail("vec64 launch failed: %s", g_kinfo.c_str());
                 g_launches += rl;
             } else if (use_cta64) {
-                if (p->ws[2].S.ensure((size_t)cnt * 128 * 8)) return fail("out of device memory (tridiagonal scratch)");
+                if (p->ws[2].S.ensure((size_t)cnt * small::cta64_bytes_per_k())) return fail("out of device memory (tridiagonal scratch)");
                 int rl = small::launch_cta64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo);
                 if (rl < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
                 g_launches += rl;
@@ -833,7 +833,7 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                 int rl;
                 if (nr) rl = small::launch_vec64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
                 else {
-                    if (p->ws[2].S.ensure((size_t)cnt * 128 * 8)) return fail("out of device memory (tridiagonal scratch)");
+                    if (p->ws[2].S.ensure((size_t)cnt * small::cta64_bytes_per_k())) return fail("out of device memory (tridiagonal scratch)");
                     rl = small::launch_cta64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo);
                 }
                 if (rl < 0) return fail("mid-path launch failed: %s", g_kinfo.c_str());
