@@ -409,6 +409,23 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
             if (rc < 0) return fail("vec32 launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
         }
+    } else if (N <= 32) {
+        // N <= 32 models the fused register path cannot take (bond tables larger than shared memory, or eigenvectors of a
+        // model whose Hermiticity gate can fire): K1 materialises H(k), the pair kernels read it in LOAD mode
+        const size_t perH = (size_t)N * N * sizeof(cplx), per_k = perH + small::vec32_bytes_per_k() + 24;
+        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
+        if (W.H.ensure(perH * chunk) || W.RT.ensure(small::vec32_bytes_per_k() * chunk)) return fail("out of device memory (heev32 workspaces)");
+        if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
+        for (long long c0 = 0; c0 < nk; c0 += chunk) {
+            long long cnt = std::min(chunk, nk - c0);
+            const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
+            if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
+            int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
+            if (rc) return rc;
+            rc = small::launch_heev32((const cplx*)W.H.p, N, cnt, evals_d, (cplx*)evecs_d, ld, k_off + c0, p->d_fail, W.RT.p, st, &g_kinfo);
+            if (rc < 0) return fail("heev32 launch failed: %s", g_kinfo.c_str());
+            g_launches += rc;
+        }
     } else if (want_vecs && N > 32 && N <= 64) {
         // K1 -> tridiag_cta64 keeping the reflectors -> vecql64 -> vecbt64
         const size_t perH = (size_t)N * N * sizeof(cplx), per_k = perH + small::vec64_bytes_per_k() + 24;
