@@ -15,8 +15,8 @@ for w in C1 C2 C3 C4 C5; do python bench.py --workload $w --no-e2e --no-cpu --st
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/final_launches_T.csv python bench.py --steps 2 --warmup 3 --mesh 256 256 256 --no-cpu --no-e2e > $O/final_ncu_bench.log 2>&1
 for kn in pair_wide32 pair_tail16 tql_small; do ncu --set full --clock-control none --import-source on -k regex:$kn -s 2 -c 1 -o $O/final_full_$kn -f python tools/run_solve.py T 64 64 64 3 > /dev/null 2>&1; done
 ncu --set full --clock-control none --import-source on -k regex:tridiag_cta64 -s 1 -c 1 -o $O/final_full_cta64 -f python tools/run_solve.py C4 32 32 32 2 > /dev/null 2>&1
-for kn in vecql32 vecbt32; do ncu --set full --clock-control none --import-source on -k regex:$kn -s 1 -c 1 -o $O/final_full_$kn -f python tools/bench_vec.py T 65536 > /dev/null 2>&1; done
-for kn in vecql64 vecbt64; do ncu --set full --clock-control none --import-source on -k regex:$kn -s 1 -c 1 -o $O/final_full_$kn -f python tools/bench_vec.py C4 8192 > /dev/null 2>&1; done
+for kn in tqlrec vecapply32 vecbt32; do ncu --set full --clock-control none --import-source on -k regex:$kn -s 1 -c 1 -o $O/final_full_$kn -f python tools/bench_vec.py T 65536 > /dev/null 2>&1; done
+for kn in tqlrec vecapply64 vecbt64; do ncu --set full --clock-control none --import-source on -k regex:$kn -s 1 -c 1 -o $O/final_full_${kn}_n64 -f python tools/bench_vec.py C4 8192 > /dev/null 2>&1; done
 ncu --set full --clock-control none --import-source on -k regex:heev_generic -s 1 -c 1 -o $O/final_full_generic512 -f python tools/run_solve.py C5 296 1 1 2 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:lorentz_partial -s 1 -c 1 -o $O/final_full_lorentz -f python tools/bench_dos.py C2 2048 2048 1 400 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:solve_n2 -s 1 -c 1 -o $O/final_full_n2 -f python tools/run_solve.py C2 4096 4096 1 2 > /dev/null 2>&1

@@ -3,7 +3,7 @@ launch list, bench lines, secondary throughput log, and the traffic record bench
 import csv, io, json, os, shutil, subprocess, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 O, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
-order = ["pair_wide32", "pair_tail16", "tql_small", "cta64", "vecql32", "vecbt32", "vecql64", "vecbt64", "generic512", "lorentz", "n2"]
+order = ["pair_wide32", "pair_tail16", "tql_small", "cta64", "tqlrec", "vecapply32", "vecbt32", "tqlrec_n64", "vecapply64_n64", "vecbt64_n64", "generic512", "lorentz", "n2"]
 reps = [os.path.join("gpurun_out", f"final_full_{k}.raw.csv") for k in order if os.path.exists(os.path.join(O, f"final_full_{k}.raw.csv"))]
 subprocess.run([sys.executable, os.path.join(R, "tools", "make_profile_summary.py"), os.path.join(P, "r01_ncu_summary_final.md"),
                 "ncu --set full summaries, round 1 final (T: N=32, 64^3 = 262144 k per launch; C4: N=64, 32^3; vec kernels: 65536 k (N=32) / 8192 k (N=64); "
