@@ -131,10 +131,43 @@ struct HeevArgs {
     int n_rows; const int* rows;                    // tracked row indices (NULL -> identity)
     cplx* vec_out; long long vs_band, vs_k, vcol0;  // vec_out[band*vs_band + (vcol0+mat)*vs_k + r]
     int* fail;          // incremented when QL exceeds its iteration limit
+    int NP, SMEM_RED;   // column count padded to a warp multiple; blockDim.x = NP * R (R threads per column)
+    int NB;             // > 0: panel formulation with NB (2, 4 or 8) deferred reflector pairs
 };
 
-template <bool SMEM_A>
-__global__ void heev_generic_kernel(HeevArgs a) {
+// trailing update of one panel: M0[k][i] -= sum_s conj(V[i][s]) W[k][s] + conj(W[i][s]) V[k][s], rows k >= jn, column i
+template <int NBT>
+SKTB_D void heev_panel_update_t(cplx* A, const cplx* Vs, const cplx* Ws, int N, int i, int jn) {
+    cplx vr[NBT], wr[NBT];
+#pragma unroll
+    for (int s = 0; s < NBT; ++s) { vr[s] = Vs[s * N + i]; wr[s] = Ws[s * N + i]; }
+    int k = jn;
+    for (; k + 1 < N; k += 2) {
+        cplx* Ak = A + (size_t)k * N + i;
+        cplx c0 = Ak[0], c1 = Ak[N];
+#pragma unroll
+        for (int s = 0; s < NBT; ++s) {
+            cfmsc(c0, vr[s], Ws[s * N + k]); cfmsc(c0, wr[s], Vs[s * N + k]);
+            cfmsc(c1, vr[s], Ws[s * N + k + 1]); cfmsc(c1, wr[s], Vs[s * N + k + 1]);
+        }
+        Ak[0] = c0; Ak[N] = c1;
+    }
+    if (k < N) {
+        cplx* Ak = A + (size_t)k * N + i;
+        cplx c0 = Ak[0];
+#pragma unroll
+        for (int s = 0; s < NBT; ++s) { cfmsc(c0, vr[s], Ws[s * N + k]); cfmsc(c0, wr[s], Vs[s * N + k]); }
+        Ak[0] = c0;
+    }
+}
+SKTB_D void heev_panel_update(cplx* A, const cplx* Vs, const cplx* Ws, int N, int i, int jn, int NB) {
+    if (NB == 8) heev_panel_update_t<8>(A, Vs, Ws, N, i, jn);
+    else if (NB == 4) heev_panel_update_t<4>(A, Vs, Ws, N, i, jn);
+    else heev_panel_update_t<2>(A, Vs, Ws, N, i, jn);
+}
+
+template <bool SMEM_A, int MAXT>
+__global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, T = blockDim.x, tid = threadIdx.x;
     double* d = reinterpret_cast<double*>(smem_raw);
@@ -145,7 +178,7 @@ __global__ void heev_generic_kernel(HeevArgs a) {
     cplx* v = reinterpret_cast<cplx*>(scratch + 64);
     cplx* w = v + N;
     cplx* v2 = w + N;
-    cplx* sA = v2 + N;                            // N*N when SMEM_A
+    cplx* sA = v2 + N + (a.SMEM_RED ? blockDim.x : 0);   // N*N when SMEM_A (after the R x NP partial sums; never with NB > 0)
     __shared__ int s_lo, s_hi, s_done;
     const int n_rows = a.n_rows;
 
@@ -167,47 +200,174 @@ __global__ void heev_generic_kernel(HeevArgs a) {
         }
         __syncthreads();
 
-        if (N <= T && N >= 2) {
-            // ---- one column per thread: look-ahead formulation (one read+write pass over the trailing matrix per
-            //      step instead of a mat-vec pass plus an update pass).  Thread i owns column i of the mirrored
-            //      matrix, so y_i = sum_k A[i][k] v_k = sum_k conj(C[k][i]) v_k needs no cross-thread reduction:
-            //      the mat-vec of reflector j+1 is accumulated while reflector j's rank-2 update streams by.
-            const int i = tid;
+        if (a.NB > 0) {
+            // ---- panel formulation (LAPACK zhetrd/zlatrd idea, column-owner layout): inside a panel of NB steps the
+            //      matrix in memory stays M0 and only the reflector pairs (v_s, w_s) accumulate in shared memory,
+            //      M_t = M0 - sum_{s<t} (v_s w_s^H + w_s v_s^H).  A step is then ONE read-only pass over the trailing
+            //      rows (y0 = M0 v) plus O(NB) corrections per thread; the rank-2NB update is applied once per
+            //      panel.  Per element and step that is 16 B read + 32/NB B read+write instead of 32 B read+write.
+            const int NB = a.NB;
+            cplx* Vs = v2 + N + (a.SMEM_RED ? blockDim.x : 0);            // [NB][N]
+            cplx* Ws = Vs + (size_t)NB * N;                                // [NB][N]
+            double* mred = reinterpret_cast<double*>(Ws + (size_t)NB * N); // [32 warps][32] + ab[32]
+            double* ab = mred + 32 * 32;
+            const int i = tid, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
             const bool mine = i < N;
+            cplx tau = cmake(0.0, 0.0);
+            int tlast = 0;
+            for (int j0 = 0; j0 + 1 < N; j0 += NB) {
+                const int tmax = min(NB, N - 1 - j0);
+                for (int t = 0; t < tmax; ++t) {
+                    const int j = j0 + t;
+                    // (1) row j of M_t (columns i >= j): the pivot column x_i = conj(M_t[j][i])
+                    cplx c = cmake(0.0, 0.0);
+                    if (mine && i >= j) {
+                        c = A[(size_t)j * N + i];
+                        for (int s2 = 0; s2 < t; ++s2) {
+                            cfmsc(c, Vs[s2 * N + i], Ws[s2 * N + j]);
+                            cfmsc(c, Ws[s2 * N + i], Vs[s2 * N + j]);
+                        }
+                        if (i == j) d[j] = c.x;
+                    }
+                    const cplx x = (mine && i > j) ? cconj(c) : cmake(0.0, 0.0);
+                    double xn = block_sum((i > j + 1) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
+                    if (i == j + 1) { scratch[40] = x.x; scratch[41] = x.y; }
+                    __syncthreads();
+                    cplx alpha = cmake(scratch[40], scratch[41]);
+                    double beta; cplx scale;
+                    householder(alpha, xn, beta, tau, scale);
+                    if (tid == 0) e[j] = beta;
+                    const cplx vi = (i == j + 1) ? cmake(1.0, 0.0) : ((mine && i > j + 1) ? cmul(x, scale) : cmake(0.0, 0.0));
+                    if (mine) { v[i] = vi; Vs[t * N + i] = vi; }
+                    __syncthreads();
+                    // (2) y0_i = sum_{k > j} conj(M0[k][i]) v_k: read-only stream
+                    cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0), acc3 = cmake(0.0, 0.0), acc4 = cmake(0.0, 0.0);
+                    if (mine && i >= j + 1) {
+                        int k = j + 1;
+                        const cplx* Ak = A + (size_t)k * N + i;
+                        for (; k + 15 < N; k += 16, Ak += 16 * (size_t)N) {      // sixteen 16 B loads in flight per thread
+                            cplx cc[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) cc[u] = Ak[u * (size_t)N];
+#pragma unroll
+                            for (int u = 0; u < 16; u += 4) {
+                                cfmac(acc, cc[u], v[k + u]); cfmac(acc2, cc[u + 1], v[k + u + 1]);
+                                cfmac(acc3, cc[u + 2], v[k + u + 2]); cfmac(acc4, cc[u + 3], v[k + u + 3]);
+                            }
+                        }
+                        for (; k + 3 < N; k += 4, Ak += 4 * (size_t)N) {
+                            cplx c0 = Ak[0], c1 = Ak[N], c2 = Ak[2 * (size_t)N], c3 = Ak[3 * (size_t)N];
+                            cfmac(acc, c0, v[k]); cfmac(acc2, c1, v[k + 1]); cfmac(acc3, c2, v[k + 2]); cfmac(acc4, c3, v[k + 3]);
+                        }
+                        for (; k < N; ++k, Ak += N) cfmac(acc, Ak[0], v[k]);
+                    }
+                    acc = cadd(cadd(acc, acc2), cadd(acc3, acc4));
+                    // corrections: a_s = w_s^H v, b_s = v_s^H v for s < t (2t block-wide complex sums at once)
+                    if (t > 0) {
+                        for (int s2 = 0; s2 < t; ++s2) {
+                            cplx ca = cmake(0.0, 0.0), cb = cmake(0.0, 0.0);
+                            if (mine) { cfmac(ca, Ws[s2 * N + i], vi); cfmac(cb, Vs[s2 * N + i], vi); }
+                            ca.x = warp_sum(ca.x); ca.y = warp_sum(ca.y); cb.x = warp_sum(cb.x); cb.y = warp_sum(cb.y);
+                            if (lane == 0) { double* m = mred + wid * 32 + 4 * s2; m[0] = ca.x; m[1] = ca.y; m[2] = cb.x; m[3] = cb.y; }
+                        }
+                        __syncthreads();
+                        if (tid < 4 * t) {
+                            double sum = 0.0;
+                            for (int q2 = 0; q2 < nw; ++q2) sum += mred[q2 * 32 + tid];
+                            ab[tid] = sum;
+                        }
+                        __syncthreads();
+                        if (mine && i >= j + 1)
+                            for (int s2 = 0; s2 < t; ++s2) {
+                                const cplx as = cmake(ab[4 * s2], ab[4 * s2 + 1]), bs = cmake(ab[4 * s2 + 2], ab[4 * s2 + 3]);
+                                cfms(acc, Vs[s2 * N + i], as);
+                                cfms(acc, Ws[s2 * N + i], bs);
+                            }
+                    }
+                    cplx p = (mine && i >= j + 1) ? cmul(tau, acc) : cmake(0.0, 0.0);
+                    cplx dl = cmake(0.0, 0.0);
+                    cfmac(dl, p, vi);
+                    cplx dot = block_sum(dl, scratch);
+                    cplx a2 = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dot);
+                    cplx wi = p; cfma(wi, a2, vi);
+                    if (mine) Ws[t * N + i] = wi;
+                    // row tracking with reflector j (tracked rows of Q): R <- R H_j
+                    for (int r = tid; r < n_rows; r += T) {
+                        cplx sdot = cmake(0.0, 0.0);
+                        for (int qq = j + 1; qq < N; ++qq) cfma(sdot, RT[(size_t)qq * n_rows + r], v[qq]);
+                        cplx ts = cmul(tau, sdot);
+                        for (int qq = j + 1; qq < N; ++qq) {
+                            cplx xx = RT[(size_t)qq * n_rows + r];
+                            cplx vc = cconj(v[qq]);
+                            cfms(xx, ts, vc);
+                            RT[(size_t)qq * n_rows + r] = xx;
+                        }
+                    }
+                    __syncthreads();
+                }
+                tlast = tmax;
+                const int jn = j0 + tmax;
+                if (tmax == NB && jn + 1 < N) {
+                    // panel update of the trailing block (rows, columns >= jn); own-row reflector entries in registers
+                    if (mine && i >= jn) heev_panel_update(A, Vs, Ws, N, i, jn, NB);
+                    tlast = 0;
+                    __syncthreads();
+                }
+            }
+            if (i == N - 1) {                                             // last diagonal entry, with the open panel applied
+                cplx c = A[(size_t)i * N + i];
+                for (int s2 = 0; s2 < tlast; ++s2) { cfmsc(c, Vs[s2 * N + i], Ws[s2 * N + i]); cfmsc(c, Ws[s2 * N + i], Vs[s2 * N + i]); }
+                A[(size_t)i * N + i] = c;
+            }
+            __syncthreads();
+        } else
+        if (N <= T && N >= 2) {
+            // ---- look-ahead formulation, R threads per column (one read+write pass over the trailing matrix per
+            //      step instead of a mat-vec pass plus an update pass).  Threads (q, i), q = tid / NP, own column i
+            //      of the mirrored matrix and the rows k = j+2+q (mod R) of it; y_i = sum_k conj(C[k][i]) v_k is a
+            //      per-column sum of R partials through shared memory: the mat-vec of reflector j+1 is accumulated
+            //      while reflector j's rank-2 update streams by.  A warp reads 32 consecutive columns of one row.
+            const int NP = a.NP, R = T / NP;
+            const int q = tid / NP, i = tid - q * NP;
+            const bool mine = i < N, lead = q == 0;
+            cplx* red = a.SMEM_RED ? v2 + N : nullptr;                     // [R][NP] when R > 1
             cplx vi = cmake(0.0, 0.0), wi = cmake(0.0, 0.0), tau = cmake(0.0, 0.0);
             // prologue: reflector 0 from column 0, plain mat-vec
             {
-                cplx x = (mine && i >= 1) ? cconj(A[i]) : cmake(0.0, 0.0);
+                cplx x = (lead && mine && i >= 1) ? cconj(A[i]) : cmake(0.0, 0.0);
                 double xn = block_sum((i > 1) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
-                if (i == 1) { scratch[40] = x.x; scratch[41] = x.y; }
-                if (i == 0) d[0] = A[0].x;
+                if (lead && i == 1) { scratch[40] = x.x; scratch[41] = x.y; }
+                if (tid == 0) d[0] = A[0].x;
                 __syncthreads();
                 cplx alpha = cmake(scratch[40], scratch[41]);
                 double beta; cplx scale;
                 householder(alpha, xn, beta, tau, scale);
-                if (i == 0) e[0] = beta;
+                if (tid == 0) e[0] = beta;
                 vi = (i == 1) ? cmake(1.0, 0.0) : ((mine && i > 1) ? cmul(x, scale) : cmake(0.0, 0.0));
-                if (mine) v[i] = vi;
+                if (lead && mine) v[i] = vi;
                 __syncthreads();
-                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
-                if (mine && i >= 1) {
-                    int k = 1;
-                    for (; k + 1 < N; k += 2) { cfmac(acc, A[(size_t)k * N + i], v[k]); cfmac(acc2, A[(size_t)(k + 1) * N + i], v[k + 1]); }
-                    if (k < N) cfmac(acc, A[(size_t)k * N + i], v[k]);
+                cplx acc = cmake(0.0, 0.0);
+                if (mine && i >= 1)
+                    for (int k = 1 + q; k < N; k += R) cfmac(acc, A[(size_t)k * N + i], v[k]);
+                if (R > 1) {
+                    red[tid] = acc;
+                    __syncthreads();
+                    if (lead) for (int qq = 1; qq < R; ++qq) acc = cadd(acc, red[qq * NP + i]);
                 }
-                cplx p = (mine && i >= 1) ? cmul(tau, cadd(acc, acc2)) : cmake(0.0, 0.0);
+                cplx p = (lead && mine && i >= 1) ? cmul(tau, acc) : cmake(0.0, 0.0);
                 cplx dl = cmake(0.0, 0.0);
                 cfmac(dl, p, vi);
                 cplx dot = block_sum(dl, scratch);
                 cplx a2 = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dot);
                 wi = p; cfma(wi, a2, vi);
-                if (mine) w[i] = wi;
+                if (lead && mine) w[i] = wi;
                 __syncthreads();
+                if (!lead && mine) { vi = v[i]; wi = w[i]; }
             }
             for (int j = 0; j + 1 < N; ++j) {
                 // (1) row j+1 of the update -> the next pivot column (entries x'_i = conj(C[j+1][i]), i > j+1)
                 cplx x = cmake(0.0, 0.0);
-                if (mine && i >= j + 1) {
+                if (lead && mine && i >= j + 1) {
                     cplx c = A[(size_t)(j + 1) * N + i];
                     cfmsc(c, vi, w[j + 1]);
                     cfmsc(c, wi, v[j + 1]);
@@ -218,57 +378,68 @@ __global__ void heev_generic_kernel(HeevArgs a) {
                 // row tracking with reflector j (tracked rows of Q): R <- R H_j
                 for (int r = tid; r < n_rows; r += T) {
                     cplx sdot = cmake(0.0, 0.0);
-                    for (int q = j + 1; q < N; ++q) cfma(sdot, RT[(size_t)q * n_rows + r], v[q]);
+                    for (int qq = j + 1; qq < N; ++qq) cfma(sdot, RT[(size_t)qq * n_rows + r], v[qq]);
                     cplx ts = cmul(tau, sdot);
-                    for (int q = j + 1; q < N; ++q) {
-                        cplx xx = RT[(size_t)q * n_rows + r];
-                        cplx vc = cconj(v[q]);
+                    for (int qq = j + 1; qq < N; ++qq) {
+                        cplx xx = RT[(size_t)qq * n_rows + r];
+                        cplx vc = cconj(v[qq]);
                         cfms(xx, ts, vc);
-                        RT[(size_t)q * n_rows + r] = xx;
+                        RT[(size_t)qq * n_rows + r] = xx;
                     }
                 }
                 if (j + 2 >= N) break;                                    // column N-1 is the last diagonal entry
-                double xn = block_sum((mine && i > j + 2) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
-                if (i == j + 2) { scratch[40] = x.x; scratch[41] = x.y; }
+                double xn = block_sum((lead && mine && i > j + 2) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
+                if (lead && i == j + 2) { scratch[40] = x.x; scratch[41] = x.y; }
                 __syncthreads();
                 cplx alpha = cmake(scratch[40], scratch[41]);
                 double beta; cplx tau2, scale;
                 householder(alpha, xn, beta, tau2, scale);
-                if (i == 0) e[j + 1] = beta;
+                if (tid == 0) e[j + 1] = beta;
                 cplx v2i = (i == j + 2) ? cmake(1.0, 0.0) : ((mine && i > j + 2) ? cmul(x, scale) : cmake(0.0, 0.0));
-                if (mine) v2[i] = v2i;
+                if (lead && mine) v2[i] = v2i;
                 __syncthreads();
                 // (2) rows k >= j+2: update and accumulate the next mat-vec in the same pass
                 cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
                 if (mine && i >= j + 2) {
-                    int k = j + 2;
-                    for (; k + 3 < N; k += 4) {                            // four independent 16 B loads in flight per thread
+                    int k = j + 2 + q;
+                    const size_t RN = (size_t)R * N;
+                    for (; k + 3 * R < N; k += 4 * R) {                    // four independent 16 B loads in flight per thread
                         cplx* Ak = A + (size_t)k * N + i;
-                        cplx c0 = Ak[0], c1 = Ak[N], c2 = Ak[2 * (size_t)N], c3 = Ak[3 * (size_t)N];
+                        cplx c0 = Ak[0], c1 = Ak[RN], c2 = Ak[2 * RN], c3 = Ak[3 * RN];
                         cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
-                        cfmsc(c1, vi, w[k + 1]); cfmsc(c1, wi, v[k + 1]);
-                        cfmsc(c2, vi, w[k + 2]); cfmsc(c2, wi, v[k + 2]);
-                        cfmsc(c3, vi, w[k + 3]); cfmsc(c3, wi, v[k + 3]);
-                        Ak[0] = c0; Ak[N] = c1; Ak[2 * (size_t)N] = c2; Ak[3 * (size_t)N] = c3;
-                        cfmac(acc, c0, v2[k]); cfmac(acc2, c1, v2[k + 1]);
-                        cfmac(acc, c2, v2[k + 2]); cfmac(acc2, c3, v2[k + 3]);
+                        cfmsc(c1, vi, w[k + R]); cfmsc(c1, wi, v[k + R]);
+                        cfmsc(c2, vi, w[k + 2 * R]); cfmsc(c2, wi, v[k + 2 * R]);
+                        cfmsc(c3, vi, w[k + 3 * R]); cfmsc(c3, wi, v[k + 3 * R]);
+                        Ak[0] = c0; Ak[RN] = c1; Ak[2 * RN] = c2; Ak[3 * RN] = c3;
+                        cfmac(acc, c0, v2[k]); cfmac(acc2, c1, v2[k + R]);
+                        cfmac(acc, c2, v2[k + 2 * R]); cfmac(acc2, c3, v2[k + 3 * R]);
                     }
-                    for (; k < N; ++k) {
+                    for (; k < N; k += R) {
                         cplx c0 = A[(size_t)k * N + i];
                         cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
                         A[(size_t)k * N + i] = c0;
                         cfmac(acc, c0, v2[k]);
                     }
                 }
-                cplx p = (mine && i >= j + 2) ? cmul(tau2, cadd(acc, acc2)) : cmake(0.0, 0.0);
+                acc = cadd(acc, acc2);
+                if (R > 1) {
+                    red[tid] = acc;
+                    __syncthreads();
+                    if (lead) for (int qq = 1; qq < R; ++qq) acc = cadd(acc, red[qq * NP + i]);
+                }
+                cplx p = (lead && mine && i >= j + 2) ? cmul(tau2, acc) : cmake(0.0, 0.0);
                 cplx dl = cmake(0.0, 0.0);
                 cfmac(dl, p, v2i);
                 cplx dot = block_sum(dl, scratch);                        // (syncs: every thread is done reading v, w)
                 cplx a2 = cmul(cmake(-0.5 * tau2.x, -0.5 * tau2.y), dot);
-                vi = v2i; tau = tau2;
-                wi = p; cfma(wi, a2, vi);
-                if (mine) { v[i] = vi; w[i] = wi; }
+                tau = tau2;
+                if (lead) {
+                    vi = v2i;
+                    wi = p; cfma(wi, a2, vi);
+                    if (mine) { v[i] = vi; w[i] = wi; }
+                }
                 __syncthreads();
+                if (!lead && mine) { vi = v[i]; wi = w[i]; }
             }
             __syncthreads();
         } else
