@@ -1,8 +1,13 @@
 """Total energy of a tight-binding model (reference: pysktb/forces.py:367-425).
 
-Only `get_total_energy` is provided: the band energy runs on the device (mesh eigenvalues through the C ABI, reduced
-by `sktb_band_energy`), the repulsive pair energy is summed on the host exactly as the reference does.  The
-reference's `get_forces` is broken as shipped and is not reproduced.
+`get_total_energy`: the band energy runs on the device (mesh eigenvalues through the C ABI, reduced by
+`sktb_band_energy`), the repulsive pair energy is summed on the host exactly as the reference does.
+
+`get_forces`: the reference's implementation raises TypeError as shipped, so its
+semantics are taken from its docstrings (forces.py:3-4, 43-58): F[a] = -dE_tot/dR_a in eV/Angstrom, shape
+(n_atoms, 3), E_tot = E_band + E_rep of `get_total_energy`.  Here the derivative is a central difference of that
+total energy over Cartesian displacements of one atom (6 n_atoms mesh solves, each one k-sharded device call), which
+includes every dependence of H(k) on the positions: scaling laws, direction cosines and the Bloch phases.
 """
 import numpy as np
 
@@ -62,5 +67,31 @@ class Forces:
                         e += float(rep(st.dist_mat[im, i, j]))
         return e
 
-    def get_forces(self, *a, **k):
-        raise NotImplementedError("the reference's Forces.get_forces raises TypeError as shipped (SURVEY.md); not reproduced")
+    def get_forces(self, n_electrons, nk=[10, 10, 10], temperature=0.0, mu=None, soc=True, parallel=True, step=1e-4):
+        """-> f64 (n_atoms, 3), eV/Angstrom (forces.py:43-72 signature; `parallel` is accepted and ignored, the mesh
+        solve always runs on the device).  Zero electronic temperature only; `step` is the displacement in Angstrom
+        of the central difference (error O(step^2))."""
+        if temperature != 0.0 or mu is not None:
+            raise NotImplementedError("get_forces: only temperature=0 with the filling fixed by n_electrons")
+        from .atom import Atom
+        from .structure import Structure
+        from .hamiltonian import Hamiltonian
+        st, ham = self.structure, self.ham
+        lat_t = np.asarray(st.lattice.get_matrix(), dtype=float).T          # cart = lat.T @ frac (structure.py:104-143)
+        forces = np.zeros((self.n_atoms, 3))
+        for a in range(self.n_atoms):
+            for d in range(3):
+                e = []
+                for sgn in (1.0, -1.0):
+                    dcart = np.zeros(3)
+                    dcart[d] = sgn * step
+                    dfrac = np.linalg.solve(lat_t, dcart)
+                    atoms = [Atom(x.element, np.asarray(x.pos, dtype=float) + (dfrac if i == a else 0.0), x.orbitals)
+                             for i, x in enumerate(st.atoms)]
+                    st2 = Structure(st.lattice, atoms, periodicity=st.periodicity, name=st.name, bond_cut=st.bond_cut,
+                                    numba=st.numba)
+                    ham2 = Hamiltonian(st2, ham.inter, numba=ham.numba, device=ham._device)
+                    e.append(Forces(ham2).get_total_energy(n_electrons, nk=nk, soc=soc)[0])
+                    del ham2
+                forces[a, d] = -(e[0] - e[1]) / (2.0 * step)
+        return forces

@@ -418,6 +418,33 @@ def test_next_rows_vs_reference_golden(tb):
     assert np.allclose(tb.Hamiltonian.kproj_weights(v, [1, 4]), np.linalg.norm(v[:, :, [1, 4]], axis=-1))
 
 
+def test_forces_central_difference_vs_oracle(tb):
+    """Forces.get_forces: -dE_tot/dR by central differences of the device total energy, on the
+    low-symmetry 3-atom model with distance laws (N = 44 with SOC).  Checked against the same difference quotient of
+    the oracle's band energy for two components, and against translation invariance (forces sum to zero)."""
+    import copy
+    from oracle import sktb_oracle as O
+    from pysktb_b200 import workloads as W
+    spec = W.lowsym_spd()
+    _, ham = W.instantiate(spec, tb, tb.scaling)
+    ne, nk, h = 10, [3, 3, 2], 1e-4
+    F = tb.Forces(ham).get_forces(ne, nk=nk, soc=True, step=h)
+    assert F.shape == (3, 3) and np.all(np.isfinite(F))
+    assert np.abs(F.sum(axis=0)).max() < 1e-6 and np.abs(F).max() > 1e-3
+    lat_t = (np.array(spec["lattice"], dtype=float) * spec["a"]).T
+    for a, d in ((1, 0), (2, 2)):
+        e = []
+        for sgn in (1.0, -1.0):
+            sp = copy.deepcopy(spec)
+            dcart = np.zeros(3); dcart[d] = sgn * h
+            el, pos, orbs = sp["atoms"][a]
+            sp["atoms"][a] = (el, (np.array(pos, dtype=float) + np.linalg.solve(lat_t, dcart)).tolist(), orbs)
+            e.append(O.total_energy_band(oracle_model(sp), ne, nk=nk, soc=True))
+        assert abs(F[a, d] + (e[0] - e[1]) / (2 * h)) < 1e-6, (a, d, F[a, d], -(e[0] - e[1]) / (2 * h))
+    with pytest.raises(NotImplementedError):
+        tb.Forces(ham).get_forces(ne, nk=nk, temperature=0.1)
+
+
 def test_ldos_multi_chunk_sums_to_dos(tb):
     """Eigenvector-based LDOS over several workspace chunks (T: ~60 000 k per chunk, 48^3 = 110 592 k; C4: ~18 000 k per
     chunk, 28^3 = 21 952 k): the projections on all orbitals of all atoms must add up to the eigenvalue-only DOS."""
