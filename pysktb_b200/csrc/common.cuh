@@ -18,6 +18,16 @@ SKTB_HD cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
 SKTB_HD cplx cmul(cplx a, cplx b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 SKTB_HD cplx cmulc(cplx a, cplx b) { return cmake(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }  // conj(a)*b
 SKTB_HD cplx cscale(double s, cplx a) { return cmake(s * a.x, s * a.y); }
+#ifdef __CUDACC__
+// 1/sqrt(a): hardware seed (~2^-22) and one cubic correction step (full double precision), no slow path
+SKTB_D double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a * y, y, 1.0);
+    const double c = fma(e, 0.375, 0.5);
+    return fma(c, y * e, y);
+}
+#endif
 // acc += a*b
 SKTB_HD void cfma(cplx& acc, cplx a, cplx b) {
     acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);

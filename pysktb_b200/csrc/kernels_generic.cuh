@@ -133,6 +133,7 @@ struct HeevArgs {
     int* fail;          // incremented when QL exceeds its iteration limit
     int NP, SMEM_RED;   // column count padded to a warp multiple; blockDim.x = NP * R (R threads per column)
     int NB;             // > 0: panel formulation with NB (2, 4 or 8) deferred reflector pairs
+    int phase;          // 0: whole solve; 1: tridiagonalise and park (d, e) in H; 2: QL + output from the parked (d, e)
 };
 
 // trailing update of one panel: M0[k][i] -= sum_s conj(V[i][s]) W[k][s] + conj(W[i][s]) V[k][s], rows k >= jn, column i
@@ -186,6 +187,12 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
         cplx* G = a.H + (size_t)mat * N * N;
         cplx* A = SMEM_A ? sA : G;
         cplx* RT = n_rows ? a.RT + (size_t)mat * N * n_rows : nullptr;
+        if (a.phase == 2) {
+            // second kernel of the split run: (d, e) were parked in the (dead) matrix buffer by the first kernel
+            const double* de = reinterpret_cast<const double*>(G);
+            for (int idx = tid; idx < N; idx += T) { d[idx] = de[idx]; e[idx] = de[N + idx]; }
+            __syncthreads();
+        } else {
         // mirror the lower triangle (UPLO='L'): upper <- conj(lower), diagonal <- real
         for (int idx = tid; idx < N * N; idx += T) {
             int r = idx / N, c = idx - r * N;
@@ -492,6 +499,15 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
         }
         if (tid == 0) { d[N - 1] = A[(size_t)(N - 1) * N + (N - 1)].x; e[N - 1] = 0.0; }
         __syncthreads();
+        if (a.phase == 1) {
+            // split run (tracked rows, N > 64): the serial QL generator would leave this SM idle, so it runs in a
+            // second launch with small CTAs, many matrices per SM
+            double* de = reinterpret_cast<double*>(G);
+            for (int idx = tid; idx < N; idx += T) { de[idx] = d[idx]; de[N + idx] = e[idx]; }
+            __syncthreads();
+            continue;
+        }
+        }
 
         // ---- tridiagonal QL ----
         bool sorted_by_construction = false;
@@ -549,58 +565,63 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             if (tid == 0) { if (tql_values(d, e, N, 1)) atomicAdd(a.fail, 1); }
             __syncthreads();
         } else {
+            // QL with tracked rows.  Every thread keeps (l, iter); the deflation scan (first m >= l with a negligible
+            // e_m) is done by the whole block, thread 0 generates the rotations of one sweep (reciprocal square root
+            // by the hardware seed + one cubic correction instead of IEEE sqrt and division: this chain is the
+            // critical path of the LDOS runs), the threads owning a tracked row apply them.
             const double eps = 2.220446049250313e-16;
-            int l = 0, iter = 0;                    // thread 0's private state
-            while (true) {
+            int l = 0, iter = 0;
+            while (l < N) {
+                int cand = N - 1;
+                for (int m = l + tid; m < N - 1; m += T) {
+                    double dd = fabs(d[m]) + fabs(d[m + 1]);
+                    if (fabs(e[m]) <= eps * dd) { cand = m; break; }
+                }
+                cand = __reduce_min_sync(0xffffffffu, cand);
+                __syncthreads();
+                if ((tid & 31) == 0) reinterpret_cast<int*>(scratch)[tid >> 5] = cand;
+                __syncthreads();
+                int m = N - 1;
+                for (int q = 0; q < ((T + 31) >> 5); ++q) m = min(m, reinterpret_cast<int*>(scratch)[q]);
+                if (m == l) { ++l; iter = 0; continue; }
+                if (++iter > 80) { if (tid == 0) atomicAdd(a.fail, 1); ++l; iter = 0; continue; }
                 if (tid == 0) {
-                    int done = 0, lo = 0, hi = 0;
-                    while (true) {
-                        if (l >= N) { done = 1; break; }
-                        int m = l;
-                        for (; m < N - 1; ++m) {
-                            double dd = fabs(d[m]) + fabs(d[m + 1]);
-                            if (fabs(e[m]) <= eps * dd) break;
-                        }
-                        if (m == l) { ++l; iter = 0; continue; }
-                        if (++iter > 80) { atomicAdd(a.fail, 1); ++l; iter = 0; continue; }
-                        double el = e[l];
-                        double g = (d[l + 1] - d[l]) / (2.0 * el);
-                        double r = sqrt(g * g + 1.0);
-                        g = d[m] - d[l] + el / (g + (g >= 0.0 ? r : -r));
-                        double s = 1.0, c = 1.0, p = 0.0;
-                        int i = m - 1;
-                        bool under = false;
-                        for (; i >= l; --i) {
-                            double ei = e[i];
-                            double f = s * ei, b = c * ei;
-                            r = sqrt(f * f + g * g);
-                            e[i + 1] = r;
-                            if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; under = true; break; }
-                            double ir = 1.0 / r;
-                            s = f * ir; c = g * ir;
-                            g = d[i + 1] - p;
-                            r = (d[i] - g) * s + 2.0 * c * b;
-                            p = s * r;
-                            d[i + 1] = g + p;
-                            g = c * r - b;
-                            cs[i] = c; sn[i] = s;
-                        }
-                        if (!under) { d[l] -= p; e[l] = g; e[m] = 0.0; }
-                        lo = under ? i + 1 : l; hi = m;          // rotations i = hi-1 .. lo were generated
-                        break;
+                    double el = e[l];
+                    double g = (d[l + 1] - d[l]) / (2.0 * el);
+                    double r = sqrt(g * g + 1.0);
+                    g = d[m] - d[l] + el / (g + (g >= 0.0 ? r : -r));
+                    double s = 1.0, c = 1.0, p = 0.0;
+                    int i = m - 1;
+                    bool under = false;
+                    double ei = e[i], di = d[i], dn = d[i + 1];
+                    for (; i >= l; --i) {
+                        const double f = s * ei, b = c * ei;
+                        const double rr = fma(f, f, g * g);
+                        if (rr == 0.0) { e[i + 1] = 0.0; d[i + 1] = dn - p; e[m] = 0.0; under = true; break; }
+                        const double ir = fast_rsqrt(rr);
+                        e[i + 1] = rr * ir;
+                        s = f * ir; c = g * ir;
+                        g = dn - p;
+                        r = (di - g) * s + 2.0 * c * b;
+                        p = s * r;
+                        d[i + 1] = g + p;
+                        g = c * r - b;
+                        cs[i] = c; sn[i] = s;
+                        dn = di;                                          // d[i] is still the unmodified entry
+                        if (i > l) { ei = e[i - 1]; di = d[i - 1]; }
                     }
-                    s_done = done; s_lo = lo; s_hi = hi;
+                    if (!under) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                    s_lo = under ? i + 1 : l; s_hi = m;                  // rotations i = hi-1 .. lo were generated
                 }
                 __syncthreads();
-                if (s_done) break;
                 const int lo = s_lo, hi = s_hi;
                 for (int r = tid; r < n_rows; r += T) {
                     cplx up = RT[(size_t)hi * n_rows + r];              // running value of row i+1
                     for (int i = hi - 1; i >= lo; --i) {
-                        double c = cs[i], s = sn[i];
+                        double c = cs[i], s2 = sn[i];
                         cplx g = RT[(size_t)i * n_rows + r];
-                        RT[(size_t)(i + 1) * n_rows + r] = cmake(s * g.x + c * up.x, s * g.y + c * up.y);
-                        up = cmake(c * g.x - s * up.x, c * g.y - s * up.y);
+                        RT[(size_t)(i + 1) * n_rows + r] = cmake(s2 * g.x + c * up.x, s2 * g.y + c * up.y);
+                        up = cmake(c * g.x - s2 * up.x, c * g.y - s2 * up.y);
                     }
                     RT[(size_t)lo * n_rows + r] = up;
                 }

@@ -338,7 +338,7 @@ static int launch_hk(sktb_plan* p, const double* k_d, long long nk, int soc, cpl
     return 0;
 }
 
-static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, int phase) {
     const int N = a.N;
     static const long long smemA_max = getenv("SKTB_GENERIC_SMEMA_KB") ? atoll(getenv("SKTB_GENERIC_SMEMA_KB")) * 1024 : 72 * 1024;
     static const long long l2_mb = getenv("SKTB_GENERIC_L2_MB") ? atoll(getenv("SKTB_GENERIC_L2_MB")) : 0;
@@ -350,14 +350,16 @@ static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
         R = std::max(1, std::min(R, 1024 / NP));
     }
     int T = std::min(1024, NP * R);
+    a.phase = phase;
+    if (phase == 2) { R = 1; T = std::min(512, std::max(64, (a.n_rows + 31) / 32 * 32)); }
     a.NP = NP; a.SMEM_RED = R > 1;
     size_t aux = ((size_t)4 * N + 64) * sizeof(double) + (size_t)3 * N * sizeof(cplx) + (R > 1 ? (size_t)T * sizeof(cplx) : 0);
     size_t withA = aux + (size_t)N * N * sizeof(cplx);
-    bool smemA = (long long)withA <= smemA_max && T <= 384;   // beyond N = 64 many CTAs per SM over L2 beat one CTA per SM in shared memory
+    bool smemA = (long long)withA <= smemA_max && T <= 384 && phase == 0;   // beyond N = 64 many CTAs per SM over L2 beat one CTA per SM in shared memory
     // panel formulation for the sizes that stream the matrix through HBM/L2 (one column per thread, N <= 1024)
     static const int nb_env = getenv("SKTB_GENERIC_NB") ? atoi(getenv("SKTB_GENERIC_NB")) : 8;
     a.NB = 0;
-    if (!smemA && R == 1 && N <= 1024 && nb_env > 0 && (N >= 96 || getenv("SKTB_GENERIC_NB"))) {
+    if (!smemA && R == 1 && N <= 1024 && nb_env > 0 && phase != 2 && (N >= 96 || getenv("SKTB_GENERIC_NB"))) {
         int NB = nb_env >= 8 ? 8 : (nb_env >= 4 ? 4 : 2);
         if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;     // measured: 4 wins below N ~ 160, none below N ~ 96
         auto panel_bytes = [&](int nb) { return (size_t)2 * nb * N * sizeof(cplx) + (32 * 32 + 32) * sizeof(double); };
@@ -380,8 +382,19 @@ static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     LAUNCHED();
     char buf[256];
     snprintf(buf, sizeof buf, "heev_generic<smemA=%d> N=%d R=%d NB=%d threads=%d smem=%zuB grid=%u rows=%d", (int)smemA, N, R, a.NB, T, smem, grid, a.n_rows);
-    g_kinfo = buf;
+    if (phase == 2) g_kinfo += std::string(" + QL kernel x") + std::to_string(T) + " thr"; else g_kinfo = buf;
     return 0;
+}
+
+// Tracked rows with N > 64: tridiagonalisation (one 1-CTA-per-SM class kernel) and the serial-generator QL (small CTAs,
+// many matrices per SM) are two launches; everything else is one.
+static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+    static const bool no_split = getenv("SKTB_GENERIC_SPLIT") != nullptr && getenv("SKTB_GENERIC_SPLIT")[0] == '0';
+    if (a.n_rows > 0 && a.N > 64 && a.N <= 1024 && !no_split) {
+        int rc = launch_heev_generic_phase(p, a, st, 1);
+        return rc ? rc : launch_heev_generic_phase(p, a, st, 2);
+    }
+    return launch_heev_generic_phase(p, a, st, 0);
 }
 
 static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked workspaces
