@@ -180,12 +180,40 @@ def next_rows_fixture(ref):
     print("next_rows", {k: v.shape for k, v in out.items()})
 
 
+FUZZ_SEEDS = 48
+
+
+def fuzz_fixture(ref):
+    """Seeded random models (workloads.random_spec): the reference's eigenvalues (and eigenvector Gram residuals) at
+    three random k each, or a flag when its Hermiticity gate raises.  tests/golden/fuzz.npz"""
+    out = {"n_seeds": np.array(FUZZ_SEEDS)}
+    for seed in range(FUZZ_SEEDS):
+        spec = W.random_spec(seed)
+        ks = np.random.default_rng(seed).random((3, 3)) * 2 - 0.5
+        st, ham = quiet(W.instantiate, spec, ref, ref.scaling, numba=0)
+        out[f"k_{seed}"] = ks
+        try:
+            ev, vec = quiet(ham.solve_kpath, list(ks), eig_vectors=True, soc=spec["soc"], parallel=0)
+            out[f"ev_{seed}"] = np.asarray(ev)
+            out[f"pw_{seed}"] = np.abs(np.asarray(vec)) ** 2              # |U|^2 per (band, k, component)
+            out[f"raises_{seed}"] = np.array(0)
+        except Exception as exc:                                         # noqa: BLE001 - the reference raises bare Exception
+            assert "not hermitian" in str(exc)
+            out[f"raises_{seed}"] = np.array(1)
+    np.savez_compressed(os.path.join(OUT, "fuzz.npz"), **out)
+    print("fuzz.npz:", FUZZ_SEEDS, "models,", sum(int(out[f"raises_{s}"]) for s in range(FUZZ_SEEDS)), "raise")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
     if "--next-rows-only" in sys.argv:
         next_rows_fixture(ref)
         return
+    if "--fuzz-only" in sys.argv:
+        fuzz_fixture(ref)
+        return
+    fuzz_fixture(ref)
     next_rows_fixture(ref)
     sk_fixture(ref)
     kmesh_fixture(ref)

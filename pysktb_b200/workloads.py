@@ -176,8 +176,58 @@ def d_soc_nonhermitian():
                 soc=True)
 
 
+def random_spec(seed=0):
+    """Seeded random model for parity fuzzing (not a reference example): triclinic cell, 1-3 atoms of two elements,
+    random orbital subsets (whole or partial shells, optionally the excited S orbital), random on-site terms, SOC
+    strengths, hoppings (some through distance laws), periodicity and cut-offs.  f shells come without d-f hoppings
+    and no model has lambda_d, so the reference's Hermiticity gate passes."""
+    r = np.random.default_rng(1000 + seed)
+    a = float(r.uniform(2.2, 3.6))
+    lat = (np.eye(3) + 0.12 * r.standard_normal((3, 3))).tolist()
+    P, D, F = ["px", "py", "pz"], ["dxy", "dyz", "dxz", "dx2-y2", "dz2"], list(SPDF[9:16])
+
+    def orbitals():
+        o = []
+        if r.random() < 0.7: o += ["s"]
+        if r.random() < 0.75: o += P if r.random() < 0.7 else [P[i] for i in sorted(r.choice(3, size=int(r.integers(1, 3)), replace=False))]
+        if r.random() < 0.45: o += D if r.random() < 0.6 else [D[i] for i in sorted(r.choice(5, size=int(r.integers(1, 5)), replace=False))]
+        if r.random() < 0.25: o += F if r.random() < 0.6 else [F[i] for i in sorted(r.choice(7, size=int(r.integers(1, 7)), replace=False))]
+        if r.random() < 0.2: o += ["S"]
+        return o or ["s"]
+    orbs = {"A": orbitals(), "B": orbitals()}
+    n_atoms = int(r.integers(1, 4))
+    els = ["A"] + [("A", "B")[int(r.integers(0, 2))] for _ in range(n_atoms - 1)]
+    atoms = [(el, r.random(3).round(3).tolist(), orbs[el]) for el in els]
+    periodicity = [None, [True, True, True], [True, True, False], [True, False, False], [False, True, True]][int(r.integers(0, 5))]
+
+    def onsite():
+        t = {"e_s": float(r.normal()), "e_p": ([float(x) for x in r.normal(size=3)] if r.random() < 0.4 else float(r.normal())),
+             "e_d": float(r.normal()), "e_f": float(r.normal()), "e_S": float(r.normal() + 3)}
+        if r.random() < 0.7: t["lambda" if r.random() < 0.5 else "lambda_p"] = float(r.uniform(0.02, 0.3))
+        if r.random() < 0.5: t["lambda_f"] = float(r.uniform(0.02, 0.3))
+        return t
+
+    def hop(d0):
+        t = {}
+        for n in ("V_sss", "V_sps", "V_pps", "V_ppp", "V_sds", "V_pds", "V_pdp", "V_dds", "V_ddp", "V_ddd", "V_sfs", "V_pfs",
+                  "V_pfp", "V_ffs", "V_ffp", "V_ffd", "V_fff", "V_SSs", "V_sSs", "V_Sps", "V_Sds", "V_Sfs"):
+            x = float(r.normal() * 0.5)
+            u = r.random()
+            if u < 0.15: t[n] = law("Harrison", V0=x, d0=d0, cutoff=3.0 * d0)
+            elif u < 0.25: t[n] = law("Exponential", V0=x, d0=d0, alpha=float(r.uniform(0.8, 2.0)))
+            elif u < 0.32: t[n] = law("PowerLaw", V0=x, d0=d0, eta=float(r.uniform(1.5, 4.0)))
+            else: t[n] = x
+        for n in ("V_dfs", "V_dfp", "V_dfd"): t[n] = 0.0
+        return t
+    nn = float(a * r.uniform(0.75, 1.15))
+    params = {"A": onsite(), "B": onsite(), "AA": hop(0.8 * a), "AB": hop(0.7 * a), "BB": hop(0.8 * a)}
+    cut = {k: {"NN": nn * float(r.uniform(0.9, 1.1))} for k in ("AA", "AB", "BB")}
+    return dict(name=f"random_{seed}", lattice=lat, a=a, atoms=atoms, periodicity=periodicity, bond_cut=cut, params=params,
+                soc=bool(r.random() < 0.7))
+
+
 ALL = {f.__name__: f for f in (cubic_sp3, cubic_s, graphene_pz, sb_buckled, ce_spdf_1atom, ce_partial, ce_spdf_2atom, ce_spf_example,
-                               zigzag_ribbon, sp_chain, lowsym_spd, d_soc_nonhermitian)}
+                               zigzag_ribbon, sp_chain, lowsym_spd, d_soc_nonhermitian, random_spec)}
 
 
 def resolve(params, scaling_ns):

@@ -131,3 +131,27 @@ def test_next_rows_oracle_vs_reference():
             fb, nk1, dim = (int(x) for x in g[tag + "_emean_args"])
             assert abs(O.total_energy_mean(m, fb, nk1, dim, soc=spec["soc"]) - float(g[tag + "_emean"])) < 1e-9
 
+
+
+def _fuzz_moment(ev, pw):
+    """Rotation-invariant (within degenerate subspaces) summary of eigenvectors: sum_n |U_nkc|^2 / (1 + eps_n^2)."""
+    return np.einsum("nkc,nk->kc", pw, 1.0 / (1.0 + np.asarray(ev) ** 2))
+
+
+def test_fuzz_oracle_vs_reference():
+    """48 seeded random models (orbital subsets, partial shells, S orbital, laws, periodicities): the oracle against the
+    reference's eigenvalues / eigenvector weights, and the same Hermiticity-gate exceptions."""
+    from pysktb_b200 import workloads as W
+    g = golden("fuzz")
+    for seed in range(int(g["n_seeds"])):
+        spec = W.random_spec(seed)
+        om = oracle_model(spec)
+        ks = g[f"k_{seed}"]
+        if int(g[f"raises_{seed}"]):
+            with pytest.raises(Exception, match="not hermitian"):
+                om.solve_kpath(list(ks), soc=spec["soc"])
+            continue
+        ev, vec = om.solve_kpath(list(ks), eig_vectors=True, soc=spec["soc"])
+        np.testing.assert_allclose(ev, g[f"ev_{seed}"], rtol=0, atol=1e-10, err_msg=spec["name"])
+        np.testing.assert_allclose(_fuzz_moment(ev, np.abs(vec) ** 2), _fuzz_moment(g[f"ev_{seed}"], g[f"pw_{seed}"]),
+                                   rtol=1e-8, atol=1e-10, err_msg=spec["name"])
