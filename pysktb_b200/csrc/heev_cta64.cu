@@ -144,7 +144,6 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     double* zstore = reinterpret_cast<double*>(vstore + (size_t)nm * PAIR_VSTORE_CPLX);
     int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nm * 1024);
     const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16;
-    const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * 32 * DSTRIDE * 8;
     void (*kW)(SmallArgs, cplx*, cplx*) = evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, false>;
     auto kB = tql_small_kernel<32, 32>;
