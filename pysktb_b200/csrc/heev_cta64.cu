@@ -98,9 +98,24 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false>, C64_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, vecql64_kernel<0>, 32, smemQ);
     if (occA < 1 || occQ < 1) { *info = "vec64 kernels do not fit"; return -1; }
-    C64Args a{H, N, nm, de, vstore, nullptr};
+    static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
+    cplx* blk32 = reinterpret_cast<cplx*>(zstore);          // the trailing blocks are consumed before Z is written
+    C64Args a{H, N, nm, de, vstore, split ? blk32 : nullptr};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
-    tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);
+    if (split) {
+        // steps 0..31 in the CTA kernel, the trailing 32 x 32 block (steps 32..62) in the one-warp-per-matrix kernel,
+        // its reflectors into rows / columns 32.. of the same [64][64] store
+        tridiag_cta64_kernel<true><<<gridA, C64_THREADS, 0, st>>>(a);
+        SmallArgs w{};
+        w.k = nullptr; w.mesh0 = w.mesh1 = w.mesh2 = 1; w.first = 0; w.nk = nm; w.N = N - 32; w.soc = 0;
+        w.scratch = de; w.flags = nullptr; w.flag_off = 0; w.Hsrc = blk32; w.Hld = 32; w.out_stride = 128; w.d_off = 32; w.e_off = 96;
+        w.v_per_k = C64_VSTORE_CPLX; w.v_stride = 64; w.v_off = 32; w.v_tau = 4096;
+        const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16;
+        const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nm + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 2));
+        pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true><<<gridW, PAIR_WARPS * 32, smemW, st>>>(w, nullptr, vstore);
+    } else {
+        tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);
+    }
     Vec64Args v{de, vstore, nm, N, evals, evecs, ld, col0, fail};
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occQ));
     static const bool use_list = !(getenv("SKTB_VEC_LIST") && getenv("SKTB_VEC_LIST")[0] == '0');
@@ -128,10 +143,10 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     vecbt64_kernel<0><<<gridV, 128, smemV64, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[256];
-    snprintf(buf, sizeof buf, "tridiag_cta64<vec> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d", gridA, C64_THREADS,
-             occA, gridQ, smemQ, occQ, gridV, N);
+    snprintf(buf, sizeof buf, "tridiag_cta64<vec%s> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d",
+             split ? ",split + pair_wide32<load,full,vec>" : "", gridA, C64_THREADS, occA, gridQ, smemQ, occQ, gridV, N);
     *info = buf;
-    return 2 + nql;
+    return 2 + nql + (split ? 1 : 0);
 }
 
 int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,

@@ -44,7 +44,8 @@ struct PairBuf {
     double* D;                       // [LN] diagonal
     cplx* vst = nullptr;             // global [32][32] reflector store of this matrix (eigenvector path) or NULL
     cplx* taust = nullptr;           // global [32] tau
-    int voff = 0;                    // row / reflector offset of this (sub)matrix inside the 32 x 32 store
+    int voff = 0;                    // row / reflector offset of this (sub)matrix inside the store
+    int vstride = 32;                // row stride of the store (32, or 64 when the block is the tail of a 64-wide matrix)
 };
 template <int LN> __host__ __device__ constexpr int pair_buf_cplx() { return 8 * LN + 2 + LN / 2; }   // V0 | V1 | P | X | alpha, pad | D
 
@@ -177,7 +178,7 @@ SKTB_D void pair_finish(PairCarry& c, const cplx (&z)[2], const cplx (&acol)[2],
                                      // step LN-1 at the end of the last phase must not write (it would land in tau[])
         if (L.h == 0) {
 #pragma unroll
-            for (int s = 2 - NS; s < 2; ++s) S.vst[(size_t)(jn + S.voff) * 32 + S.voff + (s ? L.iB : L.iA)] = c.v[s];
+            for (int s = 2 - NS; s < 2; ++s) S.vst[(size_t)(jn + S.voff) * S.vstride + S.voff + (s ? L.iB : L.iA)] = c.v[s];
         }
         if (L.l == 0) S.taust[jn + S.voff] = tau;
     }
@@ -429,7 +430,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         long long kq = kcta + warp;
         const bool k_ok = kq < a.nk;
         if (!k_ok) kq = a.nk - 1;
-        if (VEC) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
+        if (VEC) {
+            S_.vst = vstore + (size_t)kq * (a.v_per_k ? a.v_per_k : PAIR_VSTORE_CPLX);
+            S_.taust = S_.vst + (a.v_tau ? a.v_tau : 1024);
+            S_.vstride = a.v_stride ? a.v_stride : 32; S_.voff = a.v_off;
+        }
         cplx B[2][16];
         if (LOAD) pair_load(B, a.Hsrc + (size_t)kq * (a.Hld ? a.Hld * a.Hld : a.N * a.N), a.N, a.Hld ? a.Hld : a.N, L);
         else {

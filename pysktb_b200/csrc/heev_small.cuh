@@ -58,6 +58,8 @@ struct SmallArgs {
     const cplx* Hsrc = nullptr; // pair kernels in LOAD mode (sktb_heev): [nk][N][N] row-major matrices instead of K0+K1
     int Hld = 0;                // LOAD mode: leading dimension / matrix stride of Hsrc (0 -> N); tridiag_cta64's 32 x 32 blocks use 32
     int out_stride = 0, d_off = 0, e_off = 0;   // pair kernels: (d,e) record layout, 0 -> [2][32] per k; the cta64 split writes into [2][64] at 32
+    int v_per_k = 0, v_stride = 0, v_off = 0, v_tau = 0;   // reflector store layout (eigenvector path), 0 -> [32][32] + tau at 1024;
+                                                            // the cta64 split stores rows / reflectors 32.. of a [64][64] + tau at 4096 record
 };
 
 struct TqlArgs {

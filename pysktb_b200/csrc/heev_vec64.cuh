@@ -114,22 +114,29 @@ __global__ void __launch_bounds__(32) vecql64_kernel(Vec64Args a, double* __rest
 template <int J0>
 SKTB_D void vec64_backtransform4(cplx (&u)[32], const cplx* __restrict__ vst, const cplx* __restrict__ taust, const int N, const int h) {
     constexpr int LI0 = J0 >= 32 ? J0 + 1 - 32 : 0;
+    // reflectors 32.. live entirely in rows 33..63: the row half h = 0 contributes nothing (and, when the trailing
+    // block was tridiagonalised by the 32-wide kernel, its rows 0..31 of the store are not written at all)
+    const bool idle = J0 >= 32 && h == 0;
 #pragma unroll 1
     for (int j = J0 + 3; j >= J0; --j) {
         if (j > N - 2) continue;
         const cplx* v = vst + (size_t)j * 64 + 32 * h;
         cplx dot = cmake(0.0, 0.0), dot2 = cmake(0.0, 0.0);
+        if (!idle) {
 #pragma unroll
-        for (int i = LI0; i < 32; i += 2) {
-            cfmac(dot, v[i], u[i]);
-            if (i + 1 < 32) cfmac(dot2, v[i + 1], u[i + 1]);
+            for (int i = LI0; i < 32; i += 2) {
+                cfmac(dot, v[i], u[i]);
+                if (i + 1 < 32) cfmac(dot2, v[i + 1], u[i + 1]);
+            }
         }
         dot = cadd(dot, dot2);
         dot.x += __shfl_xor_sync(0xffffffffu, dot.x, 1);
         dot.y += __shfl_xor_sync(0xffffffffu, dot.y, 1);
         const cplx t = cmul(taust[j], dot);
+        if (!idle) {
 #pragma unroll
-        for (int i = LI0; i < 32; ++i) cfms(u[i], t, v[i]);
+            for (int i = LI0; i < 32; ++i) cfms(u[i], t, v[i]);
+        }
     }
 }
 

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
     cplx* w = v + N;
     cplx* v2 = w + N;
     cplx* sA = v2 + N + (a.SMEM_RED ? blockDim.x : 0);   // N*N when SMEM_A (after the R x NP partial sums; never with NB > 0)
-    __shared__ int s_lo, s_hi, s_done;
+    __shared__ int s_lo, s_hi;
     const int n_rows = a.n_rows;
 
     for (int mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
