@@ -28,19 +28,21 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     double* de = scratch;
     cplx* blk32 = reinterpret_cast<cplx*>(scratch + (size_t)nm * 128);
     cplx* blk16 = blk32 + (size_t)nm * 1024;
-    C64Args a{H, N, nm, de, nullptr, split ? blk32 : nullptr};
+    static const bool front = !(getenv("SKTB_CTA64_FRONT") && getenv("SKTB_CTA64_FRONT")[0] == '0');
+    const int off = front ? 64 - N : 0;                     // front padding: steps over the padding are skipped
+    C64Args a{H, N, nm, de, nullptr, split ? blk32 : nullptr, front ? 1 : 0};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
     int launches = 2;
     if (split) {
         tridiag_cta64_kernel<true><<<gridA, C64_THREADS, 0, st>>>(a);
         SmallArgs w{};
-        w.k = nullptr; w.mesh0 = w.mesh1 = w.mesh2 = 1; w.first = 0; w.nk = nm; w.N = N - 32; w.soc = 0;
-        w.scratch = de; w.flags = nullptr; w.flag_off = 0; w.Hsrc = blk32; w.Hld = 32; w.out_stride = 128; w.d_off = 32; w.e_off = 96;
+        w.k = nullptr; w.mesh0 = w.mesh1 = w.mesh2 = 1; w.first = 0; w.nk = nm; w.N = front ? 32 : N - 32; w.soc = 0;
+        w.scratch = de; w.flags = nullptr; w.flag_off = 0; w.Hsrc = blk32; w.Hld = 32; w.out_stride = 128; w.d_off = 32 - off; w.e_off = 96 - off;
         const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16, smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
         const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nm + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 2));
         pair_wide32_kernel<PAIR_SRC_LOAD, 4, false, false><<<gridW, PAIR_WARPS * 32, smemW, st>>>(w, blk16, nullptr);
         const unsigned gridT = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
-        pair_tail16_kernel<8><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, de, nm, 128, 32, 96);
+        pair_tail16_kernel<8><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, de, nm, 128, 32 - off, 96 - off);
         launches = 4;
     } else {
         tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);

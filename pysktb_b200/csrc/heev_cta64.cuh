@@ -173,23 +173,28 @@ SKTB_D void c64_step(cplx (&B)[2][16], PairCarry& c, const int j, const C64Lane&
     c64_finish<NS>(c, ypart, xo, beta, tau, scale, jn, L, S);
 }
 
-// SPLIT: stop after the two-slot phases (steps 0..31); the trailing 32 x 32 block goes to the N <= 32 kernels
+// SPLIT: stop after the two-slot phases (steps 0..31); the trailing 32 x 32 block goes to the N <= 32 kernels.
+// J0 (a multiple of 8, CTA-uniform): phases whose steps lie before J0 are skipped - the caller loaded the register
+// window as it would stand at step J0 (front-padded matrices: those steps would only walk over zero padding).
 template <int HALF, bool SPLIT>
-SKTB_D void c64_phases(cplx (&B)[2][16], PairCarry& c, int& j, const C64Lane& L, const C64Smem& S) {
+SKTB_D void c64_phases(cplx (&B)[2][16], PairCarry& c, int& j, const int J0, const C64Lane& L, const C64Smem& S) {
     constexpr int NS = HALF > 8 ? 2 : 1;
+    constexpr int JSTART = 4 * (16 - HALF);
+    if (J0 <= JSTART) {
 #pragma unroll 1
-    for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 2; ++it) {
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q, ++j)
-            if (j <= 62) c64_step<HALF, NS>(B, c, j, L, S);       // step 63 does not exist (warp-uniform guard)
+            for (int q = 0; q < 4; ++q, ++j)
+                if (j <= 62) c64_step<HALF, NS>(B, c, j, L, S);       // step 63 does not exist (warp-uniform guard)
 #pragma unroll
-        for (int s = 2 - NS; s < 2; ++s) {
+            for (int s = 2 - NS; s < 2; ++s) {
 #pragma unroll
-            for (int m = 0; m + 1 < HALF; ++m) B[s][m] = B[s][m + 1];
-            B[s][HALF - 1] = cmake(0.0, 0.0);
+                for (int m = 0; m + 1 < HALF; ++m) B[s][m] = B[s][m + 1];
+                B[s][HALF - 1] = cmake(0.0, 0.0);
+            }
         }
     }
-    if constexpr (HALF > 2 && !(SPLIT && HALF - 2 <= 8)) c64_phases<HALF - 2, SPLIT>(B, c, j, L, S);
+    if constexpr (HALF > 2 && !(SPLIT && HALF - 2 <= 8)) c64_phases<HALF - 2, SPLIT>(B, c, j, J0, L, S);
 }
 
 struct C64Args {
@@ -198,7 +203,40 @@ struct C64Args {
     double* scratch;        // [nm][2][64]  (d | e)
     cplx* vstore = nullptr; // [nm][C64_VSTORE_CPLX] reflectors + tau (eigenvector path) or NULL
     cplx* blocks = nullptr; // SPLIT: [nm][32][32] trailing block after step 31 (row-major, full rows)
+    int front = 0;          // 1: N < 64 is padded at the FRONT of the 64-wide frame (rows / columns < 64 - N are zero), so
+                            // that the steps over the padding can be skipped: the run starts at step 8 * ((64 - N) / 8)
 };
+
+// prologue (pivot column J0: class 0, register 0 of a window whose base is J0; registers beyond the live window and
+// X beyond row 63 are zero, so the loop runs over all 16 registers) + phases
+template <bool SPLIT>
+SKTB_D void c64_run(cplx (&B)[2][16], PairCarry& c, const int J0, const C64Lane& L, const C64Smem& S) {
+    {
+        cplx x[2] = {B[0][0], B[1][0]};
+        c64_publish<2>(x, J0, L.h == 0, L, S);
+        __syncthreads();
+        cplx xo[2];
+        double beta; cplx tau, scale;
+        c64_reflector<2>(L, S, xo, beta, tau, scale);
+        const cplx* Xl = S.X + J0 + L.h;
+        cplx ypart[2];
+        ypart[0] = ypart[1] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const cplx xq = Xl[4 * m];
+            cfma(ypart[0], B[0][m], xq); cfma(ypart[1], B[1][m], xq);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            cplx yp = cmul(scale, ypart[s]);
+            yp.x += (L.h == 1) ? B[s][0].x : 0.0; yp.y += (L.h == 1) ? B[s][0].y : 0.0;     // column J0+1 = class 1, register 0
+            ypart[s] = yp;
+        }
+        c64_finish<2>(c, ypart, xo, beta, tau, scale, J0, L, S);
+    }
+    int j = J0;
+    c64_phases<16, SPLIT>(B, c, j, J0, L, S);
+}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a) {
@@ -210,9 +248,11 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
     for (int q = t; q < C64_SMEM_CPLX; q += C64_THREADS) smem[q] = cmake(0.0, 0.0);
     __syncthreads();
     const int N = a.N;
+    const int off = a.front ? 64 - N : 0;                   // first real row / column of the frame
+    const int J0 = off & ~7;                                // first step that is run (a multiple of 8: a phase boundary)
 #pragma unroll 1
     for (long long km = blockIdx.x; km < a.nm; km += gridDim.x) {
-        // ---- load rows iA, iB x columns 4m + h with zheevd(UPLO='L') semantics: upper triangle = conj(lower) ----
+        // ---- load rows iA, iB x columns J0 + 4m + h with zheevd(UPLO='L') semantics: upper triangle = conj(lower) ----
         const cplx* H = a.H + (size_t)km * N * N;
         if (a.vstore) { S.vst = a.vstore + (size_t)km * C64_VSTORE_CPLX; S.taust = S.vst + 4096; }
         cplx B[2][16];
@@ -220,11 +260,11 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
         // together; conjugation / real diagonal / zero padding are applied to the loaded value
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            const int i = s ? L.iB : L.iA;
+            const int i = (s ? L.iB : L.iA) - off;
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
-                const int col = 4 * m + L.h;
-                const bool ok = i < N && col < N;
+                const int col = J0 + 4 * m + L.h - off;
+                const bool ok = i >= 0 && col >= 0 && i < N && col < N;
                 const int hi = ok ? max(i, col) : 0, lo = ok ? min(i, col) : 0;
                 cplx e = H[(size_t)hi * N + lo];
                 if (col > i) e.y = -e.y;
@@ -233,37 +273,12 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
                 B[s][m] = e;
             }
         }
-        // ---- prologue: pivot column 0 (class 0, register 0), plain mat-vec ----
         PairCarry c;
         c.eval = 0.0;
-        {
-            cplx x[2] = {B[0][0], B[1][0]};
-            c64_publish<2>(x, 0, L.h == 0, L, S);
-            __syncthreads();
-            cplx xo[2];
-            double beta; cplx tau, scale;
-            c64_reflector<2>(L, S, xo, beta, tau, scale);
-            const cplx* Xl = S.X + L.h;
-            cplx ypart[2];
-            ypart[0] = ypart[1] = cmake(0.0, 0.0);
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const cplx xq = Xl[4 * m];
-                cfma(ypart[0], B[0][m], xq); cfma(ypart[1], B[1][m], xq);
-            }
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                cplx yp = cmul(scale, ypart[s]);
-                yp.x += (L.h == 1) ? B[s][0].x : 0.0; yp.y += (L.h == 1) ? B[s][0].y : 0.0;     // column 1 = class 1, register 0
-                ypart[s] = yp;
-            }
-            c64_finish<2>(c, ypart, xo, beta, tau, scale, 0, L, S);
-        }
-        int j = 0;
-        c64_phases<16, SPLIT>(B, c, j, L, S);
-        if (t < 64) {
+        c64_run<SPLIT>(B, c, J0, L, S);
+        if (t >= off && t < 64) {
             double* out = a.scratch + (size_t)km * 128;
-            if (!SPLIT || t < 32) { out[t] = S.D[t]; out[64 + t] = S.E[t]; }       // SPLIT: d[0..31], e[0..31]; the rest comes from the 32-wide kernels
+            if (!SPLIT || t < 32) { out[t - off] = S.D[t]; out[64 + t - off] = S.E[t]; }   // SPLIT: d, e of steps < 32; the rest comes from the 32-wide kernels
         }
         if (SPLIT) {    // slot B = rows 32..63; registers 0..7 hold columns 32 + 4m + h (base = 32 after 32 steps)
             cplx* blk = a.blocks + (size_t)km * 1024 + (size_t)(31 - L.r) * 32 + L.h;
