@@ -27,6 +27,16 @@ SKTB_D double fast_rsqrt(double a) {
     const double c = fma(e, 0.375, 0.5);
     return fma(c, y * e, y);
 }
+// 1/a: hardware seed and two Newton steps (full double precision for normal a), no slow path
+SKTB_D double fast_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
 #endif
 // acc += a*b
 SKTB_HD void cfma(cplx& acc, cplx a, cplx b) {

@@ -10,7 +10,7 @@ size_t cta64_bytes_per_k() { return (size_t)128 * 8 + (size_t)1024 * 16 + (size_
 // pair_wide32<LOAD> (steps 32..47, one warp per matrix) -> pair_tail16 (steps 48..62, two matrices per warp) -> tql<64>.
 // SKTB_CTA64_SPLIT=0: all 63 steps in tridiag_cta64.
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
-                 std::string* info) {
+                 std::string* info, int h_ld, long long h_mstride, long long h_off, bool tridiag_only) {
     constexpr int NC = 64;
     if (N <= 32 || N > 64) { *info = "launch_cta64: N out of range"; return -1; }
     static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
@@ -30,7 +30,7 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     cplx* blk16 = blk32 + (size_t)nm * 1024;
     static const bool front = !(getenv("SKTB_CTA64_FRONT") && getenv("SKTB_CTA64_FRONT")[0] == '0');
     const int off = front ? 64 - N : 0;                     // front padding: steps over the padding are skipped
-    C64Args a{H, N, nm, de, nullptr, split ? blk32 : nullptr, front ? 1 : 0};
+    C64Args a{H, N, nm, de, nullptr, split ? blk32 : nullptr, h_ld, h_mstride, h_off, front ? 1 : 0};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
     int launches = 2;
     if (split) {
@@ -49,7 +49,8 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     }
     TqlArgs t{de, nm, N, evals, ld, col0, fail};
     const unsigned gridB = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * occB));
-    kB<<<gridB, SMALL_WARPS * 32, smemB, st>>>(t);
+    if (tridiag_only) --launches;       // the caller merges (d, e) with its own leading steps
+    else kB<<<gridB, SMALL_WARPS * 32, smemB, st>>>(t);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[320];
     snprintf(buf, sizeof buf, "hk + tridiag_cta64%s grid=%u x %d thr %d CTA/SM%s + tql_small<64> grid=%u smem=%zuB %d CTA/SM; N=%d", split ? "<split>" : "",
@@ -102,7 +103,7 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     if (occA < 1 || occQ < 1) { *info = "vec64 kernels do not fit"; return -1; }
     static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
     cplx* blk32 = reinterpret_cast<cplx*>(zstore);          // the trailing blocks are consumed before Z is written
-    C64Args a{H, N, nm, de, vstore, split ? blk32 : nullptr};
+    C64Args a{H, N, nm, de, vstore, split ? blk32 : nullptr, 0, 0, 0, 0};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
     if (split) {
         // steps 0..31 in the CTA kernel, the trailing 32 x 32 block (steps 32..62) in the one-warp-per-matrix kernel,

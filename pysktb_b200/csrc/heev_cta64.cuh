@@ -203,6 +203,8 @@ struct C64Args {
     double* scratch;        // [nm][2][64]  (d | e)
     cplx* vstore = nullptr; // [nm][C64_VSTORE_CPLX] reflectors + tau (eigenvector path) or NULL
     cplx* blocks = nullptr; // SPLIT: [nm][32][32] trailing block after step 31 (row-major, full rows)
+    int ld = 0; long long mstride = 0, hoff = 0;   // input layout: element (r, c) of matrix km at H[km * mstride + hoff + r * ld + c]
+                            // (0 -> dense [N][N]); a peeled run passes the trailing block of a larger matrix in place
     int front = 0;          // 1: N < 64 is padded at the FRONT of the 64-wide frame (rows / columns < 64 - N are zero), so
                             // that the steps over the padding can be skipped: the run starts at step 8 * ((64 - N) / 8)
 };
@@ -253,7 +255,8 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
 #pragma unroll 1
     for (long long km = blockIdx.x; km < a.nm; km += gridDim.x) {
         // ---- load rows iA, iB x columns J0 + 4m + h with zheevd(UPLO='L') semantics: upper triangle = conj(lower) ----
-        const cplx* H = a.H + (size_t)km * N * N;
+        const int ldh = a.ld ? a.ld : N;
+        const cplx* H = a.H + (size_t)km * (a.mstride ? a.mstride : (long long)N * N) + a.hoff;
         if (a.vstore) { S.vst = a.vstore + (size_t)km * C64_VSTORE_CPLX; S.taust = S.vst + 4096; }
         cplx B[2][16];
         // branch-free: the address of the lower-triangle element is clamped, all 32 loads are independent and in flight
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
                 const int col = J0 + 4 * m + L.h - off;
                 const bool ok = i >= 0 && col >= 0 && i < N && col < N;
                 const int hi = ok ? max(i, col) : 0, lo = ok ? min(i, col) : 0;
-                cplx e = H[(size_t)hi * N + lo];
+                cplx e = H[(size_t)hi * ldh + lo];
                 if (col > i) e.y = -e.y;
                 if (col == i) e.y = 0.0;
                 if (!ok) e = cmake(0.0, 0.0);

@@ -818,7 +818,7 @@ inline int padded_nc(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 12 ? 12 : 
 // scratch: >= nm * cta64_bytes_per_k() bytes.  Returns the number of kernels launched or -1 (text in *info).
 size_t cta64_bytes_per_k();
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
-                 std::string* info);
+                 std::string* info, int h_ld = 0, long long h_mstride = 0, long long h_off = 0, bool tridiag_only = false);
 
 // N <= 32 with eigenvectors (no gate): pair-layout tridiagonalisation keeping the reflectors -> vec32_kernel
 // (QL with accumulation, sort, back-transformation).  evecs: [N][ld][N] complex (reference layout [band, k, comp]).

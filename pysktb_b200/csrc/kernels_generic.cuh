@@ -133,6 +133,9 @@ struct HeevArgs {
     int* fail;          // incremented when QL exceeds its iteration limit
     int NP, SMEM_RED;   // column count padded to a warp multiple; blockDim.x = NP * R (R threads per column)
     int NB;             // > 0: panel formulation with NB (2, 4 or 8) deferred reflector pairs
+    void* peel_ws;      // host only: scratch of >= nm * peel_bytes_per_k(N) bytes enables the peeled run (64 < N <= 160, eigenvalues)
+    int peel; double* peel_de;   // phase 3: run only the first `peel` steps (a multiple of NB) of the panel formulation, leave the
+                        // updated trailing (N - peel)^2 block in H and write d, e of the peeled steps to peel_de[mat][2][peel]
     int phase;          // 0: whole solve; 1: tridiagonalise and park (d, e) in H; 2: QL + output from the parked (d, e)
 };
 
@@ -222,7 +225,8 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             const bool mine = i < N;
             cplx tau = cmake(0.0, 0.0);
             int tlast = 0;
-            for (int j0 = 0; j0 + 1 < N; j0 += NB) {
+            const int jstop = a.peel > 0 ? a.peel : N;
+            for (int j0 = 0; j0 + 1 < N && j0 < jstop; j0 += NB) {
                 const int tmax = min(NB, N - 1 - j0);
                 for (int t = 0; t < tmax; ++t) {
                     const int j = j0 + t;
@@ -320,6 +324,12 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                     tlast = 0;
                     __syncthreads();
                 }
+            }
+            if (a.peel > 0) {                                             // peeled run: the register-resident kernels take the trailing block
+                double* de = a.peel_de + (size_t)mat * 2 * a.peel;
+                for (int idx = tid; idx < a.peel; idx += T) { de[idx] = d[idx]; de[a.peel + idx] = e[idx]; }
+                __syncthreads();
+                continue;
             }
             if (i == N - 1) {                                             // last diagonal entry, with the open panel applied
                 cplx c = A[(size_t)i * N + i];
@@ -647,6 +657,65 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Eigenvalues of the tridiagonal matrices of a peeled run: (d, e) of the first P steps from the generic kernel
+// (head[mat][2][P]) and of the trailing Nt x Nt block from the register-resident kernels (tail[mat][128]: d at 0..,
+// e at 64..).  One CTA per matrix, one eigenvalue per thread: bisection on the Sturm count (dstebz recurrence).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bisect_merge_kernel(const double* __restrict__ head, int P, const double* __restrict__ tail, int Nt, long long nm,
+                                    double* __restrict__ evals, long long ld, long long col0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P + Nt, tid = threadIdx.x, T = blockDim.x;
+    double* d = reinterpret_cast<double*>(smem_raw);
+    double* e2 = d + N;
+    double* red = e2 + N;                                                 // [3][32]
+    for (long long mat = blockIdx.x; mat < nm; mat += gridDim.x) {
+        const double* hd = head + (size_t)mat * 2 * P;
+        const double* tl = tail + (size_t)mat * 128;
+        double lo_b = 1e300, hi_b = -1e300, emax = 0.0;
+        __syncthreads();
+        if (tid < N) {
+            const double di = tid < P ? hd[tid] : tl[tid - P];
+            auto eget = [&](int q) { return q < 0 || q >= N - 1 ? 0.0 : (q < P ? hd[P + q] : tl[64 + q - P]); };
+            const double el = fabs(eget(tid - 1)), er = fabs(eget(tid));
+            d[tid] = di; e2[tid] = er * er;
+            lo_b = di - el - er; hi_b = di + el + er;
+            emax = fmax(fabs(di), fmax(el, er));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo_b = fmin(lo_b, __shfl_xor_sync(0xffffffffu, lo_b, o));
+            hi_b = fmax(hi_b, __shfl_xor_sync(0xffffffffu, hi_b, o));
+            emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+        }
+        if ((tid & 31) == 0) { red[tid >> 5] = lo_b; red[32 + (tid >> 5)] = hi_b; red[64 + (tid >> 5)] = emax; }
+        __syncthreads();
+        const int nw = (T + 31) >> 5;
+        double gl = 1e300, gu = -1e300, tn = 0.0;
+        for (int q = 0; q < nw; ++q) { gl = fmin(gl, red[q]); gu = fmax(gu, red[32 + q]); tn = fmax(tn, red[64 + q]); }
+        const double eps = 2.220446049250313e-16;
+        const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, tn * tn), 1e-290);
+        gl -= 2.0 * eps * tn * N + 2.0 * pivmin; gu += 2.0 * eps * tn * N + 2.0 * pivmin;
+        if (tid < N) {
+            double lo = gl, hi = gu;
+            for (int it = 0; it < 128; ++it) {
+                const double x = 0.5 * (lo + hi);
+                if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
+                int cnt = 0;
+                double q = d[0] - x;
+                if (fabs(q) < pivmin) q = -pivmin;
+                cnt += q < 0.0;
+                for (int r = 1; r < N; ++r) {
+                    q = fma(-e2[r - 1], fast_rcp(q), d[r] - x);          // |q| >= pivmin: the reciprocal is finite
+                    if (fabs(q) < pivmin) q = -pivmin;
+                    cnt += q < 0.0;
+                }
+                if (cnt > tid) hi = x; else lo = x;
+            }
+            evals[(long long)tid * ld + col0 + mat] = 0.5 * (lo + hi);
+        }
     }
 }
 

@@ -359,9 +359,10 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
     // panel formulation for the sizes that stream the matrix through HBM/L2 (one column per thread, N <= 1024)
     static const int nb_env = getenv("SKTB_GENERIC_NB") ? atoi(getenv("SKTB_GENERIC_NB")) : 8;
     a.NB = 0;
-    if (!smemA && R == 1 && N <= 1024 && nb_env > 0 && phase != 2 && (N >= 96 || getenv("SKTB_GENERIC_NB"))) {
+    if (!smemA && R == 1 && N <= 1024 && nb_env > 0 && phase != 2 && (N >= 96 || phase == 3 || getenv("SKTB_GENERIC_NB"))) {
         int NB = nb_env >= 8 ? 8 : (nb_env >= 4 ? 4 : 2);
-        if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;     // measured: 4 wins below N ~ 160, none below N ~ 96
+        if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;
+        if (phase == 3) NB = 4;                                  // the peel count is a multiple of 4     // measured: 4 wins below N ~ 160, none below N ~ 96
         auto panel_bytes = [&](int nb) { return (size_t)2 * nb * N * sizeof(cplx) + (32 * 32 + 32) * sizeof(double); };
         while (NB > 2 && aux + panel_bytes(NB) > 200 * 1024) NB /= 2;
         if (aux + panel_bytes(NB) <= 200 * 1024) { a.NB = NB; aux += panel_bytes(NB); }
@@ -388,7 +389,33 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
 
 // Tracked rows with N > 64: tridiagonalisation (one 1-CTA-per-SM class kernel) and the serial-generator QL (small CTAs,
 // many matrices per SM) are two launches; everything else is one.
+// Peeled run (64 < N <= 160, eigenvalues only): the generic kernel does the first P steps (P = the multiple of 4 that
+// leaves a trailing block of 61..64), the register-resident kernels tridiagonalise that block in place, one
+// bisection kernel takes the merged (d, e).
+static const int PEEL_MAX = getenv("SKTB_PEEL_MAX") ? atoi(getenv("SKTB_PEEL_MAX")) : 160;
+static size_t peel_bytes_per_k(int N) { return (size_t)2 * (N - 60) * 8 + small::cta64_bytes_per_k(); }
+static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+    const int N = a.N;
+    const int P = (N - 64 + 3) / 4 * 4, Nt = N - P;
+    double* head = (double*)a.peel_ws;
+    double* c64s = head + (size_t)a.nm * 2 * P;
+    a.peel = P; a.peel_de = head;
+    int rc = launch_heev_generic_phase(p, a, st, 3);
+    if (rc) return rc;
+    std::string first = g_kinfo, info;
+    int rl = small::launch_cta64(a.H, Nt, a.nm, c64s, nullptr, 0, 0, p->d_fail, st, &info, N, (long long)N * N, (long long)P * N + P, true);
+    if (rl < 0) return fail("cta64 launch failed (peeled run): %s", info.c_str());
+    g_launches += rl;
+    const int T = (N + 31) / 32 * 32;
+    const size_t smem = ((size_t)2 * N + 96) * sizeof(double);
+    bisect_merge_kernel<<<(unsigned)std::min<long long>(a.nm, 148LL * 8), T, smem, st>>>(head, P, c64s, Nt, a.nm, a.evals, a.ld, a.col0);
+    LAUNCHED();
+    g_kinfo = "peel " + std::to_string(P) + " steps: " + first + " | " + info + " | bisect_merge";
+    return 0;
+}
+
 static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+    if (a.n_rows == 0 && a.peel_ws && a.N > 64 && a.N <= PEEL_MAX) return launch_heev_peel(p, a, st);
     static const bool no_split = getenv("SKTB_GENERIC_SPLIT") != nullptr && getenv("SKTB_GENERIC_SPLIT")[0] == '0';
     if (a.n_rows > 0 && a.N > 64 && a.N <= 1024 && !no_split) {
         int rc = launch_heev_generic_phase(p, a, st, 1);
@@ -499,6 +526,8 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
         long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));
         if (W.H.ensure(perH * chunk)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
         if (want_vecs && W.RT.ensure(perH * chunk)) return fail("out of device memory (RT workspace)");
+        const bool peel = !want_vecs && N > 64 && N <= PEEL_MAX;
+        if (peel && W.S.ensure(peel_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
         if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
         for (long long c0 = 0; c0 < nk; c0 += chunk) {
             long long cnt = std::min(chunk, nk - c0);
@@ -509,6 +538,7 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
             HeevArgs a{};
             a.H = (cplx*)W.H.p; a.N = N; a.nm = (int)cnt;
             a.evals = evals_d; a.ld = ld; a.col0 = k_off + c0;
+            if (peel) a.peel_ws = W.S.p;
             if (want_vecs) {
                 a.RT = (cplx*)W.RT.p; a.n_rows = N; a.rows = nullptr;
                 a.vec_out = (cplx*)evecs_d; a.vs_band = ld * N; a.vs_k = N; a.vcol0 = k_off + c0;
@@ -625,12 +655,15 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
     }
     long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / perH)));
     if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(perH * chunk))) return fail("out of device memory (heev workspace)");
+    const bool peel = !evecs_d && N > 64 && N <= PEEL_MAX && !heev_generic_only;
+    if (peel && p->ws[2].S.ensure(peel_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
     for (long long c0 = 0; c0 < nm; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)nm - c0);
         CK(cudaMemcpyAsync(p->ws[2].H.p, (const cplx*)H_d + (size_t)c0 * N * N, perH * cnt, cudaMemcpyDeviceToDevice, st));
         HeevArgs a{};
         a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
         a.evals = evals_d; a.ld = nm; a.col0 = c0;
+        if (peel) a.peel_ws = p->ws[2].S.p;
         if (evecs_d) {
             a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = N; a.rows = nullptr;
             a.vec_out = (cplx*)evecs_d; a.vs_band = (long long)nm * N; a.vs_k = N; a.vcol0 = c0;
