@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                     if (fabs(q) < pivmin) q = -pivmin;
                     cnt += q < 0.0;
                     for (int r = 1; r < N; ++r) {
-                        q = d[r] - x - e2[r - 1] / q;
+                        q = fma(-e2[r - 1], fast_rcp(q), d[r] - x);      // |q| >= pivmin: the reciprocal is finite
                         if (fabs(q) < pivmin) q = -pivmin;
                         cnt += q < 0.0;
                     }

@@ -836,6 +836,10 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 if (rl < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
                 g_launches += rl;
             } else {
+                if (!n_rows && N > 64 && N <= PEEL_MAX) {
+                    if (p->ws[2].S.ensure((size_t)cnt * peel_bytes_per_k(N))) return fail("out of device memory (peel workspace)");
+                    a.peel_ws = p->ws[2].S.p;
+                }
                 rc = launch_heev_generic(p, a, st);
                 if (rc) return rc;
             }
@@ -931,6 +935,9 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                 if (nr) {
                     a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = nr; a.rows = d_rows;
                     a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * nr; a.vs_k = nr; a.vcol0 = 0;
+                } else if (N > 64 && N <= PEEL_MAX) {
+                    if (p->ws[2].S.ensure((size_t)cnt * peel_bytes_per_k(N))) return fail("out of device memory (peel workspace)");
+                    a.peel_ws = p->ws[2].S.p;
                 }
                 rc = launch_heev_generic(p, a, st);
                 if (rc) return rc;

@@ -257,7 +257,30 @@ def test_large_ribbon_against_lapack_on_device_hamiltonian(tb):
     assert np.abs(h48.solve_kpath(list(k), soc=False) - m.solve_kpath(list(k), soc=False)).max() < EIG_TOL
 
 
-@pytest.mark.parametrize("N", [1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 47, 64, 96, 110, 111, 160])
+@pytest.mark.parametrize("n_chains", [33, 40, 64, 81, 120])
+def test_mid_size_ribbons_peeled_run(tb, n_chains):
+    """64 < N <= 240 (ribbons of 66 .. 240 pz orbitals): the peeled run (generic panel steps + register-resident kernels
+    on the trailing block + bisection) and, above N = 160, the generic kernel alone: eigenvalues against LAPACK on the
+    device-built H(k) (many k, so that the persistent CTAs loop), trace identity, and the DOS path against a Lorentzian
+    sum over the same eigenvalues."""
+    from oracle import sktb_oracle as O
+    from pysktb_b200 import workloads as W
+    spec = W.zigzag_ribbon(n_chains)
+    _, ham = W.instantiate(spec, tb, tb.scaling)
+    N = 2 * n_chains
+    k = np.stack([np.linspace(0, 1, 41, endpoint=False), np.zeros(41), np.zeros(41)], axis=1)
+    H = ham.get_ham_batch(k, l_soc=False)
+    ev = ham.solve_kpath(list(k), soc=False)
+    assert ev.shape == (N, 41)
+    for q in range(0, 41, 5):
+        assert np.abs(ev[:, q] - np.linalg.eigvalsh(H[q])).max() < EIG_TOL
+    assert np.abs(ev.sum(axis=0) - np.trace(H, axis1=1, axis2=2).real).max() < 1e-9
+    E = np.linspace(-3, 3, 33)
+    dos = tb.GreensFunction(ham).dos(E, nk=[41, 1, 1], eta=0.06, soc=False)
+    np.testing.assert_allclose(dos, O.lorentz_dos(ev, E, 0.06), rtol=1e-9)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 47, 64, 65, 68, 96, 110, 111, 128, 159, 160, 161])
 def test_heev_random_hermitian_vs_lapack(tb, N):
     """K2 alone (sktb_heev) on random complex matrices, lower-triangle semantics, both storage regimes."""
     import torch
