@@ -563,6 +563,53 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
     }
 }
 
+// Per-lane QL on the tridiagonal matrices of a peeled run (64 < N <= 160): (d, e) of the first P steps from the generic
+// kernel (head[mat][2][P]) and of the trailing Nt x Nt block from the register-resident kernels (tail[mat][128]: d at
+// 0.., e at 64..).  One matrix per lane like tql_small_kernel; the ascending order comes from a rank count in shared
+// memory (a register sorting network of this size would not fit).  Dynamic shared memory: warps * 2 * N * DSTRIDE * 8.
+template <int UNUSED>
+__global__ void __launch_bounds__(SMALL_WARPS * 32) tql_merge_kernel(const double* __restrict__ head, int P, const double* __restrict__ tail, int Nt,
+                                                                     long long nm, double* __restrict__ evals, long long ld, long long col0, int* fail) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int N = P + Nt;
+    double* dbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * N * DSTRIDE;
+    double* ebuf = dbuf + (size_t)N * DSTRIDE;
+    const long long n_batches = (nm + 31) / 32;
+#pragma unroll 1
+    for (long long batch = (long long)blockIdx.x * warps + warp; batch < n_batches; batch += (long long)gridDim.x * warps) {
+        const long long kbase = batch * 32;
+        const int cnt = (int)min((long long)32, nm - kbase);
+        const long long mat = kbase + min(lane, cnt - 1);
+        const double* hd = head + (size_t)mat * 2 * P;
+        const double* tl = tail + (size_t)mat * 128;
+#pragma unroll 4
+        for (int t = 0; t < P; ++t) { dbuf[t * DSTRIDE + lane] = hd[t]; ebuf[t * DSTRIDE + lane] = hd[P + t]; }
+#pragma unroll 4
+        for (int t = 0; t < Nt; ++t) { dbuf[(P + t) * DSTRIDE + lane] = tl[t]; ebuf[(P + t) * DSTRIDE + lane] = tl[64 + t]; }
+        __syncwarp();
+        if (tql_lane(dbuf + lane, ebuf + lane, N)) atomicAdd(fail, 1);
+        // ascending rank of every eigenvalue of this lane's matrix (ties by index), permuted into ebuf
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            const double di = dbuf[i * DSTRIDE + lane];
+            int rank = 0;
+#pragma unroll 4
+            for (int q = 0; q < N; ++q) {
+                const double dq = dbuf[q * DSTRIDE + lane];
+                rank += (dq < di || (dq == di && q < i)) ? 1 : 0;
+            }
+            ebuf[rank * DSTRIDE + lane] = di;
+        }
+        __syncwarp();
+        if (lane < cnt) {
+#pragma unroll 4
+            for (int q = 0; q < N; ++q) evals[(long long)q * ld + col0 + kbase + lane] = ebuf[q * DSTRIDE + lane];
+        }
+        __syncwarp();
+    }
+}
+
 #include "heev_pair.cuh"
 #include "heev_cta64.cuh"
 #include "heev_vec32.cuh"

@@ -406,6 +406,21 @@ static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     int rl = small::launch_cta64(a.H, Nt, a.nm, c64s, nullptr, 0, 0, p->d_fail, st, &info, N, (long long)N * N, (long long)P * N + P, true);
     if (rl < 0) return fail("cta64 launch failed (peeled run): %s", info.c_str());
     g_launches += rl;
+    // tridiagonal eigenvalues: per-lane QL (32 matrices per warp, ~40x fewer instructions than bisection, but one long
+    // serial chain per batch) once the batch fills the device, bisection (one eigenvalue per thread) for small batches
+    static const long long ql_min = getenv("SKTB_PEEL_QL_MIN") ? atoll(getenv("SKTB_PEEL_QL_MIN")) : 2048;
+    const size_t per_warp = (size_t)2 * N * small::DSTRIDE * sizeof(double);
+    const int warps = (int)std::min<size_t>(small::SMALL_WARPS, (200 * 1024) / per_warp);
+    if (a.nm >= ql_min && warps >= 1) {
+        const size_t smem = per_warp * warps;
+        CK(cudaFuncSetAttribute(small::tql_merge_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long batches = (a.nm + 31) / 32;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((batches + warps - 1) / warps, 148));
+        small::tql_merge_kernel<0><<<grid, warps * 32, smem, st>>>(head, P, c64s, Nt, a.nm, a.evals, a.ld, a.col0, p->d_fail);
+        LAUNCHED();
+        g_kinfo = "peel " + std::to_string(P) + " steps: " + first + " | " + info + " | tql_merge x" + std::to_string(warps) + " warps";
+        return 0;
+    }
     const int T = (N + 31) / 32 * 32;
     const size_t smem = ((size_t)2 * N + 96) * sizeof(double);
     bisect_merge_kernel<<<(unsigned)std::min<long long>(a.nm, 148LL * 8), T, smem, st>>>(head, P, c64s, Nt, a.nm, a.evals, a.ld, a.col0);
