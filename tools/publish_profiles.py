@@ -9,7 +9,8 @@ subprocess.run([sys.executable, os.path.join(R, "tools", "make_profile_summary.p
                 "ncu --set full summaries, round 1 final (T: N=32, 64^3 = 262144 k per launch; C4: N=64, 32^3; vec kernels: 65536 k (N=32) / 8192 k (N=64); "
                 "generic: N=512, 296 matrices; lorentz: C2 2048^2 x 400 E; n2: 4096^2)"] + reps, cwd=R, check=True)
 for src, dst in [("final_launches_T.csv", "r01_launches_T_bench256.csv"), ("final_bench_T.json", "r01_bench_T_1gpu_final.json"),
-                 ("final_bench_T_reference.json", "r01_bench_T_reference_arm.json"), ("final_secondary.log", "r01_secondary_throughput.log")] + \
+                 ("final_bench_T_reference.json", "r01_bench_T_reference_arm.json"), ("final_secondary.log", "r01_secondary_throughput.log"),
+                 ("final_nscan.log", "r01_heev_size_scan.log")] + \
                 [(f"final_bench_{w}.json", f"r01_bench_{w}_1gpu.json") for w in ("C1", "C2", "C3", "C4", "C5")]:
     if os.path.exists(os.path.join(O, src)):
         shutil.copy(os.path.join(O, src), os.path.join(P, dst))
@@ -21,7 +22,8 @@ def dram(rep):
     return g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
 tj = {}
 for key, rep, n, nk, note in (("pair_wide32", "final_full_pair_wide32.raw.csv", 32, 262144, "algorithmic: 512 B (d,e) + 4096 B trailing block per k = 1.208e9 B"),
-                              ("tridiag_cta64", "final_full_cta64.raw.csv", 64, 32768, "algorithmic: 64 KB H(k) in (lower triangle 32 KB) + 1 KB (d,e) out per k")):
+                              ("tridiag_cta64", "final_full_cta64.raw.csv", 64, 32768, "algorithmic: 64 KB H(k) in (lower triangle 32 KB) + 1 KB (d,e) out per k"),
+                              ("heev_generic", "final_full_generic512.raw.csv", 512, 296, "panel formulation, NB = 8: 16 B read per element and step + 32/8 B read+write = 0.90 GB per matrix")):
     f = os.path.join(O, rep)
     if os.path.exists(f):
         r, w = dram(f)
