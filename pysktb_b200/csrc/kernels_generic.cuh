@@ -133,7 +133,7 @@ struct HeevArgs {
     int* fail;          // incremented when QL exceeds its iteration limit
     int NP, SMEM_RED;   // column count padded to a warp multiple; blockDim.x = NP * R (R threads per column)
     int NB;             // > 0: panel formulation with NB (2, 4 or 8) deferred reflector pairs
-    void* peel_ws;      // host only: scratch of >= nm * peel_bytes_per_k(N) bytes enables the peeled run (64 < N <= 160, eigenvalues)
+    void* peel_ws;      // host only: scratch of >= nm * peel_bytes_per_k(N) bytes enables the peeled run (64 < N <= 320, eigenvalues)
     int peel; double* peel_de;   // phase 3: run only the first `peel` steps (a multiple of NB) of the panel formulation, leave the
                         // updated trailing (N - peel)^2 block in H and write d, e of the peeled steps to peel_de[mat][2][peel]
     int phase;          // 0: whole solve; 1: tridiagonalise and park (d, e) in H; 2: QL + output from the parked (d, e)

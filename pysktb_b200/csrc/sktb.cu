@@ -362,7 +362,7 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
     if (!smemA && R == 1 && N <= 1024 && nb_env > 0 && phase != 2 && (N >= 96 || phase == 3 || getenv("SKTB_GENERIC_NB"))) {
         int NB = nb_env >= 8 ? 8 : (nb_env >= 4 ? 4 : 2);
         if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;
-        if (phase == 3) NB = 4;                                  // the peel count is a multiple of 4     // measured: 4 wins below N ~ 160, none below N ~ 96
+        if (phase == 3) NB = (N >= 160 && a.peel % 8 == 0) ? 8 : 4;   // the peel count is a multiple of NB     // measured: 4 wins below N ~ 160, none below N ~ 96
         auto panel_bytes = [&](int nb) { return (size_t)2 * nb * N * sizeof(cplx) + (32 * 32 + 32) * sizeof(double); };
         while (NB > 2 && aux + panel_bytes(NB) > 200 * 1024) NB /= 2;
         if (aux + panel_bytes(NB) <= 200 * 1024) { a.NB = NB; aux += panel_bytes(NB); }
@@ -389,14 +389,15 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
 
 // Tracked rows with N > 64: tridiagonalisation (one 1-CTA-per-SM class kernel) and the serial-generator QL (small CTAs,
 // many matrices per SM) are two launches; everything else is one.
-// Peeled run (64 < N <= 160, eigenvalues only): the generic kernel does the first P steps (P = the multiple of 4 that
-// leaves a trailing block of 61..64), the register-resident kernels tridiagonalise that block in place, one
+// Peeled run (64 < N <= PEEL_MAX, eigenvalues only): the generic kernel does the first P steps (P = the multiple of the
+// panel width 4 or 8 that leaves a trailing block of 57..64), the register-resident kernels tridiagonalise that block in place, one
 // bisection kernel takes the merged (d, e).
-static const int PEEL_MAX = getenv("SKTB_PEEL_MAX") ? atoi(getenv("SKTB_PEEL_MAX")) : 160;
+static const int PEEL_MAX = getenv("SKTB_PEEL_MAX") ? atoi(getenv("SKTB_PEEL_MAX")) : 320;
 static size_t peel_bytes_per_k(int N) { return (size_t)2 * (N - 60) * 8 + small::cta64_bytes_per_k(); }
 static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     const int N = a.N;
-    const int P = (N - 64 + 3) / 4 * 4, Nt = N - P;
+    const int nb = N >= 160 ? 8 : 4;
+    const int P = (N - 64 + nb - 1) / nb * nb, Nt = N - P;
     double* head = (double*)a.peel_ws;
     double* c64s = head + (size_t)a.nm * 2 * P;
     a.peel = P; a.peel_de = head;

@@ -280,7 +280,7 @@ def test_mid_size_ribbons_peeled_run(tb, n_chains):
     np.testing.assert_allclose(dos, O.lorentz_dos(ev, E, 0.06), rtol=1e-9)
 
 
-@pytest.mark.parametrize("N", [1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 47, 64, 65, 68, 96, 110, 111, 128, 159, 160, 161])
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 47, 64, 65, 68, 96, 110, 111, 128, 159, 160, 161, 200, 320, 321])
 def test_heev_random_hermitian_vs_lapack(tb, N):
     """K2 alone (sktb_heev) on random complex matrices, lower-triangle semantics, both storage regimes."""
     import torch
