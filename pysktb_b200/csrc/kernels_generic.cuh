@@ -131,7 +131,6 @@ struct HeevArgs {
     int n_rows; const int* rows;                    // tracked row indices (NULL -> identity)
     cplx* vec_out; long long vs_band, vs_k, vcol0;  // vec_out[band*vs_band + (vcol0+mat)*vs_k + r]
     int* fail;          // incremented when QL exceeds its iteration limit
-    int NP, SMEM_RED;   // column count padded to a warp multiple; blockDim.x = NP * R (R threads per column)
     int NB;             // > 0: panel formulation with NB (2, 4 or 8) deferred reflector pairs
     void* peel_ws;      // host only: scratch of >= nm * peel_bytes_per_k(N) bytes enables the peeled run (64 < N <= 320, eigenvalues)
     int peel; double* peel_de;   // phase 3: run only the first `peel` steps (a multiple of NB) of the panel formulation, leave the
@@ -182,7 +181,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
     cplx* v = reinterpret_cast<cplx*>(scratch + 64);
     cplx* w = v + N;
     cplx* v2 = w + N;
-    cplx* sA = v2 + N + (a.SMEM_RED ? blockDim.x : 0);   // N*N when SMEM_A (after the R x NP partial sums; never with NB > 0)
+    cplx* sA = v2 + N;                            // N*N when SMEM_A (never together with NB > 0)
     __shared__ int s_lo, s_hi;
     const int n_rows = a.n_rows;
 
@@ -217,7 +216,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             //      rows (y0 = M0 v) plus O(NB) corrections per thread; the rank-2NB update is applied once per
             //      panel.  Per element and step that is 16 B read + 32/NB B read+write instead of 32 B read+write.
             const int NB = a.NB;
-            cplx* Vs = v2 + N + (a.SMEM_RED ? blockDim.x : 0);            // [NB][N]
+            cplx* Vs = v2 + N;                                             // [NB][N]
             cplx* Ws = Vs + (size_t)NB * N;                                // [NB][N]
             double* mred = reinterpret_cast<double*>(Ws + (size_t)NB * N); // [32 warps][32] + ab[32]
             double* ab = mred + 32 * 32;
@@ -339,52 +338,46 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             __syncthreads();
         } else
         if (N <= T && N >= 2) {
-            // ---- look-ahead formulation, R threads per column (one read+write pass over the trailing matrix per
-            //      step instead of a mat-vec pass plus an update pass).  Threads (q, i), q = tid / NP, own column i
-            //      of the mirrored matrix and the rows k = j+2+q (mod R) of it; y_i = sum_k conj(C[k][i]) v_k is a
-            //      per-column sum of R partials through shared memory: the mat-vec of reflector j+1 is accumulated
-            //      while reflector j's rank-2 update streams by.  A warp reads 32 consecutive columns of one row.
-            const int NP = a.NP, R = T / NP;
-            const int q = tid / NP, i = tid - q * NP;
-            const bool mine = i < N, lead = q == 0;
-            cplx* red = a.SMEM_RED ? v2 + N : nullptr;                     // [R][NP] when R > 1
+            // ---- one column per thread: look-ahead formulation (one read+write pass over the trailing matrix per
+            //      step instead of a mat-vec pass plus an update pass).  Thread i owns column i of the mirrored
+            //      matrix, so y_i = sum_k A[i][k] v_k = sum_k conj(C[k][i]) v_k needs no cross-thread reduction:
+            //      the mat-vec of reflector j+1 is accumulated while reflector j's rank-2 update streams by.
+            const int i = tid;
+            const bool mine = i < N;
             cplx vi = cmake(0.0, 0.0), wi = cmake(0.0, 0.0), tau = cmake(0.0, 0.0);
             // prologue: reflector 0 from column 0, plain mat-vec
             {
-                cplx x = (lead && mine && i >= 1) ? cconj(A[i]) : cmake(0.0, 0.0);
+                cplx x = (mine && i >= 1) ? cconj(A[i]) : cmake(0.0, 0.0);
                 double xn = block_sum((i > 1) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
-                if (lead && i == 1) { scratch[40] = x.x; scratch[41] = x.y; }
-                if (tid == 0) d[0] = A[0].x;
+                if (i == 1) { scratch[40] = x.x; scratch[41] = x.y; }
+                if (i == 0) d[0] = A[0].x;
                 __syncthreads();
                 cplx alpha = cmake(scratch[40], scratch[41]);
                 double beta; cplx scale;
                 householder(alpha, xn, beta, tau, scale);
-                if (tid == 0) e[0] = beta;
+                if (i == 0) e[0] = beta;
                 vi = (i == 1) ? cmake(1.0, 0.0) : ((mine && i > 1) ? cmul(x, scale) : cmake(0.0, 0.0));
-                if (lead && mine) v[i] = vi;
+                if (mine) v[i] = vi;
                 __syncthreads();
-                cplx acc = cmake(0.0, 0.0);
-                if (mine && i >= 1)
-                    for (int k = 1 + q; k < N; k += R) cfmac(acc, A[(size_t)k * N + i], v[k]);
-                if (R > 1) {
-                    red[tid] = acc;
-                    __syncthreads();
-                    if (lead) for (int qq = 1; qq < R; ++qq) acc = cadd(acc, red[qq * NP + i]);
+                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                if (mine && i >= 1) {
+                    int k = 1;
+                    for (; k + 1 < N; k += 2) { cfmac(acc, A[(size_t)k * N + i], v[k]); cfmac(acc2, A[(size_t)(k + 1) * N + i], v[k + 1]); }
+                    if (k < N) cfmac(acc, A[(size_t)k * N + i], v[k]);
                 }
-                cplx p = (lead && mine && i >= 1) ? cmul(tau, acc) : cmake(0.0, 0.0);
+                cplx p = (mine && i >= 1) ? cmul(tau, cadd(acc, acc2)) : cmake(0.0, 0.0);
                 cplx dl = cmake(0.0, 0.0);
                 cfmac(dl, p, vi);
                 cplx dot = block_sum(dl, scratch);
                 cplx a2 = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dot);
                 wi = p; cfma(wi, a2, vi);
-                if (lead && mine) w[i] = wi;
+                if (mine) w[i] = wi;
                 __syncthreads();
-                if (!lead && mine) { vi = v[i]; wi = w[i]; }
             }
             for (int j = 0; j + 1 < N; ++j) {
                 // (1) row j+1 of the update -> the next pivot column (entries x'_i = conj(C[j+1][i]), i > j+1)
                 cplx x = cmake(0.0, 0.0);
-                if (lead && mine && i >= j + 1) {
+                if (mine && i >= j + 1) {
                     cplx c = A[(size_t)(j + 1) * N + i];
                     cfmsc(c, vi, w[j + 1]);
                     cfmsc(c, wi, v[j + 1]);
@@ -395,68 +388,57 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                 // row tracking with reflector j (tracked rows of Q): R <- R H_j
                 for (int r = tid; r < n_rows; r += T) {
                     cplx sdot = cmake(0.0, 0.0);
-                    for (int qq = j + 1; qq < N; ++qq) cfma(sdot, RT[(size_t)qq * n_rows + r], v[qq]);
+                    for (int q = j + 1; q < N; ++q) cfma(sdot, RT[(size_t)q * n_rows + r], v[q]);
                     cplx ts = cmul(tau, sdot);
-                    for (int qq = j + 1; qq < N; ++qq) {
-                        cplx xx = RT[(size_t)qq * n_rows + r];
-                        cplx vc = cconj(v[qq]);
+                    for (int q = j + 1; q < N; ++q) {
+                        cplx xx = RT[(size_t)q * n_rows + r];
+                        cplx vc = cconj(v[q]);
                         cfms(xx, ts, vc);
-                        RT[(size_t)qq * n_rows + r] = xx;
+                        RT[(size_t)q * n_rows + r] = xx;
                     }
                 }
                 if (j + 2 >= N) break;                                    // column N-1 is the last diagonal entry
-                double xn = block_sum((lead && mine && i > j + 2) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
-                if (lead && i == j + 2) { scratch[40] = x.x; scratch[41] = x.y; }
+                double xn = block_sum((mine && i > j + 2) ? fma(x.x, x.x, x.y * x.y) : 0.0, scratch);
+                if (i == j + 2) { scratch[40] = x.x; scratch[41] = x.y; }
                 __syncthreads();
                 cplx alpha = cmake(scratch[40], scratch[41]);
                 double beta; cplx tau2, scale;
                 householder(alpha, xn, beta, tau2, scale);
-                if (tid == 0) e[j + 1] = beta;
+                if (i == 0) e[j + 1] = beta;
                 cplx v2i = (i == j + 2) ? cmake(1.0, 0.0) : ((mine && i > j + 2) ? cmul(x, scale) : cmake(0.0, 0.0));
-                if (lead && mine) v2[i] = v2i;
+                if (mine) v2[i] = v2i;
                 __syncthreads();
                 // (2) rows k >= j+2: update and accumulate the next mat-vec in the same pass
                 cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
                 if (mine && i >= j + 2) {
-                    int k = j + 2 + q;
-                    const size_t RN = (size_t)R * N;
-                    for (; k + 3 * R < N; k += 4 * R) {                    // four independent 16 B loads in flight per thread
+                    int k = j + 2;
+                    for (; k + 3 < N; k += 4) {                            // four independent 16 B loads in flight per thread
                         cplx* Ak = A + (size_t)k * N + i;
-                        cplx c0 = Ak[0], c1 = Ak[RN], c2 = Ak[2 * RN], c3 = Ak[3 * RN];
+                        cplx c0 = Ak[0], c1 = Ak[N], c2 = Ak[2 * (size_t)N], c3 = Ak[3 * (size_t)N];
                         cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
-                        cfmsc(c1, vi, w[k + R]); cfmsc(c1, wi, v[k + R]);
-                        cfmsc(c2, vi, w[k + 2 * R]); cfmsc(c2, wi, v[k + 2 * R]);
-                        cfmsc(c3, vi, w[k + 3 * R]); cfmsc(c3, wi, v[k + 3 * R]);
-                        Ak[0] = c0; Ak[RN] = c1; Ak[2 * RN] = c2; Ak[3 * RN] = c3;
-                        cfmac(acc, c0, v2[k]); cfmac(acc2, c1, v2[k + R]);
-                        cfmac(acc, c2, v2[k + 2 * R]); cfmac(acc2, c3, v2[k + 3 * R]);
+                        cfmsc(c1, vi, w[k + 1]); cfmsc(c1, wi, v[k + 1]);
+                        cfmsc(c2, vi, w[k + 2]); cfmsc(c2, wi, v[k + 2]);
+                        cfmsc(c3, vi, w[k + 3]); cfmsc(c3, wi, v[k + 3]);
+                        Ak[0] = c0; Ak[N] = c1; Ak[2 * (size_t)N] = c2; Ak[3 * (size_t)N] = c3;
+                        cfmac(acc, c0, v2[k]); cfmac(acc2, c1, v2[k + 1]);
+                        cfmac(acc, c2, v2[k + 2]); cfmac(acc2, c3, v2[k + 3]);
                     }
-                    for (; k < N; k += R) {
+                    for (; k < N; ++k) {
                         cplx c0 = A[(size_t)k * N + i];
                         cfmsc(c0, vi, w[k]); cfmsc(c0, wi, v[k]);
                         A[(size_t)k * N + i] = c0;
                         cfmac(acc, c0, v2[k]);
                     }
                 }
-                acc = cadd(acc, acc2);
-                if (R > 1) {
-                    red[tid] = acc;
-                    __syncthreads();
-                    if (lead) for (int qq = 1; qq < R; ++qq) acc = cadd(acc, red[qq * NP + i]);
-                }
-                cplx p = (lead && mine && i >= j + 2) ? cmul(tau2, acc) : cmake(0.0, 0.0);
+                cplx p = (mine && i >= j + 2) ? cmul(tau2, cadd(acc, acc2)) : cmake(0.0, 0.0);
                 cplx dl = cmake(0.0, 0.0);
                 cfmac(dl, p, v2i);
                 cplx dot = block_sum(dl, scratch);                        // (syncs: every thread is done reading v, w)
                 cplx a2 = cmul(cmake(-0.5 * tau2.x, -0.5 * tau2.y), dot);
-                tau = tau2;
-                if (lead) {
-                    vi = v2i;
-                    wi = p; cfma(wi, a2, vi);
-                    if (mine) { v[i] = vi; w[i] = wi; }
-                }
+                vi = v2i; tau = tau2;
+                wi = p; cfma(wi, a2, vi);
+                if (mine) { v[i] = vi; w[i] = wi; }
                 __syncthreads();
-                if (!lead && mine) { vi = v[i]; wi = w[i]; }
             }
             __syncthreads();
         } else

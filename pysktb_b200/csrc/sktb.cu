@@ -341,28 +341,20 @@ static int launch_hk(sktb_plan* p, const double* k_d, long long nk, int soc, cpl
 static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, int phase) {
     const int N = a.N;
     static const long long smemA_max = getenv("SKTB_GENERIC_SMEMA_KB") ? atoll(getenv("SKTB_GENERIC_SMEMA_KB")) * 1024 : 72 * 1024;
-    static const long long l2_mb = getenv("SKTB_GENERIC_L2_MB") ? atoll(getenv("SKTB_GENERIC_L2_MB")) : 0;
-    static const int r_env = getenv("SKTB_GENERIC_R") ? atoi(getenv("SKTB_GENERIC_R")) : 0;
     const int NP = std::max(32, (N + 31) / 32 * 32);
-    int R = 1;
-    if (NP <= 1024) {
-        R = r_env > 0 ? r_env : 1;
-        R = std::max(1, std::min(R, 1024 / NP));
-    }
-    int T = std::min(1024, NP * R);
+    int T = std::min(1024, NP);
     a.phase = phase;
-    if (phase == 2) { R = 1; T = std::min(512, std::max(64, (a.n_rows + 31) / 32 * 32)); }
-    a.NP = NP; a.SMEM_RED = R > 1;
-    size_t aux = ((size_t)4 * N + 64) * sizeof(double) + (size_t)3 * N * sizeof(cplx) + (R > 1 ? (size_t)T * sizeof(cplx) : 0);
+    if (phase == 2) T = std::min(512, std::max(64, (a.n_rows + 31) / 32 * 32));
+    size_t aux = ((size_t)4 * N + 64) * sizeof(double) + (size_t)3 * N * sizeof(cplx);
     size_t withA = aux + (size_t)N * N * sizeof(cplx);
     bool smemA = (long long)withA <= smemA_max && T <= 384 && phase == 0;   // beyond N = 64 many CTAs per SM over L2 beat one CTA per SM in shared memory
     // panel formulation for the sizes that stream the matrix through HBM/L2 (one column per thread, N <= 1024)
     static const int nb_env = getenv("SKTB_GENERIC_NB") ? atoi(getenv("SKTB_GENERIC_NB")) : 8;
     a.NB = 0;
-    if (!smemA && R == 1 && N <= 1024 && nb_env > 0 && phase != 2 && (N >= 96 || phase == 3 || getenv("SKTB_GENERIC_NB"))) {
+    if (!smemA && N <= 1024 && phase != 2 && (phase == 3 || (nb_env > 0 && (N >= 96 || getenv("SKTB_GENERIC_NB"))))) {
         int NB = nb_env >= 8 ? 8 : (nb_env >= 4 ? 4 : 2);
-        if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;
-        if (phase == 3) NB = (N >= 160 && a.peel % 8 == 0) ? 8 : 4;   // the peel count is a multiple of NB     // measured: 4 wins below N ~ 160, none below N ~ 96
+        if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;            // measured: 4 wins below N ~ 160, none below N ~ 96
+        if (phase == 3) NB = (N >= 160 && a.peel % 8 == 0) ? 8 : 4;       // the peel count is a multiple of NB
         auto panel_bytes = [&](int nb) { return (size_t)2 * nb * N * sizeof(cplx) + (32 * 32 + 32) * sizeof(double); };
         while (NB > 2 && aux + panel_bytes(NB) > 200 * 1024) NB /= 2;
         if (aux + panel_bytes(NB) <= 200 * 1024) { a.NB = NB; aux += panel_bytes(NB); }
@@ -370,11 +362,6 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
     size_t smem = smemA ? withA : aux;
     a.fail = p->d_fail;
     unsigned grid = (unsigned)std::min<long long>(a.nm, 148LL * 32);
-    if (!smemA && l2_mb > 0) {
-        long long fit = (l2_mb << 20) / ((long long)N * N * (long long)sizeof(cplx));
-        fit = std::max(148LL, fit / 148 * 148);
-        grid = (unsigned)std::min<long long>(grid, fit);
-    }
     // Three builds: A in shared memory (N <= 64, the fallback of the register-resident paths), A in global memory
     // with a free register budget (T <= 384), and the 64-register build that keeps two 512-thread CTAs per SM.
     auto kern = smemA ? heev_generic_kernel<true, 384> : (T <= 384 ? heev_generic_kernel<false, 384> : (a.NB > 0 && T <= 512 ? heev_generic_kernel<false, 512> : heev_generic_kernel<false, 1024>));
@@ -382,7 +369,7 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
     kern<<<grid, T, smem, st>>>(a);
     LAUNCHED();
     char buf[256];
-    snprintf(buf, sizeof buf, "heev_generic<smemA=%d> N=%d R=%d NB=%d threads=%d smem=%zuB grid=%u rows=%d", (int)smemA, N, R, a.NB, T, smem, grid, a.n_rows);
+    snprintf(buf, sizeof buf, "heev_generic<smemA=%d> N=%d NB=%d threads=%d smem=%zuB grid=%u rows=%d", (int)smemA, N, a.NB, T, smem, grid, a.n_rows);
     if (phase == 2) g_kinfo += std::string(" + QL kernel x") + std::to_string(T) + " thr"; else g_kinfo = buf;
     return 0;
 }
