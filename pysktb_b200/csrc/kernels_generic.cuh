@@ -131,6 +131,7 @@ struct HeevArgs {
     int n_rows; const int* rows;                    // tracked row indices (NULL -> identity)
     cplx* vec_out; long long vs_band, vs_k, vcol0;  // vec_out[band*vs_band + (vcol0+mat)*vs_k + r]
     int* fail;          // incremented when QL exceeds its iteration limit
+    int remap_min_threads;   // panel formulation: CTAs of at least this many threads re-map idle threads onto the trailing columns
     int NB;             // > 0: panel formulation with NB (2, 4 or 8) deferred reflector pairs
     void* peel_ws;      // host only: scratch of >= nm * peel_bytes_per_k(N) bytes enables the peeled run (64 < N <= 320, eigenvalues)
     int peel; double* peel_de;   // phase 3: run only the first `peel` steps (a multiple of NB) of the panel formulation, leave the
@@ -138,22 +139,24 @@ struct HeevArgs {
     int phase;          // 0: whole solve; 1: tridiagonalise and park (d, e) in H; 2: QL + output from the parked (d, e)
 };
 
-// trailing update of one panel: M0[k][i] -= sum_s conj(V[i][s]) W[k][s] + conj(W[i][s]) V[k][s], rows k >= jn, column i
-template <int NBT>
-SKTB_D void heev_panel_update_t(cplx* A, const cplx* Vs, const cplx* Ws, int N, int i, int jn) {
+// trailing update of one panel: M0[k][i] -= sum_s conj(V[i][s]) W[k][s] + conj(W[i][s]) V[k][s], column i, rows
+// k = k0, k0 + R, ... (R threads share a column once the trailing block is narrower than the CTA)
+template <int NBT, bool STRIDED>
+SKTB_D void heev_panel_update_t(cplx* A, const cplx* Vs, const cplx* Ws, int N, int i, int k0, int Rr) {
+    const int R = STRIDED ? Rr : 1;                      // R = 1 is the common case: keep its addressing free of the stride
     cplx vr[NBT], wr[NBT];
 #pragma unroll
     for (int s = 0; s < NBT; ++s) { vr[s] = Vs[s * N + i]; wr[s] = Ws[s * N + i]; }
-    int k = jn;
-    for (; k + 1 < N; k += 2) {
+    int k = k0;
+    for (; k + R < N; k += 2 * R) {
         cplx* Ak = A + (size_t)k * N + i;
-        cplx c0 = Ak[0], c1 = Ak[N];
+        cplx c0 = Ak[0], c1 = Ak[(size_t)R * N];
 #pragma unroll
         for (int s = 0; s < NBT; ++s) {
             cfmsc(c0, vr[s], Ws[s * N + k]); cfmsc(c0, wr[s], Vs[s * N + k]);
-            cfmsc(c1, vr[s], Ws[s * N + k + 1]); cfmsc(c1, wr[s], Vs[s * N + k + 1]);
+            cfmsc(c1, vr[s], Ws[s * N + k + R]); cfmsc(c1, wr[s], Vs[s * N + k + R]);
         }
-        Ak[0] = c0; Ak[N] = c1;
+        Ak[0] = c0; Ak[(size_t)R * N] = c1;
     }
     if (k < N) {
         cplx* Ak = A + (size_t)k * N + i;
@@ -163,10 +166,42 @@ SKTB_D void heev_panel_update_t(cplx* A, const cplx* Vs, const cplx* Ws, int N, 
         Ak[0] = c0;
     }
 }
-SKTB_D void heev_panel_update(cplx* A, const cplx* Vs, const cplx* Ws, int N, int i, int jn, int NB) {
-    if (NB == 8) heev_panel_update_t<8>(A, Vs, Ws, N, i, jn);
-    else if (NB == 4) heev_panel_update_t<4>(A, Vs, Ws, N, i, jn);
-    else heev_panel_update_t<2>(A, Vs, Ws, N, i, jn);
+SKTB_D void heev_panel_update(cplx* A, const cplx* Vs, const cplx* Ws, int N, int i, int k0, int R, int NB) {
+    if (R == 1) {
+        if (NB == 8) heev_panel_update_t<8, false>(A, Vs, Ws, N, i, k0, 1);
+        else if (NB == 4) heev_panel_update_t<4, false>(A, Vs, Ws, N, i, k0, 1);
+        else heev_panel_update_t<2, false>(A, Vs, Ws, N, i, k0, 1);
+    } else {
+        if (NB == 8) heev_panel_update_t<8, true>(A, Vs, Ws, N, i, k0, R);
+        else if (NB == 4) heev_panel_update_t<4, true>(A, Vs, Ws, N, i, k0, R);
+        else heev_panel_update_t<2, true>(A, Vs, Ws, N, i, k0, R);
+    }
+}
+
+// y0 partial of one thread: sum over rows k = k0, k0 + R, ... of conj(M0[k][i]) v_k (read-only stream)
+template <bool STRIDED>
+SKTB_D cplx heev_panel_matvec(const cplx* A, const cplx* v, int N, int i, int k0, int Rr) {
+    const int R = STRIDED ? Rr : 1;
+    cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0), acc3 = cmake(0.0, 0.0), acc4 = cmake(0.0, 0.0);
+    int k = k0;
+    const size_t RN = (size_t)R * N;
+    const cplx* Ak = A + (size_t)k * N + i;
+    for (; k + 15 * R < N; k += 16 * R, Ak += 16 * RN) {                 // sixteen 16 B loads in flight per thread
+        cplx cc[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cc[u] = Ak[u * RN];
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+            cfmac(acc, cc[u], v[k + u * R]); cfmac(acc2, cc[u + 1], v[k + (u + 1) * R]);
+            cfmac(acc3, cc[u + 2], v[k + (u + 2) * R]); cfmac(acc4, cc[u + 3], v[k + (u + 3) * R]);
+        }
+    }
+    for (; k + 3 * R < N; k += 4 * R, Ak += 4 * RN) {
+        cplx c0 = Ak[0], c1 = Ak[RN], c2 = Ak[2 * RN], c3 = Ak[3 * RN];
+        cfmac(acc, c0, v[k]); cfmac(acc2, c1, v[k + R]); cfmac(acc3, c2, v[k + 2 * R]); cfmac(acc4, c3, v[k + 3 * R]);
+    }
+    for (; k < N; k += R, Ak += RN) cfmac(acc, Ak[0], v[k]);
+    return cadd(cadd(acc, acc2), cadd(acc3, acc4));
 }
 
 template <bool SMEM_A, int MAXT>
@@ -220,6 +255,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             cplx* Ws = Vs + (size_t)NB * N;                                // [NB][N]
             double* mred = reinterpret_cast<double*>(Ws + (size_t)NB * N); // [32 warps][32] + ab[32]
             double* ab = mred + 32 * 32;
+            cplx* red = reinterpret_cast<cplx*>(ab + 32);                  // [T] partial mat-vec sums (R threads per column)
             const int i = tid, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
             const bool mine = i < N;
             cplx tau = cmake(0.0, 0.0);
@@ -227,6 +263,13 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             const int jstop = a.peel > 0 ? a.peel : N;
             for (int j0 = 0; j0 + 1 < N && j0 < jstop; j0 += NB) {
                 const int tmax = min(NB, N - 1 - j0);
+                // The two streaming loops are re-mapped once the trailing block is narrower than the CTA: R threads
+                // (q = 0..R-1) share column i2 = cbase + c and take the rows k = first + q (mod R), so that every thread
+                // keeps loads in flight; ownership of everything else stays "thread i = column i".
+                int cbase = (j0 + 1) & ~31, R = 1;
+                while (T >= a.remap_min_threads && R < 16 && 2 * R * ((N - cbase + 31) & ~31) <= T) R *= 2;
+                if (R == 1) cbase = 0;                                        // identity mapping: i2 = tid
+                const int CP = T / R, q = tid / CP, i2 = cbase + (tid - q * CP);
                 for (int t = 0; t < tmax; ++t) {
                     const int j = j0 + t;
                     // (1) row j of M_t (columns i >= j): the pivot column x_i = conj(M_t[j][i])
@@ -251,27 +294,16 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                     if (mine) { v[i] = vi; Vs[t * N + i] = vi; }
                     __syncthreads();
                     // (2) y0_i = sum_{k > j} conj(M0[k][i]) v_k: read-only stream
-                    cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0), acc3 = cmake(0.0, 0.0), acc4 = cmake(0.0, 0.0);
-                    if (mine && i >= j + 1) {
-                        int k = j + 1;
-                        const cplx* Ak = A + (size_t)k * N + i;
-                        for (; k + 15 < N; k += 16, Ak += 16 * (size_t)N) {      // sixteen 16 B loads in flight per thread
-                            cplx cc[16];
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) cc[u] = Ak[u * (size_t)N];
-#pragma unroll
-                            for (int u = 0; u < 16; u += 4) {
-                                cfmac(acc, cc[u], v[k + u]); cfmac(acc2, cc[u + 1], v[k + u + 1]);
-                                cfmac(acc3, cc[u + 2], v[k + u + 2]); cfmac(acc4, cc[u + 3], v[k + u + 3]);
-                            }
-                        }
-                        for (; k + 3 < N; k += 4, Ak += 4 * (size_t)N) {
-                            cplx c0 = Ak[0], c1 = Ak[N], c2 = Ak[2 * (size_t)N], c3 = Ak[3 * (size_t)N];
-                            cfmac(acc, c0, v[k]); cfmac(acc2, c1, v[k + 1]); cfmac(acc3, c2, v[k + 2]); cfmac(acc4, c3, v[k + 3]);
-                        }
-                        for (; k < N; ++k, Ak += N) cfmac(acc, Ak[0], v[k]);
+                    cplx acc = cmake(0.0, 0.0);
+                    if (i2 < N && i2 >= j + 1)
+                        acc = R == 1 ? heev_panel_matvec<false>(A, v, N, i2, j + 1, 1) : heev_panel_matvec<true>(A, v, N, i2, j + 1 + q, R);
+                    if (R > 1) {                                              // column sums of the R partials, back to the column owners
+                        red[tid] = acc;
+                        __syncthreads();
+                        acc = cmake(0.0, 0.0);
+                        if (mine && i >= cbase)
+                            for (int qq = 0; qq < R; ++qq) acc = cadd(acc, red[qq * CP + (i - cbase)]);
                     }
-                    acc = cadd(cadd(acc, acc2), cadd(acc3, acc4));
                     // corrections: a_s = w_s^H v, b_s = v_s^H v for s < t (2t block-wide complex sums at once)
                     if (t > 0) {
                         for (int s2 = 0; s2 < t; ++s2) {
@@ -319,7 +351,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                 const int jn = j0 + tmax;
                 if (tmax == NB && jn + 1 < N) {
                     // panel update of the trailing block (rows, columns >= jn); own-row reflector entries in registers
-                    if (mine && i >= jn) heev_panel_update(A, Vs, Ws, N, i, jn, NB);
+                    if (i2 < N && i2 >= jn) heev_panel_update(A, Vs, Ws, N, i2, jn + q, R, NB);
                     tlast = 0;
                     __syncthreads();
                 }

@@ -350,12 +350,14 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
     bool smemA = (long long)withA <= smemA_max && T <= 384 && phase == 0;   // beyond N = 64 many CTAs per SM over L2 beat one CTA per SM in shared memory
     // panel formulation for the sizes that stream the matrix through HBM/L2 (one column per thread, N <= 1024)
     static const int nb_env = getenv("SKTB_GENERIC_NB") ? atoi(getenv("SKTB_GENERIC_NB")) : 8;
+    static const int remap_min = getenv("SKTB_GENERIC_REMAP_MIN") ? atoi(getenv("SKTB_GENERIC_REMAP_MIN")) : 256;   // same-box A/B: +1..2 % from 256 threads up, nothing below
+    a.remap_min_threads = remap_min;
     a.NB = 0;
     if (!smemA && N <= 1024 && phase != 2 && (phase == 3 || (nb_env > 0 && (N >= 96 || getenv("SKTB_GENERIC_NB"))))) {
         int NB = nb_env >= 8 ? 8 : (nb_env >= 4 ? 4 : 2);
         if (!getenv("SKTB_GENERIC_NB")) NB = N >= 160 ? 8 : 4;            // measured: 4 wins below N ~ 160, none below N ~ 96
         if (phase == 3) NB = (N >= 160 && a.peel % 8 == 0) ? 8 : 4;       // the peel count is a multiple of NB
-        auto panel_bytes = [&](int nb) { return (size_t)2 * nb * N * sizeof(cplx) + (32 * 32 + 32) * sizeof(double); };
+        auto panel_bytes = [&](int nb) { return (size_t)2 * nb * N * sizeof(cplx) + (32 * 32 + 32) * sizeof(double) + (size_t)T * sizeof(cplx); };
         while (NB > 2 && aux + panel_bytes(NB) > 200 * 1024) NB /= 2;
         if (aux + panel_bytes(NB) <= 200 * 1024) { a.NB = NB; aux += panel_bytes(NB); }
     }

@@ -44,6 +44,8 @@ CASES = {
     "SKTB_GENERIC_NB=0": [(100, 40, False), (200, 20, False), (130, 10, True)],
     "SKTB_GENERIC_NB=2": [(100, 40, False), (330, 10, False)],
     "SKTB_PEEL_MAX=0": [(65, 60, False), (128, 40, False)],
+    "SKTB_GENERIC_REMAP_MIN=32": [(100, 20, False), (330, 10, False), (130, 10, True)],
+    "SKTB_GENERIC_REMAP_MIN=100000": [(512, 5, False)],
     "SKTB_PEEL_QL_MIN=1": [(65, 60, False), (100, 70, False), (200, 33, False)],
     "SKTB_GENERIC_SPLIT=0": [(80, 20, True), (130, 10, True)],
     "SKTB_VEC_LIST=0": [(32, 200, True), (64, 100, True)],
