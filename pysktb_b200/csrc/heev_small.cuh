@@ -717,7 +717,7 @@ static int launch_pair(const LaunchCtx& c) {
     const int n = c.a.t.n_orb, nb = c.a.t.n_bonds, N = c.a.N;
     // (3-warp wide CTAs that leave registers for a co-resident tail/QL CTA, and 3 CTAs x 3 warps, were measured:
     //  2.6e7 / 2.8e7 k/s against 3.4e7 for 2 x 4 warps at 255 registers - not kept)
-    static const int tail_s = getenv("SKTB_TAIL_S") ? atoi(getenv("SKTB_TAIL_S")) : 8;
+    static const int tail_s = getenv("SKTB_TAIL_S") ? atoi(getenv("SKTB_TAIL_S")) : 4;
     constexpr int WWr = PAIR_WARPS;
     const size_t smemW = table_doubles(n, nb, N, SOC, false) * 8 + (size_t)WWr * (pair_buf_cplx<32>() + nb) * 16;
     const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;

@@ -435,7 +435,7 @@ static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked
 // The pair-layout pipeline (24 < N <= 32) keeps two chunks in flight and parks a 4 KB trailing block per k-point.
 static size_t small_scratch_bytes(int N, long long nk) {
     if (small::padded_nc(N) == 32) {
-        static const int chunk_log2 = getenv("SKTB_PAIR_CHUNK_LOG2") ? atoi(getenv("SKTB_PAIR_CHUNK_LOG2")) : 19;
+        static const int chunk_log2 = getenv("SKTB_PAIR_CHUNK_LOG2") ? atoi(getenv("SKTB_PAIR_CHUNK_LOG2")) : 20;
         long long chunk = std::min<long long>(std::max<long long>(nk, 32), 1LL << chunk_log2);
         chunk = (chunk + 31) / 32 * 32;
         return (size_t)chunk * 2 * small::PAIR_BYTES_PER_K;
