@@ -382,7 +382,7 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
 // panel width 4 or 8 that leaves a trailing block of 57..64), the register-resident kernels tridiagonalise that block in place, one
 // bisection kernel takes the merged (d, e).
 static const int PEEL_MAX = getenv("SKTB_PEEL_MAX") ? atoi(getenv("SKTB_PEEL_MAX")) : 320;
-static size_t peel_bytes_per_k(int N) { return (size_t)2 * (N - 60) * 8 + small::cta64_bytes_per_k(); }
+static size_t peel_bytes_per_k(int N) { return (size_t)2 * (N - 56) * 8 + small::cta64_bytes_per_k(); }   // P <= N - 57
 static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     const int N = a.N;
     const int nb = N >= 160 ? 8 : 4;
@@ -692,7 +692,8 @@ extern "C" int sktb_solve_host(sktb_plan* p, const double* k_h, int64_t nk, int3
     for (int s = 0; s < 2; ++s)
         if (!p->hs[s]) CK(cudaStreamCreateWithFlags(&p->hs[s], cudaStreamNonBlocking));
     // chunk: bounded device staging (<= 512 MB of eigenvalues, <= 1 GB of eigenvectors per stream)
-    long long chunk = std::min<long long>(nk, std::max<long long>(1, ((long long)512 << 20) / ((long long)N * 8)));
+    static const long long host_chunk_mb = getenv("SKTB_HOST_CHUNK_MB") ? atoll(getenv("SKTB_HOST_CHUNK_MB")) : 512;
+    long long chunk = std::min<long long>(nk, std::max<long long>(1, (host_chunk_mb << 20) / ((long long)N * 8)));
     if (evecs_h) chunk = std::min<long long>(chunk, std::max<long long>(1, ((long long)1 << 30) / ((long long)N * N * 16)));
     if (nk > 4 * 148 && chunk > (nk + 3) / 4) chunk = (nk + 3) / 4;      // at least 4 chunks so the copies overlap
     const bool gate = p->asym_bound > 0.5e-9;
