@@ -117,6 +117,7 @@ SKTB_D int tql_scan(const double* d, const double* e, int l, int n) {
     return m;
 }
 
+template <bool FAST = true>
 SKTB_D int tql_lane(double* d, double* e, int n) {
     const double eps = 2.220446049250313e-16;
 #define D_(i) d[(i) * DSTRIDE]
@@ -134,9 +135,20 @@ SKTB_D int tql_lane(double* d, double* e, int n) {
         }
         ++iter;
         double el = E_(l), dl = D_(l);
-        double g = (D_(l + 1) - dl) / (2.0 * el);
-        double r = sqrt(fma(g, g, 1.0));
-        g = D_(m) - dl + el / (g + (g >= 0.0 ? r : -r));
+        double g, r;
+        if (FAST) {
+            // Wilkinson shift with Newton-refined hardware reciprocals (no IEEE slow paths); a non-finite intermediate
+            // (|e_l| tiny against the diagonal gap) means the shift is d[m] - d[l] to working precision
+            g = (D_(l + 1) - dl) * fast_rcp(2.0 * el);
+            const double h = fma(g, g, 1.0);
+            r = h * fast_rsqrt(h);
+            const double q = el * fast_rcp(g + (g >= 0.0 ? r : -r));
+            g = D_(m) - dl + ((fabs(q) <= 1.7e308) ? q : 0.0);
+        } else {
+            g = (D_(l + 1) - dl) / (2.0 * el);
+            r = sqrt(fma(g, g, 1.0));
+            g = D_(m) - dl + el / (g + (g >= 0.0 ? r : -r));
+        }
         double s = 1.0, c = 1.0, p = 0.0;
         bool under = false;
         double di1 = D_(m);                           // original d[i+1]
@@ -146,8 +158,8 @@ SKTB_D int tql_lane(double* d, double* e, int n) {
             double ei = E_(i), di = D_(i);
             double f = s * ei, b = c * ei;
             double h2 = fma(f, f, g * g);
-            if (h2 == 0.0) { E_(i + 1) = 0.0; D_(i + 1) = di1 - p; E_(m) = 0.0; under = true; break; }
-            double ir = rsqrt(h2);
+            if (FAST ? h2 < 1e-290 : h2 == 0.0) { E_(i + 1) = 0.0; D_(i + 1) = di1 - p; E_(m) = 0.0; under = true; break; }
+            double ir = FAST ? fast_rsqrt(h2) : rsqrt(h2);
             r = h2 * ir;
             s = f * ir; c = g * ir;
             g = di1 - p;
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, 3) tridiag_fold32_kernel(Sma
 }
 
 // one tridiagonal matrix per lane: transpose (d,e) through shared memory, QL, bitonic sort, coalesced store
-template <int NC, int P2>
+template <int NC, int P2, bool FAST = true>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
             }
         }
         __syncwarp();
-        if (tql_lane(dbuf + lane, ebuf + lane, N)) atomicAdd(a.fail, 1);
+        if (tql_lane<FAST>(dbuf + lane, ebuf + lane, N)) atomicAdd(a.fail, 1);
         double ev[P2];
 #pragma unroll
         for (int q = 0; q < P2; ++q) ev[q] = (q < N && q < NC) ? dbuf[q * DSTRIDE + lane] : __longlong_as_double(0x7ff0000000000000LL);
@@ -727,7 +739,8 @@ static int launch_pair(const LaunchCtx& c) {
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, true> : pair_wide32_kernel<SRC, 4, true>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, false> : pair_wide32_kernel<SRC, 4, false>;
     void (*kT)(const cplx*, double*, long long, int, int, int) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
-    auto kB = tql_small_kernel<NC, 32>;
+    static const bool tql_fast = !(getenv("SKTB_TQL_FAST") && getenv("SKTB_TQL_FAST")[0] == '0');
+    void (*kB)(TqlArgs) = tql_fast ? tql_small_kernel<NC, 32, true> : tql_small_kernel<NC, 32, false>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
     }
