@@ -210,7 +210,11 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     const size_t smemQ = (size_t)VECQL_WARPS * VEC32_SMEM_DOUBLES * 8;
     double* zstore = reinterpret_cast<double*>(vstore + (size_t)nk * PAIR_VSTORE_CPLX);
     int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nk * 1024);
-    void (*kW)(SmallArgs, cplx*, cplx*) = soc ? pair_wide32_kernel<PAIR_SRC_SOC, 4, true, true> : pair_wide32_kernel<PAIR_SRC_NOSOC, 4, true, true>;
+    // split like the eigenvalue path: steps 0..15 in the one-warp kernel, the trailing 16 x 16 block (parked in the Z
+    // region, which is written later) in the two-matrices-per-warp kernel; both keep their reflectors
+    static const bool split = !(getenv("SKTB_VEC32_SPLIT") && getenv("SKTB_VEC32_SPLIT")[0] == '0');
+    void (*kW)(SmallArgs, cplx*, cplx*) = split ? (soc ? pair_wide32_kernel<PAIR_SRC_SOC, 4, false, true> : pair_wide32_kernel<PAIR_SRC_NOSOC, 4, false, true>)
+                                                : (soc ? pair_wide32_kernel<PAIR_SRC_SOC, 4, true, true> : pair_wide32_kernel<PAIR_SRC_NOSOC, 4, true, true>);
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
     }
@@ -223,7 +227,13 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occV, vecbt32_kernel<0>, VEC32_WARPS * 32, smemBT);
     if (occW < 1 || occQ < 1 || occV < 1) { *info = "vec32 kernels do not fit (smem " + std::to_string(smemW) + ")"; return -1; }
     const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nk + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * occW));
-    kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, nullptr, vstore);
+    cplx* blk16 = reinterpret_cast<cplx*>(zstore);
+    kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, split ? blk16 : nullptr, vstore);
+    if (split) {
+        const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
+        const unsigned gridT = (unsigned)std::max<long long>(1, std::min<long long>(((nk + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
+        pair_tail16_kernel<4, true><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, a.scratch, nk, 64, 0, 32, vstore);
+    }
     Vec32Args v{a.scratch, vstore, nk, N, evals, evecs, ld, col0, fail};
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>((nk + VECQL_WARPS - 1) / VECQL_WARPS, (long long)sms * occQ));
     const int nq = launch_vecql32_family(v, nk, zstore, rankstore, sms, st);
@@ -231,10 +241,10 @@ int launch_vec32(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     vecbt32_kernel<0><<<gridV, VEC32_WARPS * 32, smemBT, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[320];
-    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,full,vec> grid=%u x %d thr smem=%zuB %d CTA/SM + vecql32 grid=%u smem=%zuB %d CTA/SM + vecbt32 grid=%u %d CTA/SM; N=%d",
-             soc, gridW, PAIR_WARPS * 32, smemW, occW, gridQ, smemQ, occQ, gridV, occV, N);
+    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,%s,vec> grid=%u x %d thr smem=%zuB %d CTA/SM + vecql32 grid=%u smem=%zuB %d CTA/SM + vecbt32 grid=%u %d CTA/SM; N=%d",
+             soc, split ? "split + pair_tail16<vec>" : "full", gridW, PAIR_WARPS * 32, smemW, occW, gridQ, smemQ, occQ, gridV, occV, N);
     *info = buf;
-    return 3;
+    return 2 + nq + (split ? 1 : 0);
 }
 
 }  // namespace small

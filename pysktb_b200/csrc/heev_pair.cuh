@@ -462,15 +462,16 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
 
 // TAIL kernel: tridiagonalisation of the trailing 16x16 blocks (steps 16..30), two matrices per warp, d[16..31] and
 // e[16..30] into the (d,e) scratch.  Few registers: co-resides with the wide kernel of the next chunk.
-template <int S>
+template <int S, bool VEC = false>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const cplx* __restrict__ blocks, double* __restrict__ scratch, long long nk,
-                                                                          int out_stride, int d_off, int e_off) {
+                                                                          int out_stride, int d_off, int e_off, cplx* __restrict__ vstore = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 4;
     cplx* myw = reinterpret_cast<cplx*>(smem_raw) + (size_t)(2 * warp + g) * pair_buf_cplx<16>();
     for (int t = lane & 15; t < pair_buf_cplx<16>(); t += 16) myw[t] = cmake(0.0, 0.0);
     __syncwarp();
-    const PairBuf S_ = pair_buf<16>(myw);
+    PairBuf S_ = pair_buf<16>(myw);
+    S_.voff = 16;                 // eigenvector path: reflectors 16..30 / rows 16..31 of the [32][32] store
     const PairLane L = pair_lane<16>(lane);
     const long long n_pairs = (nk + 1) / 2;
 #pragma unroll 1
@@ -489,10 +490,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const c
             B[0][m] = blk[(2 * m + L.h) * 16 + L.iA];
             B[1][m] = blk[(2 * m + L.h) * 16 + L.iB];
         }
+        if (VEC) { S_.vst = vstore + (size_t)kq * PAIR_VSTORE_CPLX; S_.taust = S_.vst + 1024; }
         PairCarry c;
-        pair_prologue<16, false>(B, c, L, S_);
+        pair_prologue<16, VEC>(B, c, L, S_);
         int j = 0;
-        pair_phases<16, 8, 0, S, false>(B, c, j, L, S_);
+        pair_phases<16, 8, 0, S, VEC>(B, c, j, L, S_);
         if (k_ok) {
             double* out = scratch + (size_t)kq * out_stride;
             out[d_off + 16 + L.l] = S_.D[L.l]; out[e_off + 16 + L.l] = c.eval;

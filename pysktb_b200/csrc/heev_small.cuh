@@ -738,7 +738,7 @@ static int launch_pair(const LaunchCtx& c) {
     constexpr int SRC = SOC ? PAIR_SRC_SOC : PAIR_SRC_NOSOC;
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, true> : pair_wide32_kernel<SRC, 4, true>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, false> : pair_wide32_kernel<SRC, 4, false>;
-    void (*kT)(const cplx*, double*, long long, int, int, int) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
+    void (*kT)(const cplx*, double*, long long, int, int, int, cplx*) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
     static const bool tql_fast = !(getenv("SKTB_TQL_FAST") && getenv("SKTB_TQL_FAST")[0] == '0');
     void (*kB)(TqlArgs) = tql_fast ? tql_small_kernel<NC, 32, true> : tql_small_kernel<NC, 32, false>;
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
@@ -785,7 +785,7 @@ static int launch_pair(const LaunchCtx& c) {
         if (mode == 2) { cudaEventRecord(ps->evWide[b], sW); cudaStreamWaitEvent(sT, ps->evWide[b], 0); }
         if (mode != 0) {
             gridT = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
-            kT<<<gridT, PAIR_WARPS * 32, smemT, sT>>>(blocks, de, cnt, 2 * NC, 0, NC);
+            kT<<<gridT, PAIR_WARPS * 32, smemT, sT>>>(blocks, de, cnt, 2 * NC, 0, NC, nullptr);
             ++launches;
         }
         TqlArgs t{de, cnt, N, c.evals, c.ld, c.col0 + c0, c.fail};
