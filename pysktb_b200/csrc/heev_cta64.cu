@@ -163,15 +163,26 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     int* rankstore = reinterpret_cast<int*>(zstore + (size_t)nm * 1024);
     const size_t smemW = (size_t)PAIR_WARPS * pair_buf_cplx<32>() * 16;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * 32 * DSTRIDE * 8;
-    void (*kW)(SmallArgs, cplx*, cplx*) = evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, false>;
+    // steps 0..15 in the one-warp kernel, the trailing 16 x 16 block (parked in the Z region) two matrices per warp
+    static const bool split = !(getenv("SKTB_VEC32_SPLIT") && getenv("SKTB_VEC32_SPLIT")[0] == '0');
+    void (*kW)(SmallArgs, cplx*, cplx*) = split ? (evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, false, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, false, false>)
+                                                : (evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, false>);
     auto kB = tql_small_kernel<32, 32>;
     if (cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) { *info = "cudaFuncSetAttribute failed"; return -1; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nm + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 2));
-    kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, nullptr, evecs ? vstore : nullptr);
+    cplx* blk16 = reinterpret_cast<cplx*>(zstore);
+    kW<<<gridW, PAIR_WARPS * 32, smemW, st>>>(a, split ? blk16 : nullptr, evecs ? vstore : nullptr);
     int launches = 1;
+    if (split) {
+        const size_t smemT = (size_t)PAIR_WARPS * 2 * pair_buf_cplx<16>() * 16;
+        const unsigned gridT = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
+        if (evecs) pair_tail16_kernel<4, true><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, a.scratch, nm, 64, 0, 32, vstore);
+        else pair_tail16_kernel<4, false><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, a.scratch, nm, 64, 0, 32, nullptr);
+        ++launches;
+    }
     if (evecs) {
         Vec32Args v{a.scratch, vstore, nm, N, evals, evecs, ld, col0, fail};
         if (!vecbt32_smem_ok()) { *info = "cudaFuncSetAttribute(vecbt32) failed"; return -1; }
@@ -187,7 +198,7 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     }
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[200];
-    snprintf(buf, sizeof buf, "pair_wide32<load,full%s> grid=%u x %d thr + %s; N=%d", evecs ? ",vec" : "", gridW, PAIR_WARPS * 32,
+    snprintf(buf, sizeof buf, "pair_wide32<load,%s%s> grid=%u x %d thr + %s; N=%d", split ? "split + pair_tail16" : "full", evecs ? ",vec" : "", gridW, PAIR_WARPS * 32,
              evecs ? "vecql32 + vecbt32" : "tql_small", N);
     *info = buf;
     return launches;

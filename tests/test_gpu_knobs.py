@@ -49,6 +49,7 @@ CASES = {
     "SKTB_PEEL_QL_MIN=1": [(65, 60, False), (100, 70, False), (200, 33, False)],
     "SKTB_GENERIC_SPLIT=0": [(80, 20, True), (130, 10, True)],
     "SKTB_VEC_LIST=0": [(32, 200, True), (64, 100, True)],
+    "SKTB_VEC32_SPLIT=0": [(32, 200, True), (20, 100, True), (32, 300, False), (9, 50, False)],
     "SKTB_NO_PAIR=1": [(32, 300, False), (26, 300, False)],
     "SKTB_HEEV_GENERIC=1": [(8, 50, False), (32, 50, True), (64, 30, False)],
 }
