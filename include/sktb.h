@@ -91,7 +91,8 @@ int sktb_solve_mesh(sktb_plan* plan, const int32_t nk_mesh[3], int64_t first, in
 
 /* Batched Hermitian eigensolve of caller-supplied matrices: Hamiltonian._sol_ham (hamiltonian.py:108-126).
  * H_d [nm][N][N] row-major complex (only the lower triangle and the real diagonal enter the eigensolve, as with
- * numpy's default UPLO='L'); evals_d [N][nm]; evecs_d NULL or [N][nm][N]; nonherm_d NULL or [nm] gate flags.   */
+ * numpy's default UPLO='L'); evals_d [N][nm]; evecs_d NULL or [N][nm][N]; nonherm_d NULL or [nm] gate flags.
+ * Entries are expected at energy scale: no LAPACK-style rescaling is done, 1e-140 < |H_ij| < 1e140 (or exactly 0). */
 int sktb_heev(sktb_plan* plan, const double* H_d, int32_t N, int64_t nm, double* evals_d, double* evecs_d,
               int32_t* nonherm_d, void* stream);
 
