@@ -17,7 +17,10 @@ def tql_scan(d, e, l, n):
     return m
 
 
-def tql_lane(d, e_in, tiny=0.0):
+def tql_lane(d, e_in, tiny=0.0, record=None):
+    """record: optional list that receives the rotation list of the record-and-replay eigenvector path
+    (csrc/heev_vec32.cuh, tql_lane_rec): per sweep a header (m, count) followed by `count` pairs (c, s) for the rotations
+    i = m-1, m-2, ... in the order they are generated; replay_rotations() applies them to Z."""
     d = np.array(d, float)
     n = len(d)
     e = np.zeros(n)
@@ -44,6 +47,7 @@ def tql_lane(d, e_in, tiny=0.0):
         under = False
         di1, dnext, mb = d[m], 0.0, m
         i = m - 1
+        rots = []
         while i >= l:
             ei, di = e[i], d[i]
             f, b = s * ei, c * ei
@@ -56,6 +60,7 @@ def tql_lane(d, e_in, tiny=0.0):
                 break
             r = np.sqrt(h2)
             s, c = f / r, g / r
+            rots.append((c, s))
             g = di1 - p
             rr = (di - g) * s + 2.0 * c * b
             p = s * rr
@@ -70,6 +75,8 @@ def tql_lane(d, e_in, tiny=0.0):
             g = c * rr - b
             di1 = di
             i -= 1
+        if record is not None and rots:
+            record.append((m, rots))
         if under:
             m = tql_scan(d, e, l, n)
             continue
@@ -80,3 +87,19 @@ def tql_lane(d, e_in, tiny=0.0):
             it = 0
         m = mb
     return d, sweeps, fail
+
+
+def replay_rotations(n, record):
+    """Z <- product of the recorded plane rotations (the vecapply kernels: one row of Z per lane, a running `up` value, one
+    load and one store per rotation).  Column q of the result is the eigenvector of eigenvalue d[q] of tql_lane."""
+    Z = np.eye(n)
+    for m, rots in record:
+        up = Z[:, m].copy()
+        i = m - 1
+        for c, s in rots:
+            g = Z[:, i].copy()
+            Z[:, i + 1] = s * g + c * up
+            up = c * g - s * up
+            i -= 1
+        Z[:, i + 1] = up
+    return Z
