@@ -43,3 +43,20 @@ def test_peeled_run_hands_over_a_consistent_block(N):
     Tfull[P:, P:] = blk
     Tfull[P, P - 1] = Tfull[P - 1, P] = e[P - 1]
     assert np.abs(np.linalg.eigvalsh(A) - np.linalg.eigvalsh(Tfull)).max() < 1e-11
+
+
+@pytest.mark.parametrize("N,NB", [(6, 2), (32, 4), (45, 8)])
+def test_reflector_store_and_back_transformation(N, NB):
+    """Eigenvector path: tridiagonalise keeping (v_j, tau_j), eigenvectors Z of the real tridiagonal matrix,
+    U = H_0 ... H_{N-2} Z diagonalises the input (conventions of the vecbt32 / vecbt64 kernels)."""
+    A = _herm(N, 7 * N)
+    refl = {}
+    d, e = proto.tridiag_panel(A, NB, reflectors=refl)
+    T = np.diag(d) + np.diag(e[:N - 1], 1) + np.diag(e[:N - 1], -1)
+    lam, Z = np.linalg.eigh(T)
+    U = proto.back_transform(refl, Z)
+    assert np.abs(U.conj().T @ U - np.eye(N)).max() < 1e-12
+    assert np.abs(A @ U - U * lam[None, :]).max() < 1e-11 * max(1.0, np.abs(A).max())
+    # v_j has zeros up to row j and a unit entry at j+1, as the kernels store it explicitly
+    for j in range(N - 1):
+        assert np.all(refl["V"][:j + 1, j] == 0) and refl["V"][j + 1, j] == 1

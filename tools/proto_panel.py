@@ -19,11 +19,16 @@ def householder(alpha, xnorm2):
     return beta, complex((beta - alpha.real) / beta, -alpha.imag / beta), 1.0 / (alpha - beta)
 
 
-def tridiag_panel(A, NB=8, peel=0):
-    """A Hermitian (N, N).  Returns (d, e) - and the trailing block after `peel` steps when peel > 0."""
+def tridiag_panel(A, NB=8, peel=0, reflectors=None):
+    """A Hermitian (N, N).  Returns (d, e) - and the trailing block after `peel` steps when peel > 0.
+    reflectors: optional dict that receives "V" (N, N-1; column j = v_j with the unit entry at j+1) and "tau" (N-1,), the
+    store the eigenvector kernels keep (csrc/heev_pair.cuh / heev_cta64.cuh, VEC = true)."""
     M0 = np.array(A, dtype=complex)
     N = M0.shape[0]
     d, e = np.zeros(N), np.zeros(N)
+    if reflectors is not None:
+        reflectors["V"] = np.zeros((N, max(N - 1, 0)), complex)
+        reflectors["tau"] = np.zeros(max(N - 1, 0), complex)
     stop = peel if peel > 0 else N
     j0 = 0
     V = W = np.zeros((N, 0), complex)
@@ -47,6 +52,8 @@ def tridiag_panel(A, NB=8, peel=0):
             p = tau * y
             w = p - 0.5 * tau * np.vdot(p, v) * v
             V[:, t], W[:, t] = v, w
+            if reflectors is not None:
+                reflectors["V"][:, j], reflectors["tau"][j] = v, tau
         jn = j0 + tmax
         if tmax == NB and jn + 1 < N:
             M0 -= V @ W.conj().T + W @ V.conj().T                            # deferred rank-2NB update
@@ -57,6 +64,17 @@ def tridiag_panel(A, NB=8, peel=0):
     last = M0[N - 1, N - 1] - V[N - 1] @ W[N - 1].conj() - W[N - 1] @ V[N - 1].conj()
     d[N - 1] = last.real
     return d, e
+
+
+def back_transform(reflectors, Z):
+    """U = H_0 H_1 ... H_{N-2} Z with H_j = I - tau_j v_j v_j^H (the vecbt kernels: per eigenvector and reflector one dot
+    product t = tau_j (v_j^H u) and one update u -= t v_j, reflectors applied from j = N-2 down to 0)."""
+    U = np.array(Z, dtype=complex)
+    V, tau = reflectors["V"], reflectors["tau"]
+    for j in range(V.shape[1] - 1, -1, -1):
+        t = tau[j] * (V[:, j].conj() @ U)
+        U -= np.outer(V[:, j], t)
+    return U
 
 
 if __name__ == "__main__":
