@@ -60,3 +60,19 @@ def test_reflector_store_and_back_transformation(N, NB):
     # v_j has zeros up to row j and a unit entry at j+1, as the kernels store it explicitly
     for j in range(N - 1):
         assert np.all(refl["V"][:j + 1, j] == 0) and refl["V"][j + 1, j] == 1
+
+
+@pytest.mark.parametrize("N", [33, 40, 57, 63])
+def test_front_padding_makes_the_leading_steps_trivial(N):
+    """tridiag_cta64 pads 32 < N < 64 at the FRONT of its 64-wide frame and skips the phases before
+    J0 = 8 * ((64 - N) // 8): the steps over the zero padding are identity reflectors with d = e = 0, so the tridiagonal
+    matrix of the frame is 0_(64-N) (+) T(A) and starting at J0 changes nothing."""
+    off = 64 - N
+    A = _herm(N, 50 + N)
+    frame = np.zeros((64, 64), complex)
+    frame[off:, off:] = A
+    refl = {}
+    d, e = proto.tridiag_panel(frame, 4, reflectors=refl)
+    assert np.all(d[:off] == 0.0) and np.all(e[:off] == 0.0) and np.all(refl["tau"][:off] == 0.0)
+    T = np.diag(d[off:]) + np.diag(e[off:63], 1) + np.diag(e[off:63], -1)
+    assert np.abs(np.linalg.eigvalsh(A) - np.linalg.eigvalsh(T)).max() < 1e-11
