@@ -658,7 +658,11 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             double di = d[i];
             int rank = sorted_by_construction ? i : 0;
             if (!sorted_by_construction)
-                for (int q = 0; q < N; ++q) { double dq = d[q]; rank += (dq < di) || (dq == di && q < i); }
+                for (int q = 0; q < N; ++q) {      // NaNs order last, ties (and NaN against NaN) by index: every slot is written, as numpy's sort does
+                    double dq = d[q];
+                    const bool qn = dq != dq, in = di != di;
+                    rank += (!qn && (in || dq < di)) || ((dq == di || (qn && in)) && q < i);
+                }
             a.evals[(long long)rank * a.ld + a.col0 + mat] = di;
             e[i] = (double)rank;                   // e is free now: keep the permutation
         }

@@ -49,6 +49,22 @@ static int fail(const char* fmt, ...) {
         if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+// Every entry point works on the plan's device and restores the caller's current device on return (a process that
+// drives several GPUs must not see its current device change under it; torch reads it through cudaGetDevice).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                                               \
+    DeviceGuard _dev_guard(dev);                                                                     \
+    if (!_dev_guard.ok) return fail("cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(cudaGetLastError()))
+
 struct Buf {
     void* p = nullptr;
     size_t cap = 0;
@@ -139,7 +155,7 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("no CUDA device: libsktb has no CPU fallback (cudaGetDeviceCount: %s)", cudaGetErrorString(cudaGetLastError()));
     if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
-    CK(cudaSetDevice(device));
+    ON_DEVICE(device);
     const int na = D->n_atoms, n = D->n_orb, nb = D->n_bonds;
     if (na <= 0 || n <= 0 || nb < 0) return fail("bad model sizes");
     for (int a = 0; a < na; ++a)
@@ -294,7 +310,7 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
 
 extern "C" void sktb_plan_destroy(sktb_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     cudaDeviceSynchronize();
     for (void* d : p->owned) cudaFree(d);
     for (auto& w : p->ws) { w.H.release(); w.RT.release(); w.K.release(); w.S.release(); }
@@ -449,10 +465,10 @@ static size_t small_scratch_bytes(int N, long long nk) {
 static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc,
                       double* evals_d, double* evecs_d, long long ld, long long k_off, int* flags_d, cudaStream_t st, bool timed,
                       int ws_id = 2) {
-    sktb_plan::WorkSet& W = p->ws[ws_id];
     if (!p || !evals_d) return fail("null argument");
     if (nk <= 0) return 0;
-    CK(cudaSetDevice(p->device));
+    sktb_plan::WorkSet& W = p->ws[ws_id];
+    ON_DEVICE(p->device);
     const int N = soc ? 2 * p->n_orb : p->n_orb;
     int launches0 = (int)g_launches.load();
     if (timed) CK(cudaEventRecord(p->ev0, st));
@@ -559,7 +575,7 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
 extern "C" int sktb_hk(sktb_plan* p, const double* k_d, int64_t nk, int32_t soc, double* H_d, int32_t* nonherm_d, void* stream) {
     if (!p || !k_d || !H_d) return fail("null argument");
     if (nk <= 0) return 0;
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return launch_hk(p, k_d, nk, soc, (cplx*)H_d, nonherm_d, 0, (cudaStream_t)stream);
 }
 
@@ -579,7 +595,7 @@ extern "C" int sktb_solve_mesh(sktb_plan* p, const int32_t nk_mesh[3], int64_t f
 
 extern "C" int sktb_ql_failures(sktb_plan* p, int32_t* count) {
     if (!p || !count) return fail("null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     CK(cudaMemcpy(count, p->d_fail, sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -619,7 +635,7 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
     if (!p || !H_d || !evals_d) return fail("null argument");
     if (N <= 0) return fail("bad matrix size");
     if (nm <= 0) return 0;
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     size_t perH = (size_t)N * N * sizeof(cplx);
     if (nonherm_d) {
@@ -685,7 +701,7 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
 extern "C" int sktb_solve_host(sktb_plan* p, const double* k_h, int64_t nk, int32_t soc, double* evals_h, double* evecs_h,
                                int32_t* nonherm_any) {
     if (!p || !k_h || !evals_h) return fail("null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     if (nonherm_any) *nonherm_any = 0;
     if (nk <= 0) return 0;
     const int N = soc ? 2 * p->n_orb : p->n_orb;
@@ -764,7 +780,7 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     if (!p || !energies_d || !out_d) return fail("null argument");
     if (!k_d && !nk_mesh) return fail("need k points or a mesh");
     if (nE <= 0) return 0;
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = soc ? 2 * p->n_orb : p->n_orb;
     const int ng = n_groups > 0 ? n_groups : 1;
@@ -873,7 +889,7 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                              int32_t n_idx, const int32_t* idx, double* out_d, int32_t* nonherm_any_h, void* stream) {
     if (!p || !k_d || !energies_d || !out_d) return fail("null argument");
     if (nk <= 0 || nE <= 0) return 0;
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = soc ? 2 * p->n_orb : p->n_orb;
     std::vector<int> rows, grp_rows;
@@ -969,7 +985,7 @@ extern "C" int sktb_gauss_dos(sktb_plan* p, const double* evals_d, int64_t n, co
     if (!p || !energies_d || !out_d) return fail("null argument");
     if (nE <= 0) return 0;
     if (!(w > 0.0)) return fail("gaussian width must be positive");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(out_d, 0, (size_t)nE * 8, st));
     if (n <= 0) return 0;
@@ -990,7 +1006,7 @@ extern "C" int sktb_gauss_dos(sktb_plan* p, const double* evals_d, int64_t n, co
 
 extern "C" int sktb_band_energy(sktb_plan* p, const double* evals_d, int64_t ld, int64_t nk, int32_t n_occ, double* out_d, void* stream) {
     if (!p || !out_d) return fail("null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(out_d, 0, 8, st));
     if (nk <= 0 || n_occ <= 0) return 0;
@@ -1008,7 +1024,7 @@ extern "C" int sktb_band_energy(sktb_plan* p, const double* evals_d, int64_t ld,
 // measurement helper
 // ------------------------------------------------------------------------------------------------------
 extern "C" int sktb_fp64_peak(int device, double* tflops, double* ms_out) {
-    CK(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     double* d = nullptr;

@@ -39,7 +39,9 @@ def solve_kpath_sharded(ham, k_list, soc=True, gather=True, solver=None):
     N = local.shape[0] if local is not None else None
     # agree on N (a rank with an empty slice does not know it)
     use_cuda = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    # the plan's device, not torch's current one: the plan picks its GPU from LOCAL_RANK (hamiltonian.py) and the caller
+    # need not have called torch.cuda.set_device
+    dev = torch.device("cuda", _plan_device(ham)) if use_cuda else torch.device("cpu")
     n_t = torch.tensor([N or 0], dtype=torch.int64, device=dev)
     dist.all_reduce(n_t, op=dist.ReduceOp.MAX)
     N = int(n_t.item())
@@ -56,8 +58,16 @@ def solve_kpath_sharded(ham, k_list, soc=True, gather=True, solver=None):
     return out
 
 
-def allreduce_sum(arr):
-    """Sum a host array over ranks (DOS partial histograms)."""
+def _plan_device(ham):
+    import torch
+
+    d = getattr(ham, "_device", None)
+    return int(d) if d is not None else torch.cuda.current_device()
+
+
+def allreduce_sum(arr, device=None):
+    """Sum a host array over ranks (DOS partial histograms).  `device`: CUDA device index (or a Hamiltonian) the NCCL
+    collective runs on; defaults to torch's current device."""
     import torch
     import torch.distributed as dist
 
@@ -67,6 +77,8 @@ def allreduce_sum(arr):
     use_cuda = dist.get_backend() == "nccl"
     t = torch.from_numpy(np.ascontiguousarray(arr))
     if use_cuda:
-        t = t.cuda()
+        if device is not None and not isinstance(device, int):
+            device = _plan_device(device)
+        t = t.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()

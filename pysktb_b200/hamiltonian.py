@@ -375,8 +375,9 @@ class Hamiltonian(object):
                                       fl.data_ptr() if gate else None, self._stream()))
             out = torch.zeros(1, dtype=torch.float64, device="cuda")
             _lib.check(lib.sktb_band_energy(self._plan, ev.data_ptr(), len(mesh), len(mesh), neig, out.data_ptr(), self._stream()))
-            if gate and bool(fl.any().item()):
-                raise Exception(_NOT_HERMITIAN)
+            if gate and bool(fl.any().item()):    # the reference goes through ARPACK here, not through _sol_ham's gate
+                import warnings
+                warnings.warn("H(k) is not Hermitian for some k: total_energy follows the lower-triangle spectrum", RuntimeWarning)
             total = float(out.cpu()[0])
         return total / (len(mesh) * neig)
 

@@ -7,8 +7,18 @@ import sys
 
 import pytest
 
-pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu_ready():
+    try:
+        import torch
+        return torch.cuda.is_available() and os.path.exists(os.path.join(ROOT, "pysktb_b200", "libsktb.so"))
+    except Exception:
+        return False
+
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not _gpu_ready(), reason="needs a CUDA device and the built libsktb.so")]
 
 CHECK = r"""
 import sys, numpy as np, torch
