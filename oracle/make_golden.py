@@ -196,6 +196,8 @@ def fuzz_fixture(ref):
             ev, vec = quiet(ham.solve_kpath, list(ks), eig_vectors=True, soc=spec["soc"], parallel=0)
             out[f"ev_{seed}"] = np.asarray(ev)
             out[f"pw_{seed}"] = np.abs(np.asarray(vec)) ** 2              # |U|^2 per (band, k, component)
+            if seed % 4 == 0:
+                out[f"vec_{seed}"] = np.asarray(vec)                      # full eigenvectors [band, k, comp]: projector tests
             out[f"raises_{seed}"] = np.array(0)
         except Exception as exc:                                         # noqa: BLE001 - the reference raises bare Exception
             assert "not hermitian" in str(exc)
@@ -204,9 +206,52 @@ def fuzz_fixture(ref):
     print("fuzz.npz:", FUZZ_SEEDS, "models,", sum(int(out[f"raises_{s}"]) for s in range(FUZZ_SEEDS)), "raise")
 
 
+from oracle.make_golden_cases import LAW_CASES, LAW_DISTANCES  # noqa: E402
+
+
+def laws_fixture(ref):
+    """scaling.py:312-447 - Polynomial / Tabulated / Custom (and Constant) through the reference's own `__call__`, scalar
+    calls as `System.get_hop_params` makes them (system.py:206-210).  tests/golden/laws_misc.npz"""
+    out = {"d": LAW_DISTANCES}
+    for tag, (kind, kw) in LAW_CASES.items():
+        lawobj = getattr(ref.scaling, kind)(**kw)
+        out[tag] = np.array([float(lawobj(float(x))) for x in LAW_DISTANCES])
+    np.savez_compressed(os.path.join(OUT, "laws_misc.npz"), **out)
+    print("laws_misc", {k: v.shape for k, v in out.items()})
+
+
+def nonherm_dos_fixture(ref):
+    """f-orbital models: H(k) is not Hermitian, so the reference's inverse-based DOS (greens.py:70) is not an
+    eigenvalue sum.  The fixture records the reference's numbers; the tests assert the size of the deviation of the
+    lower-triangle-spectrum DOS this package returns.  tests/golden/nonherm_dos.npz"""
+    out = {}
+    E = np.linspace(-4.0, 4.0, 17)
+    for tag, spec, nk, eta in (("ce_spf_example", W.ce_spf_example(), [3, 3, 3], 0.1), ("T", W.ce_spdf_1atom(), [3, 3, 2], 0.1),
+                               ("C4", W.ce_spdf_2atom(), [2, 2, 2], 0.1)):
+        st, ham = quiet(W.instantiate, spec, ref, ref.scaling, numba=0)
+        gf = ref.GreensFunction(ham)
+        out[tag + "_E"], out[tag + "_nk"], out[tag + "_eta"] = E, np.array(nk), np.array(eta)
+        out[tag + "_dos_inv"] = quiet(gf.dos, E, nk=nk, eta=eta, soc=spec["soc"], parallel=False)
+        mesh = gf._generate_kmesh(nk)
+        ev = quiet(ham.solve_kpath, list(mesh), eig_vectors=False, soc=spec["soc"], parallel=0)   # the reference's own lower-triangle spectrum
+        lor = ((eta / np.pi) / ((E[:, None, None] - ev[None]) ** 2 + eta ** 2)).sum(axis=(1, 2)) / len(mesh)
+        out[tag + "_dos_lower"] = lor
+        out[tag + "_asym"] = np.array(max(np.abs(h - h.conj().T).max() for h in (ham.get_ham(k, l_soc=spec["soc"]) for k in mesh)))
+        print(tag, "max |H - H^dagger| =", float(out[tag + "_asym"]), " max rel |dos_lower / dos_inv - 1| =",
+              float(np.abs(lor / out[tag + "_dos_inv"] - 1).max()))
+    np.savez_compressed(os.path.join(OUT, "nonherm_dos.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
+    if "--round2-only" in sys.argv:
+        laws_fixture(ref)
+        nonherm_dos_fixture(ref)
+        model_fixture(ref, W.lowsym_spd(laws="misc"), nk_test=12, dos=(np.linspace(-3, 3, 13), [2, 2, 2], 0.1),
+                      ldos=(np.linspace(-3, 3, 7), [2, 2, 1], 0.1, [2, 1], None))
+        fuzz_fixture(ref)
+        return
     if "--next-rows-only" in sys.argv:
         next_rows_fixture(ref)
         return
@@ -235,6 +280,10 @@ def main():
     model_fixture(ref, W.lowsym_spd(laws=True), nk_test=12, dos=(E(-3, 3, 13), [2, 2, 2], 0.1),
                   ldos=(E(-3, 3, 7), [2, 2, 1], 0.1, [2, 1], None))
     model_fixture(ref, W.lowsym_spd(laws=False), nk_test=10)
+    model_fixture(ref, W.lowsym_spd(laws="misc"), nk_test=12, dos=(E(-3, 3, 13), [2, 2, 2], 0.1),
+                  ldos=(E(-3, 3, 7), [2, 2, 1], 0.1, [2, 1], None))
+    laws_fixture(ref)
+    nonherm_dos_fixture(ref)
     model_fixture(ref, W.d_soc_nonhermitian(), nk_test=8)
 
 

@@ -143,10 +143,27 @@ def sp_chain():
                 soc=True)
 
 
+def custom_law_func(d):
+    """User function of the `Custom` law in `lowsym_spd(laws="misc")` (module level: the reference's, this package's and
+    the oracle's law objects all wrap this same callable)."""
+    return -0.45 * (2.4 / d) ** 2.5 * np.exp(-0.2 * (d - 2.4))
+
+
 def lowsym_spd(seed=3, laws=True):
     """Low-symmetry triclinic 3-atom s/p/d model with two elements, distance laws and p-SOC.
     Not in the reference's examples: it exercises generic direction cosines, the ScalingLaw path
-    (system.py:205-213) and unequal orbital counts per atom.  Hermitian (no f, no lambda_d)."""
+    (system.py:205-213) and unequal orbital counts per atom.  Hermitian (no f, no lambda_d).
+    laws="misc": the remaining law classes of scaling.py:312-447 - Polynomial, Tabulated (cubic spline), Custom."""
+    if laws == "misc":
+        spec = lowsym_spd(seed, laws=False)
+        AA = dict(spec["params"]["AA"])
+        AA["V_sss"] = law("Polynomial", coeffs=[-0.6, 0.35, -0.08, 0.01], d0=2.4, cutoff=4.4)
+        AA["V_pps"] = law("Tabulated", distances=[1.8, 2.2, 2.6, 3.0, 3.4, 3.8], values=[1.55, 1.08, 0.77, 0.55, 0.4, 0.29])
+        AA["V_pds"] = law("Custom", func=custom_law_func, d0=2.4, cutoff=3.3, smooth_width=0.7)
+        AA["V_dds"] = law("Polynomial", coeffs=[-0.5], d0=2.4)
+        spec["params"] = dict(spec["params"], AA=AA)
+        spec["name"] = "lowsym_spd_misc"
+        return spec
     r = np.random.default_rng(seed)
     lat = (np.eye(3) + 0.15 * r.standard_normal((3, 3))).tolist()
     sd = ["s", "px", "py", "pz", "dxy", "dyz", "dxz", "dx2-y2", "dz2"]

@@ -36,6 +36,7 @@ GOLDEN_SPECS = {
     "C5_zigzag_32": ("zigzag_ribbon", {"n_chains": 32}), "sp_chain": ("sp_chain", {}),
     "lowsym_spd_laws": ("lowsym_spd", {"laws": True}), "lowsym_spd": ("lowsym_spd", {"laws": False}),
     "d_soc_nonherm": ("d_soc_nonhermitian", {}),
+    "lowsym_spd_misc": ("lowsym_spd", {"laws": "misc"}),          # Polynomial / Tabulated / Custom laws (scaling.py:312-447)
 }
 
 # oracle-only cases (no fixture file): padded / non-SOC variants of the 32-wide register kernels

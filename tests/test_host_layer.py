@@ -68,6 +68,25 @@ def test_scaling_laws_match_reference_hoppings():
         np.testing.assert_allclose(T[np.ix_(ki, kj)], H[im, starts[i]:starts[i + 1], starts[j]:starts[j + 1]].real, rtol=0, atol=1e-14)
 
 
+def test_polynomial_tabulated_custom_laws_bit_exact():
+    """scaling.py:312-447 through the product's classes == the reference's own `__call__` values (laws_misc.npz, made by
+    oracle/make_golden.py:laws_fixture), and the oracle's scalar restatement of the same laws."""
+    from oracle.make_golden_cases import LAW_CASES
+    from oracle import laws_oracle
+    g = golden("laws_misc")
+    for tag, (kind, kw) in LAW_CASES.items():
+        lawobj = getattr(tb.scaling, kind)(**kw)
+        got = np.array([lawobj(float(x)) for x in g["d"]])
+        assert np.array_equal(got, g[tag]), (tag, np.abs(got - g[tag]).max())
+        assert isinstance(lawobj(float(g["d"][0])), float)
+        np.testing.assert_array_equal(lawobj(g["d"]), g[tag])                       # array calls agree with scalar calls
+        if kind != "Constant":
+            okw = {k: v for k, v in kw.items()}
+            orc = laws_oracle.make(kind, **okw)
+            np.testing.assert_allclose([orc(float(x)) for x in g["d"]], g[tag], rtol=1e-15, atol=0)
+    assert repr(tb.scaling.ensure_scaling(-0.37)) == "Constant(-0.37)"
+
+
 def test_error_conventions():
     with pytest.raises(AssertionError, match="wrong orbitals"):
         tb.Atom("X", [0, 0, 0], ["s", "pq"])

@@ -155,3 +155,60 @@ def test_fuzz_oracle_vs_reference():
         np.testing.assert_allclose(ev, g[f"ev_{seed}"], rtol=0, atol=1e-10, err_msg=spec["name"])
         np.testing.assert_allclose(_fuzz_moment(ev, np.abs(vec) ** 2), _fuzz_moment(g[f"ev_{seed}"], g[f"pw_{seed}"]),
                                    rtol=1e-8, atol=1e-10, err_msg=spec["name"])
+
+
+NONHERM = {"ce_spf_example": ("ce_spf_example", {}), "T": ("ce_spdf_1atom", {}), "C4": ("ce_spdf_2atom", {})}
+# max_E |DOS(lower-triangle spectrum) / DOS(reference's dense inverse) - 1| on the fixture's mesh: the documented deviation
+# for f-orbital models, whose H(k) is NOT Hermitian (|H - H^dagger| ~ 1.4 eV, purely imaginary)
+NONHERM_DEVIATION = {"ce_spf_example": 0.9004073575305005, "T": 0.9486637184619495, "C4": 0.6988516850186401}
+
+
+@pytest.mark.parametrize("tag", ["ce_spf_example", "T"])
+def test_nonhermitian_dos_deviation_recorded(tag):
+    """For f-orbital models the reference's inverse-based DOS (greens.py:70) is not an eigenvalue sum; the fixture holds
+    the reference's numbers for both readings.  The oracle follows the reference on both; the deviation between them is
+    the number DESIGN.md records (the CUDA path returns the lower-triangle reading, tests/test_gpu_parity.py)."""
+    from pysktb_b200 import workloads as W
+    g = golden("nonherm_dos")
+    fn, kw = NONHERM[tag]
+    spec = W.ALL[fn](**kw)
+    m = oracle_model(spec)
+    E, nk, eta = g[tag + "_E"], [int(x) for x in g[tag + "_nk"]], float(g[tag + "_eta"])
+    np.testing.assert_allclose(m.dos(E, nk, eta, spec["soc"]), g[tag + "_dos_inv"], rtol=1e-10)          # the reference's inverse
+    ev = m.solve_kpath(list(m.kmesh(nk)), soc=spec["soc"])
+    low = lorentz_dos(ev, E, eta)
+    np.testing.assert_allclose(low, g[tag + "_dos_lower"], rtol=1e-10)                                    # its lower-triangle spectrum
+    dev = float(np.abs(low / g[tag + "_dos_inv"] - 1).max())
+    assert abs(dev - NONHERM_DEVIATION[tag]) < 1e-8 and float(g[tag + "_asym"]) > 1.0
+
+
+def cluster_projectors(ev, vec, tol=1e-7):
+    """Spectral projectors of one k-point: [(mean eigenvalue, P)] with P = sum over a degenerate cluster of u u^H
+    (rows of `vec` are eigenvectors, the reference's layout); gauge- and basis-independent within a cluster."""
+    out, start = [], 0
+    for n in range(1, len(ev) + 1):
+        if n == len(ev) or ev[n] - ev[n - 1] > tol:
+            U = vec[start:n]
+            out.append((float(np.mean(ev[start:n])), U.T @ U.conj()))
+            start = n
+    return out
+
+
+def test_fuzz_projectors_oracle_vs_reference():
+    """Every 4th fuzz model carries the reference's full eigenvectors: spectral projectors of every degenerate cluster."""
+    from pysktb_b200 import workloads as W
+    g = golden("fuzz")
+    n_checked = 0
+    for seed in range(0, int(g["n_seeds"]), 4):
+        if int(g[f"raises_{seed}"]):
+            continue
+        spec = W.random_spec(seed)
+        ev, vec = oracle_model(spec).solve_kpath(list(g[f"k_{seed}"]), eig_vectors=True, soc=spec["soc"])
+        for q in range(ev.shape[1]):
+            ref = cluster_projectors(g[f"ev_{seed}"][:, q], g[f"vec_{seed}"][:, q, :])
+            got = cluster_projectors(ev[:, q], vec[:, q, :])
+            assert len(ref) == len(got), spec["name"]
+            for (e0, P0), (e1, P1) in zip(ref, got):
+                assert abs(e0 - e1) < 1e-10 and np.abs(P0 - P1).max() < 1e-8, spec["name"]
+                n_checked += 1
+    assert n_checked > 100
