@@ -14,7 +14,7 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     constexpr int NC = 64;
     if (N <= 32 || N > 64) { *info = "launch_cta64: N out of range"; return -1; }
     static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
-    auto kB = tql_small_kernel<NC, 64>;
+    void (*kB)(TqlArgs) = tql_mode_env() == 2 ? tql_small_kernel<NC, 64, 2> : tql_small_kernel<NC, 64, 1>;
     const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
     if (cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) {
         *info = "cudaFuncSetAttribute(smem=" + std::to_string(smemB) + ") failed"; return -1;
@@ -167,7 +167,7 @@ int launch_heev32(const cplx* H, int N, long long nm, double* evals, cplx* evecs
     static const bool split = !(getenv("SKTB_VEC32_SPLIT") && getenv("SKTB_VEC32_SPLIT")[0] == '0');
     void (*kW)(SmallArgs, cplx*, cplx*) = split ? (evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, false, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, false, false>)
                                                 : (evecs ? pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true> : pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, false>);
-    auto kB = tql_small_kernel<32, 32>;
+    void (*kB)(TqlArgs) = tql_mode_env() == 2 ? tql_small_kernel<32, 32, 2> : tql_small_kernel<32, 32, 1>;
     if (cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB) != cudaSuccess) { *info = "cudaFuncSetAttribute failed"; return -1; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

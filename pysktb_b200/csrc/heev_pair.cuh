@@ -40,20 +40,20 @@ constexpr int PAIR_VSTORE_CPLX = 32 * 32 + 32;      // reflectors [j][i] + tau[j
 // One buffer set per matrix: reflector broadcast buffers of 2 LN entries whose upper half stays zero (window
 // columns beyond the matrix read v = p = x = 0).
 struct PairBuf {
-    cplx *V0, *V1, *P, *X, *alpha;   // V double-buffered by step parity
-    double* D;                       // [LN] diagonal
+    cplx *V0, *V1, *P, *X, *alpha;   // V double-buffered by step parity; X, alpha, D: one copy per column parity (branch-free publish)
+    double* D;                       // [2][LN] diagonal: entry j lives in copy j & 1
     cplx* vst = nullptr;             // global [32][32] reflector store of this matrix (eigenvector path) or NULL
     cplx* taust = nullptr;           // global [32] tau
     int voff = 0;                    // row / reflector offset of this (sub)matrix inside the store
     int vstride = 32;                // row stride of the store (32, or 64 when the block is the tail of a 64-wide matrix)
 };
-template <int LN> __host__ __device__ constexpr int pair_buf_cplx() { return 8 * LN + 2 + LN / 2; }   // V0 | V1 | P | X | alpha, pad | D
+template <int LN> __host__ __device__ constexpr int pair_buf_cplx() { return 11 * LN + 2; }   // V0 | V1 | P | X[2] | alpha[2] | D[2]
 
 template <int LN>
 SKTB_D PairBuf pair_buf(cplx* base) {
     PairBuf b;
-    b.V0 = base; b.V1 = base + 2 * LN; b.P = base + 4 * LN; b.X = base + 6 * LN; b.alpha = base + 8 * LN;
-    b.D = reinterpret_cast<double*>(base + 8 * LN + 2);
+    b.V0 = base; b.V1 = base + 2 * LN; b.P = base + 4 * LN; b.X = base + 6 * LN; b.alpha = base + 10 * LN;
+    b.D = reinterpret_cast<double*>(base + 10 * LN + 2);
     return b;
 }
 
@@ -128,16 +128,19 @@ struct PairCarry {
     double g, tau2, eval;
 };
 
-// publish pivot column jn: X (masked to rows > jn+1), alpha = A[jn+1][jn], d[jn] = A[jn][jn]  (owner-parity lanes)
-template <int NS>
-SKTB_D void pair_publish(const cplx (&x)[2], const int jn, const bool owner, const PairLane& L, const PairBuf& S) {
+// publish pivot column jn: X (masked to rows > jn+1), alpha = A[jn+1][jn], d[jn] = A[jn][jn].  Branch-free: the lanes of
+// BOTH column parities store - each into its own parity's copy of X / alpha / D - and the readers take the copy of the
+// parity that owns column jn (the other copy receives that parity's register of the same window slot: never read).
+template <int LN, int NS>
+SKTB_D void pair_publish(const cplx (&x)[2], const int jn, const PairLane& L, const PairBuf& S) {
+    cplx* Xw = S.X + L.h * (2 * LN);
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) {
         const int i = s ? L.iB : L.iA;
         const cplx xv = (i > jn + 1) ? x[s] : cmake(0.0, 0.0);
-        if (owner) S.X[i] = xv;
-        if (owner && i == jn + 1) *S.alpha = x[s];
-        if (owner && i == jn) S.D[jn] = x[s].x;
+        Xw[i] = xv;
+        if (i == jn + 1) S.alpha[L.h] = x[s];
+        if (i == jn) S.D[L.h * LN + jn] = x[s].x;
     }
 }
 
@@ -193,19 +196,29 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
     constexpr int ME = EVEN ? 0 : 1;          // register of the next pivot column
     constexpr int SH = EVEN ? 0 : 1;          // destination shift
     const int base = EVEN ? j : j - 1;
+    constexpr int PH = EVEN ? 1 : 0;          // parity of the lanes that own the next pivot column jn
     const cplx* Pl = S.P + base + L.h;
     const cplx* Vl = (EVEN ? S.V0 : S.V1) + base + L.h;
-    const cplx* Xl = S.X + base + L.h;
+    const cplx* Xs = S.X + PH * (2 * LN);
+    const cplx* Xl = Xs + base + L.h;
     const int jn = j + 1;
 
-    // ---- reduction for w' (issued first, consumed after the p-half of the update) ----
-    const double G = pair_rsum<LN>(c.g);
+    // ---- reduction for w': one butterfly stage per slice of the p-half of the update, in SOURCE order (ptxas keeps the
+    // rough order of independent work: with the reduction written first its DADDs - each waiting ~30 cycles for a shuffle
+    // - were issued ahead of the DFMA stream and stalled the in-order warp at the top of every step) ----
+    constexpr int NST = LN == 32 ? 4 : 3;     // xor 2, 4, 8 (, 16): lanes of equal column parity within the matrix
+    constexpr int CH = (HALF - ME + NST) / (NST + 1) > 0 ? (HALF - ME + NST) / (NST + 1) : 1;
+    double G = c.g;
 #pragma unroll
     for (int m = ME; m < HALF; ++m) {
         const cplx pq = Pl[2 * m];
 #pragma unroll
         for (int s = 2 - NS; s < 2; ++s) pair_upd1(B[s][m], c.v[s], pq);
+        const int done = m - ME + 1;
+        if (done % CH == 0 && done / CH <= NST) G += __shfl_xor_sync(0xffffffffu, G, 1 << (done / CH));
     }
+#pragma unroll
+    for (int st = (HALF - ME) / CH + 1; st <= NST; ++st) G += __shfl_xor_sync(0xffffffffu, G, 1 << st);   // stages the loop was too short for
     const double coef = -c.tau2 * G;
     cplx wp[2], x[2];
     {
@@ -217,16 +230,16 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
             x[s] = B[s][ME];
         }
     }
-    pair_publish<NS>(x, jn, L.h == (EVEN ? 1 : 0), L, S);
+    pair_publish<LN, NS>(x, jn, L, S);
     __syncwarp();
     cplx xo[2];
     double xnp = 0.0;
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) {
-        xo[s] = S.X[s ? L.iB : L.iA];
+        xo[s] = Xs[s ? L.iB : L.iA];
         xnp = fma(xo[s].x, xo[s].x, xnp); xnp = fma(xo[s].y, xo[s].y, xnp);
     }
-    const cplx alpha = *S.alpha;
+    const cplx alpha = S.alpha[PH];
     const double xn = pair_rsum<LN>(xnp);
     // ---- v-half on the remaining registers fused with the look-ahead mat-vec ----
     cplx z[2], acol[2];
@@ -261,7 +274,7 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
 template <int LN, bool VEC>
 SKTB_D void pair_prologue(cplx (&B)[2][LN / 2], PairCarry& c, const PairLane& L, const PairBuf& S) {
     cplx x[2] = {B[0][0], B[1][0]};
-    pair_publish<2>(x, 0, L.h == 0, L, S);
+    pair_publish<LN, 2>(x, 0, L, S);           // column 0: parity-0 copy
     __syncwarp();
     cplx xo[2];
     double xnp = 0.0;
@@ -270,7 +283,7 @@ SKTB_D void pair_prologue(cplx (&B)[2][LN / 2], PairCarry& c, const PairLane& L,
         xo[s] = S.X[s ? L.iB : L.iA];
         xnp = fma(xo[s].x, xo[s].x, xnp); xnp = fma(xo[s].y, xo[s].y, xnp);
     }
-    const cplx alpha = *S.alpha;
+    const cplx alpha = S.alpha[0];
     const double xn = pair_rsum<LN>(xnp);
     cplx z[2], acol[2];
     z[0] = z[1] = cmake(0.0, 0.0);
@@ -449,7 +462,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
         pair_phases<32, 16, FULL ? 0 : 8, S, VEC>(B, c, j, L, S_);
         if (k_ok) {
             double* out = a.scratch + (size_t)kq * (a.out_stride ? a.out_stride : 2 * NC);
-            out[a.d_off + lane] = S_.D[lane]; out[(a.out_stride ? a.e_off : NC) + lane] = c.eval;
+            out[a.d_off + lane] = S_.D[(lane & 1) * 32 + lane]; out[(a.out_stride ? a.e_off : NC) + lane] = c.eval;
             if (!FULL) {
                 cplx* blk = blocks + (size_t)kq * 256 + (15 - L.r);
 #pragma unroll
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const c
         pair_phases<16, 8, 0, S, VEC>(B, c, j, L, S_);
         if (k_ok) {
             double* out = scratch + (size_t)kq * out_stride;
-            out[d_off + 16 + L.l] = S_.D[L.l]; out[e_off + 16 + L.l] = c.eval;
+            out[d_off + 16 + L.l] = S_.D[(L.l & 1) * 16 + L.l]; out[e_off + 16 + L.l] = c.eval;
         }
         __syncwarp();
     }

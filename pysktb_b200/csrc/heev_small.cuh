@@ -187,6 +187,95 @@ SKTB_D int tql_lane(double* d, double* e, int n) {
     return fail;
 }
 
+// Square-root-free implicit QL (Pal-Walker-Kahan), eigenvalues only, one matrix per lane: the recurrence of LAPACK
+// dsterf's QL branch - the routine numpy's eigvalsh ends in (hamiltonian.py:119 -> zheevd(jobz='N') -> dsterf) - on
+// (d, e^2), as the same flat state machine as tql_lane: one trip = one sweep of the lane's unreduced block [l..m], the
+// deflation tests of the next sweep folded into the sweep.  Per inner step: 2 LDS + 2 STS, two independent hardware
+// reciprocals (1/r and 1/p; 1/c = r/p) with Newton refinement, ~20 FP64 ops - about half of the rotation-based sweep
+// (one rsqrt, but both the (c, s) rotation and the f/b/r recurrence).  Deflation: e^2 <= eps^2 |d_m d_{m+1}| (dsterf's
+// test) + a norm-relative floor (1e-3 eps ||T||)^2 so that exactly-zero diagonals (zero modes) deflate as well.
+// tools/proto_pwk.py is the scalar model of this function.
+SKTB_D int tql_scan_pwk(const double* d, const double* e, int l, int n, const double eps2, const double floor2) {
+    int m = l;
+    for (; m < n - 1; ++m)
+        if (e[m * DSTRIDE] <= fma(eps2, fabs(d[m * DSTRIDE] * d[(m + 1) * DSTRIDE]), floor2)) break;
+    return m;
+}
+
+SKTB_D int tql_lane_pwk(double* d, double* e, int n) {
+    const double eps2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+#define D_(i) d[(i) * DSTRIDE]
+#define E_(i) e[(i) * DSTRIDE]
+    double anorm = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double ei = (i < n - 1) ? E_(i) : 0.0;
+        anorm = fmax(anorm, fmax(fabs(D_(i)), fabs(ei)));
+        E_(i) = ei * ei;
+    }
+    const double floor2 = eps2 * anorm * anorm * 1.0e-6;
+    int fail = 0, l = 0, iter = 0;
+    int m = tql_scan_pwk(d, e, 0, n, eps2, floor2);
+    while (true) {
+        if (m == l || iter > 80) {
+            if (m != l) fail = 1;
+            ++l; iter = 0;
+            if (l >= n) break;
+            m = tql_scan_pwk(d, e, l, n, eps2, floor2);
+            continue;
+        }
+        ++iter;
+        const double p = D_(l), e2l = E_(l);
+        const double rte = e2l * fast_rsqrt(e2l);
+        const double sg = (D_(l + 1) - p) * fast_rcp(2.0 * rte);
+        const double h = fma(sg, sg, 1.0);
+        const double r0 = h * fast_rsqrt(h);
+        const double q = rte * fast_rcp(sg + (sg >= 0.0 ? r0 : -r0));
+        const double sigma = p - ((fabs(q) <= 1.7e308) ? q : 0.0);
+        double c = 1.0, s = 0.0;
+        double gamma = D_(m) - sigma;
+        double pp = gamma * gamma;
+        double dnext = 0.0;
+        int mb = m;
+        for (int i = m - 1; i >= l; --i) {
+            const double bb = E_(i), alpha = D_(i);
+            const double r = pp + bb;
+            const double ir = fast_rcp(r), ipp = fast_rcp(pp);     // independent: 1/c = r / pp
+            const double e2new = s * r;
+            const double oldc = c, oldgam = gamma;
+            c = pp * ir; s = bb * ir;
+            gamma = fma(c, alpha - sigma, -s * oldgam);
+            const double dnew = oldgam + (alpha - gamma);
+            D_(i + 1) = dnew;
+            const double g2 = gamma * gamma;
+            pp = (c > 1.0e-290) ? g2 * (r * ipp) : oldc * bb;
+            const double adn = fabs(dnew);
+            if (i != m - 1) {
+                E_(i + 1) = e2new;
+                if (e2new <= fma(eps2, adn * dnext, floor2)) mb = i + 1;
+            }
+            dnext = adn;
+        }
+        const double e2n = s * pp, dl = sigma + gamma;
+        E_(l) = e2n; D_(l) = dl; E_(m) = 0.0;
+        if (e2n <= fma(eps2, fabs(dl) * dnext, floor2)) { ++l; iter = 0; }
+        m = mb;
+    }
+#undef D_
+#undef E_
+    return fail;
+}
+
+// MODE 0: IEEE sqrt / division rotations, 1: rsqrt rotations (tql_lane<true>), 2: square-root-free PWK sweep
+template <int MODE>
+SKTB_D int tql_lane_mode(double* d, double* e, int n) {
+    if constexpr (MODE == 2) return tql_lane_pwk(d, e, n);
+    else return tql_lane<MODE == 1>(d, e, n);
+}
+inline int tql_mode_env() {
+    static const int mode = getenv("SKTB_TQL_MODE") ? atoi(getenv("SKTB_TQL_MODE")) : ((getenv("SKTB_TQL_FAST") && getenv("SKTB_TQL_FAST")[0] == '0') ? 0 : 2);
+    return mode;
+}
+
 template <int L>
 SKTB_D double group_sum(double v) {
 #pragma unroll
@@ -533,7 +622,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, 3) tridiag_fold32_kernel(Sma
 }
 
 // one tridiagonal matrix per lane: transpose (d,e) through shared memory, QL, bitonic sort, coalesced store
-template <int NC, int P2, bool FAST = true>
+template <int NC, int P2, int MODE = 2>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -561,7 +650,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
             }
         }
         __syncwarp();
-        if (tql_lane<FAST>(dbuf + lane, ebuf + lane, N)) atomicAdd(a.fail, 1);
+        if (tql_lane_mode<MODE>(dbuf + lane, ebuf + lane, N)) atomicAdd(a.fail, 1);
         double ev[P2];
 #pragma unroll
         for (int q = 0; q < P2; ++q) ev[q] = (q < N && q < NC) ? dbuf[q * DSTRIDE + lane] : __longlong_as_double(0x7ff0000000000000LL);
@@ -579,7 +668,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_small_kernel(TqlArgs a) 
 // kernel (head[mat][2][P]) and of the trailing Nt x Nt block from the register-resident kernels (tail[mat][128]: d at
 // 0.., e at 64..).  One matrix per lane like tql_small_kernel; the ascending order comes from a rank count in shared
 // memory (a register sorting network of this size would not fit).  Dynamic shared memory: warps * 2 * N * DSTRIDE * 8.
-template <int UNUSED>
+template <int MODE>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_merge_kernel(const double* __restrict__ head, int P, const double* __restrict__ tail, int Nt,
                                                                      long long nm, double* __restrict__ evals, long long ld, long long col0, int* fail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -600,7 +689,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_merge_kernel(const doubl
 #pragma unroll 4
         for (int t = 0; t < Nt; ++t) { dbuf[(P + t) * DSTRIDE + lane] = tl[t]; ebuf[(P + t) * DSTRIDE + lane] = tl[64 + t]; }
         __syncwarp();
-        if (tql_lane(dbuf + lane, ebuf + lane, N)) atomicAdd(fail, 1);
+        if (tql_lane_mode<MODE>(dbuf + lane, ebuf + lane, N)) atomicAdd(fail, 1);
         // ascending rank of every eigenvalue of this lane's matrix (ties by index), permuted into ebuf
 #pragma unroll 1
         for (int i = 0; i < N; ++i) {
@@ -739,8 +828,8 @@ static int launch_pair(const LaunchCtx& c) {
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, true> : pair_wide32_kernel<SRC, 4, true>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, false> : pair_wide32_kernel<SRC, 4, false>;
     void (*kT)(const cplx*, double*, long long, int, int, int, cplx*) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
-    static const bool tql_fast = !(getenv("SKTB_TQL_FAST") && getenv("SKTB_TQL_FAST")[0] == '0');
-    void (*kB)(TqlArgs) = tql_fast ? tql_small_kernel<NC, 32, true> : tql_small_kernel<NC, 32, false>;
+    const int tql_mode = tql_mode_env();
+    void (*kB)(TqlArgs) = tql_mode == 2 ? tql_small_kernel<NC, 32, 2> : (tql_mode == 1 ? tql_small_kernel<NC, 32, 1> : tql_small_kernel<NC, 32, 0>);
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemW) + ") failed"; return -1;
     }
@@ -825,7 +914,7 @@ static int launch_one(const LaunchCtx& c) {
     void (*kA)(SmallArgs);
     if constexpr (FOLD) kA = tridiag_fold32_kernel<SOC, GATE>;
     else kA = tridiag_small_kernel<NC, L, SOC, GATE>;
-    auto kB = tql_small_kernel<NC, P2>;
+    void (*kB)(TqlArgs) = tql_mode_env() == 2 ? tql_small_kernel<NC, P2, 2> : tql_small_kernel<NC, P2, 1>;
     if (smemA > 48 * 1024 && cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA) != cudaSuccess) {
         *c.info = "cudaFuncSetAttribute(smem=" + std::to_string(smemA) + ") failed"; return -1;
     }

@@ -419,10 +419,11 @@ static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     const int warps = (int)std::min<size_t>(small::SMALL_WARPS, (200 * 1024) / per_warp);
     if (a.nm >= ql_min && warps >= 1) {
         const size_t smem = per_warp * warps;
-        CK(cudaFuncSetAttribute(small::tql_merge_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kM = small::tql_mode_env() == 2 ? small::tql_merge_kernel<2> : small::tql_merge_kernel<1>;
+        CK(cudaFuncSetAttribute(kM, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long batches = (a.nm + 31) / 32;
         const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((batches + warps - 1) / warps, 148));
-        small::tql_merge_kernel<0><<<grid, warps * 32, smem, st>>>(head, P, c64s, Nt, a.nm, a.evals, a.ld, a.col0, p->d_fail);
+        kM<<<grid, warps * 32, smem, st>>>(head, P, c64s, Nt, a.nm, a.evals, a.ld, a.col0, p->d_fail);
         LAUNCHED();
         g_kinfo = "peel " + std::to_string(P) + " steps: " + first + " | " + info + " | tql_merge x" + std::to_string(warps) + " warps";
         return 0;
