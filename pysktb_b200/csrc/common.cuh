@@ -178,4 +178,34 @@ SKTB_HD void kmesh_point(long long idx, int n0, int n1, int n2, double& kx, doub
 #endif
 }
 
+// Device view of the k-independent model tables (see sktb_model_desc in include/sktb.h).
+struct PlanView {
+    int n_atoms, n_orb, n_bonds, n_pairs, soc_nnz;
+    const int* atom_start;    // [n_atoms+1]
+    const int* orb_atom;      // [n_orb]
+    const int* pair_of;       // [n_atoms*n_atoms] -> pair id or -1
+    const int* pair_begin;    // [n_pairs+1] range into the pair-sorted bond arrays
+    const double* bond_vec;   // [n_bonds][3]  (pair-sorted, image ascending inside a pair)
+    const long long* bond_off;  // [n_bonds] offset of the bond's [n_i][n_j] block in T
+    const double* T;          // packed hopping blocks
+    const double* onsite;     // [n_orb]
+    const int* soc_row; const int* soc_col; const cplx* soc_val;
+    double rec[9];            // inv(lattice).T row-major
+};
+
+#ifdef __CUDACC__
+// phase of one bond at fractional k: exp(2 pi i (k @ rec) . d), same operation order as calc_g
+// (hamiltonian.py:280, :311): kc = k@rec ; arg = (2*pi) * dot(kc, d).
+SKTB_D cplx bond_phase(const double* rec, double k0, double k1, double k2, const double* d) {
+    double c0 = __dadd_rn(__dadd_rn(__dmul_rn(k0, rec[0]), __dmul_rn(k1, rec[3])), __dmul_rn(k2, rec[6]));
+    double c1 = __dadd_rn(__dadd_rn(__dmul_rn(k0, rec[1]), __dmul_rn(k1, rec[4])), __dmul_rn(k2, rec[7]));
+    double c2 = __dadd_rn(__dadd_rn(__dmul_rn(k0, rec[2]), __dmul_rn(k1, rec[5])), __dmul_rn(k2, rec[8]));
+    double dot = __dadd_rn(__dadd_rn(__dmul_rn(c0, d[0]), __dmul_rn(c1, d[1])), __dmul_rn(c2, d[2]));
+    double arg = __dmul_rn(6.283185307179586, dot);
+    cplx ph;
+    sincos(arg, &ph.y, &ph.x);
+    return ph;
+}
+#endif
+
 }  // namespace sktb

@@ -9,8 +9,20 @@ size_t cta64_bytes_per_k() { return (size_t)128 * 8 + (size_t)1024 * 16 + (size_
 // Eigenvalues for 32 < N <= 64: tridiag_cta64 (steps 0..31, four warps per matrix) -> trailing 32 x 32 block ->
 // pair_wide32<LOAD> (steps 32..47, one warp per matrix) -> pair_tail16 (steps 48..62, two matrices per warp) -> tql<64>.
 // SKTB_CTA64_SPLIT=0: all 63 steps in tridiag_cta64.
+// fill the BUILD fields of the kernel arguments and opt the kernel into its dynamic shared memory
+static bool c64_apply_build(C64Args& a, const C64Build* b, void (*kern)(C64Args), std::string* info) {
+    a.H = nullptr; a.pv = b->pv; a.k = b->k;
+    a.mesh0 = b->mesh ? b->mesh[0] : 1; a.mesh1 = b->mesh ? b->mesh[1] : 1; a.mesh2 = b->mesh ? b->mesh[2] : 1;
+    a.first = b->first; a.soc = b->soc; a.Sdense = b->Sdense;
+    // static (14 KB) + dynamic shared memory beyond 48 KB needs the opt-in: always ask for it
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes()) != cudaSuccess) {
+        *info = "cudaFuncSetAttribute(tridiag_cta64<build>, " + std::to_string(b->smem_bytes()) + ") failed"; return false;
+    }
+    return true;
+}
+
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
-                 std::string* info, int h_ld, long long h_mstride, long long h_off, bool tridiag_only) {
+                 std::string* info, int h_ld, long long h_mstride, long long h_off, bool tridiag_only, const C64Build* build) {
     constexpr int NC = 64;
     if (N <= 32 || N > 64) { *info = "launch_cta64: N out of range"; return -1; }
     static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
@@ -22,7 +34,7 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     int dev = 0, sms = 148, occA = 0, occB = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false>, C64_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false, false>, C64_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
     if (occA < 1 || occB < 1) { *info = "cta64 kernels do not fit"; return -1; }
     double* de = scratch;
@@ -33,8 +45,12 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     C64Args a{H, N, nm, de, nullptr, split ? blk32 : nullptr, h_ld, h_mstride, h_off, front ? 1 : 0};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
     int launches = 2;
+    void (*kA)(C64Args) = split ? (build ? tridiag_cta64_kernel<true, true> : tridiag_cta64_kernel<true, false>)
+                                : (build ? tridiag_cta64_kernel<false, true> : tridiag_cta64_kernel<false, false>);
+    const size_t smemA = build ? build->smem_bytes() : 0;
+    if (build && !c64_apply_build(a, build, kA, info)) return -1;
     if (split) {
-        tridiag_cta64_kernel<true><<<gridA, C64_THREADS, 0, st>>>(a);
+        kA<<<gridA, C64_THREADS, smemA, st>>>(a);
         SmallArgs w{};
         w.k = nullptr; w.mesh0 = w.mesh1 = w.mesh2 = 1; w.first = 0; w.nk = nm; w.N = front ? 32 : N - 32; w.soc = 0;
         w.scratch = de; w.flags = nullptr; w.flag_off = 0; w.Hsrc = blk32; w.Hld = 32; w.out_stride = 128; w.d_off = 32 - off; w.e_off = 96 - off;
@@ -45,7 +61,7 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
         pair_tail16_kernel<8><<<gridT, PAIR_WARPS * 32, smemT, st>>>(blk16, de, nm, 128, 32 - off, 96 - off);
         launches = 4;
     } else {
-        tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);
+        kA<<<gridA, C64_THREADS, smemA, st>>>(a);
     }
     TqlArgs t{de, nm, N, evals, ld, col0, fail};
     const unsigned gridB = (unsigned)std::max<long long>(1, std::min<long long>(((nm + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * occB));
@@ -53,8 +69,8 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
     else kB<<<gridB, SMALL_WARPS * 32, smemB, st>>>(t);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[320];
-    snprintf(buf, sizeof buf, "hk + tridiag_cta64%s grid=%u x %d thr %d CTA/SM%s + tql_small<64> grid=%u smem=%zuB %d CTA/SM; N=%d", split ? "<split>" : "",
-             gridA, C64_THREADS, occA, split ? " + pair_wide32<load> + pair_tail16" : "", gridB, smemB, occB, N);
+    snprintf(buf, sizeof buf, "%stridiag_cta64%s%s grid=%u x %d thr %d CTA/SM%s + tql_small<64> grid=%u smem=%zuB %d CTA/SM; N=%d", build ? "" : "hk + ",
+             split ? "<split>" : "", build ? "<K0+K1 fused>" : "", gridA, C64_THREADS, occA, split ? " + pair_wide32<load> + pair_tail16" : "", gridB, smemB, occB, N);
     *info = buf;
     return launches;
 }
@@ -88,7 +104,7 @@ static int launch_vecql32_family(const Vec32Args& v, long long nm, double* zstor
 size_t vec64_bytes_per_k() { return (size_t)128 * 8 + (size_t)C64_VSTORE_CPLX * 16 + 4096 * 8 + 64 * 4 + (size_t)VECREC64_CAP * 16 + 64 * 8 + 16; }   // (d,e) | reflectors | Z | ranks | rotation list | d final | flag
 
 int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
-                 cudaStream_t st, std::string* info) {
+                 cudaStream_t st, std::string* info, const C64Build* build) {
     if (N <= 32 || N > 64 || !evecs) { *info = "launch_vec64: bad arguments"; return -1; }
     double* de = reinterpret_cast<double*>(scratch);
     cplx* vstore = reinterpret_cast<cplx*>(de + (size_t)nm * 128);
@@ -98,17 +114,21 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     int dev = 0, sms = 148, occA = 0, occQ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false>, C64_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occA, tridiag_cta64_kernel<false, false>, C64_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occQ, vecql64_kernel<0>, 32, smemQ);
     if (occA < 1 || occQ < 1) { *info = "vec64 kernels do not fit"; return -1; }
     static const bool split = !(getenv("SKTB_CTA64_SPLIT") && getenv("SKTB_CTA64_SPLIT")[0] == '0');
     cplx* blk32 = reinterpret_cast<cplx*>(zstore);          // the trailing blocks are consumed before Z is written
     C64Args a{H, N, nm, de, vstore, split ? blk32 : nullptr, 0, 0, 0, 0};
     const unsigned gridA = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occA));
+    void (*kA)(C64Args) = split ? (build ? tridiag_cta64_kernel<true, true> : tridiag_cta64_kernel<true, false>)
+                                : (build ? tridiag_cta64_kernel<false, true> : tridiag_cta64_kernel<false, false>);
+    const size_t smemA = build ? build->smem_bytes() : 0;
+    if (build && !c64_apply_build(a, build, kA, info)) return -1;
     if (split) {
         // steps 0..31 in the CTA kernel, the trailing 32 x 32 block (steps 32..62) in the one-warp-per-matrix kernel,
         // its reflectors into rows / columns 32.. of the same [64][64] store
-        tridiag_cta64_kernel<true><<<gridA, C64_THREADS, 0, st>>>(a);
+        kA<<<gridA, C64_THREADS, smemA, st>>>(a);
         SmallArgs w{};
         w.k = nullptr; w.mesh0 = w.mesh1 = w.mesh2 = 1; w.first = 0; w.nk = nm; w.N = N - 32; w.soc = 0;
         w.scratch = de; w.flags = nullptr; w.flag_off = 0; w.Hsrc = blk32; w.Hld = 32; w.out_stride = 128; w.d_off = 32; w.e_off = 96;
@@ -117,7 +137,7 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
         const unsigned gridW = (unsigned)std::max<long long>(1, std::min<long long>((nm + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 2));
         pair_wide32_kernel<PAIR_SRC_LOAD, 4, true, true><<<gridW, PAIR_WARPS * 32, smemW, st>>>(w, nullptr, vstore);
     } else {
-        tridiag_cta64_kernel<false><<<gridA, C64_THREADS, 0, st>>>(a);
+        kA<<<gridA, C64_THREADS, smemA, st>>>(a);
     }
     Vec64Args v{de, vstore, nm, N, evals, evecs, ld, col0, fail};
     const unsigned gridQ = (unsigned)std::max<long long>(1, std::min<long long>(nm, (long long)sms * occQ));
@@ -146,8 +166,8 @@ int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs,
     vecbt64_kernel<0><<<gridV, 128, smemV64, st>>>(v, zstore, rankstore);
     if (cudaGetLastError() != cudaSuccess) { *info = "launch failed"; return -1; }
     char buf[256];
-    snprintf(buf, sizeof buf, "tridiag_cta64<vec%s> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d",
-             split ? ",split + pair_wide32<load,full,vec>" : "", gridA, C64_THREADS, occA, gridQ, smemQ, occQ, gridV, N);
+    snprintf(buf, sizeof buf, "tridiag_cta64<vec%s%s> grid=%u x %d thr %d CTA/SM + vecql64 grid=%u smem=%zuB %d CTA/SM + vecbt64 grid=%u; N=%d",
+             split ? ",split + pair_wide32<load,full,vec>" : "", build ? ",K0+K1 fused" : "", gridA, C64_THREADS, occA, gridQ, smemQ, occQ, gridV, N);
     *info = buf;
     return 2 + nql + (split ? 1 : 0);
 }

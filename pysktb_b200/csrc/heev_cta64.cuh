@@ -113,14 +113,19 @@ SKTB_D void c64_step(cplx (&B)[2][16], PairCarry& c, const int j, const C64Lane&
     const cplx* Pl = S.P + base + L.h;
     const cplx* Vl = S.V + base + L.h;
     const cplx* Xl = S.X + base + L.h;
-    const double G = c64_wsum(c.g);
-    // ---- p-half of the update on the live window ----
+    // ---- p-half of the update on the live window, one butterfly stage of the w' reduction per slice of it (source
+    // order matters to ptxas: written first, the reduction's DADDs stall the in-order warp ahead of the DFMA stream) ----
+    constexpr int CH = (HALF + 5) / 6;
+    double G = c.g;
 #pragma unroll
     for (int m = 0; m < HALF; ++m) {
         const cplx pq = Pl[4 * m];
 #pragma unroll
         for (int s = 2 - NS; s < 2; ++s) pair_upd1(B[s][m], c.v[s], pq);
+        if ((m + 1) % CH == 0 && (m + 1) / CH <= 5) G += __shfl_xor_sync(0xffffffffu, G, 32 >> ((m + 1) / CH));
     }
+#pragma unroll
+    for (int st = HALF / CH + 1; st <= 5; ++st) G += __shfl_xor_sync(0xffffffffu, G, 32 >> st);
     const double coef = -c.tau2 * G;
     cplx wp[2], x[2];
 #pragma unroll
@@ -207,7 +212,56 @@ struct C64Args {
                             // (0 -> dense [N][N]); a peeled run passes the trailing block of a larger matrix in place
     int front = 0;          // 1: N < 64 is padded at the FRONT of the 64-wide frame (rows / columns < 64 - N are zero), so
                             // that the steps over the padding can be skipped: the run starts at step 8 * ((64 - N) / 8)
+    // BUILD mode (K0 + K1 fused: H(k) never exists in memory): H == NULL, the CTA assembles the lower triangle of the
+    // orbital-space h(k) in shared memory from the plan's bond tables and every thread picks its window entries from it
+    PlanView pv{};
+    const double* k = nullptr;      // [nm][3] fractional k-points, or NULL -> mesh points first.. of (mesh0, mesh1, mesh2)
+    int mesh0 = 1, mesh1 = 1, mesh2 = 1;
+    long long first = 0;
+    int soc = 0;
+    const cplx* Sdense = nullptr;   // soc: dense soc_mat [N][N] row-major (only the lower triangle is read)
 };
+
+// host-side description of a fused build (NULL -> the caller materialised H with K1)
+struct C64Build {
+    PlanView pv;
+    const double* k; const int32_t* mesh; long long first;
+    int soc;
+    const cplx* Sdense;
+    size_t smem_bytes() const { const size_t n = (size_t)pv.n_orb; return (n * (n + 1) / 2 + (size_t)pv.n_bonds) * sizeof(cplx); }
+};
+
+// K0 + K1 in the CTA: bond phases (calc_g arithmetic), then the packed lower triangle hs[mu (mu+1)/2 + nu], nu <= mu, of
+//   h_mu,nu(k) = sum_{bonds b of pair (atom(mu), atom(nu))} T_b[mu,nu] phase_b + delta onsite        (hamiltonian.py:98-103)
+// with the accumulation order of hk_kernel (pair-sorted bonds, image ascending) - the two paths agree bit for bit.
+SKTB_D void c64_build_h(const C64Args& a, const long long km, cplx* hs, cplx* phs) {
+    const PlanView& P = a.pv;
+    const int n = P.n_orb, t = threadIdx.x;
+    double k0, k1, k2;
+    if (a.k) { k0 = a.k[3 * km]; k1 = a.k[3 * km + 1]; k2 = a.k[3 * km + 2]; }
+    else kmesh_point(a.first + km, a.mesh0, a.mesh1, a.mesh2, k0, k1, k2);
+    for (int b = t; b < P.n_bonds; b += C64_THREADS) phs[b] = bond_phase(P.rec, k0, k1, k2, P.bond_vec + 3 * b);
+    __syncthreads();
+    for (int e = t; e < n * n; e += C64_THREADS) {
+        const int mu = e / n, nu = e - mu * n;
+        if (nu > mu) continue;
+        cplx v = cmake(0.0, 0.0);
+        const int ai = P.orb_atom[mu], aj = P.orb_atom[nu];
+        const int pr = P.pair_of[ai * P.n_atoms + aj];
+        if (pr >= 0) {
+            const int ni_off = mu - P.atom_start[ai], nj_off = nu - P.atom_start[aj];
+            const int nj = P.atom_start[aj + 1] - P.atom_start[aj];
+            for (int b = P.pair_begin[pr]; b < P.pair_begin[pr + 1]; ++b) {
+                const double tv = P.T[P.bond_off[b] + (long long)ni_off * nj + nj_off];
+                const cplx ph = phs[b];
+                v.x = fma(tv, ph.x, v.x); v.y = fma(tv, ph.y, v.y);
+            }
+        }
+        if (mu == nu) v.x += P.onsite[mu];
+        hs[mu * (mu + 1) / 2 + nu] = v;
+    }
+    __syncthreads();
+}
 
 // prologue (pivot column J0: class 0, register 0 of a window whose base is J0; registers beyond the live window and
 // X beyond row 63 are zero, so the loop runs over all 16 registers) + phases
@@ -240,9 +294,10 @@ SKTB_D void c64_run(cplx (&B)[2][16], PairCarry& c, const int J0, const C64Lane&
     c64_phases<16, SPLIT>(B, c, j, J0, L, S);
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool BUILD = false>
 __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a) {
     __shared__ __align__(16) cplx smem[C64_SMEM_CPLX];
+    extern __shared__ __align__(16) unsigned char c64_dyn[];       // BUILD: hs (packed lower triangle of h(k)) | bond phases
     const int t = threadIdx.x;
     C64Lane L;
     L.r = t & 31; L.h = t >> 5; L.iA = L.r; L.iB = 63 - L.r;
@@ -259,6 +314,37 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
         const cplx* H = a.H + (size_t)km * (a.mstride ? a.mstride : (long long)N * N) + a.hoff;
         if (a.vstore) { S.vst = a.vstore + (size_t)km * C64_VSTORE_CPLX; S.taust = S.vst + 4096; }
         cplx B[2][16];
+        if constexpr (BUILD) {
+            // H(k) = kron(h, I2) + soc_mat (soc) | h, read with zheevd(UPLO='L') semantics from the lower triangle in
+            // shared memory; the soc entries come from the dense table (L1 / L2 resident, shared by every k-point)
+            cplx* hs = reinterpret_cast<cplx*>(c64_dyn);
+            const int n = a.pv.n_orb;
+            c64_build_h(a, km, hs, hs + (size_t)n * (n + 1) / 2);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = (s ? L.iB : L.iA) - off;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int col = J0 + 4 * m + L.h - off;
+                    const bool ok = i >= 0 && col >= 0 && i < N && col < N;
+                    const int hi = ok ? max(i, col) : 0, lo = ok ? min(i, col) : 0;
+                    cplx e;
+                    if (a.soc) {
+                        const int mu = hi >> 1, nu = lo >> 1;
+                        e = hs[mu * (mu + 1) / 2 + nu];
+                        if ((hi ^ lo) & 1) e = cmake(0.0, 0.0);            // kron(h, I2): opposite spins do not couple
+                        const cplx sv = a.Sdense[(size_t)hi * N + lo];
+                        e = cmake(e.x + sv.x, e.y + sv.y);
+                    } else {
+                        e = hs[hi * (hi + 1) / 2 + lo];
+                    }
+                    if (col > i) e.y = -e.y;
+                    if (col == i) e.y = 0.0;
+                    if (!ok) e = cmake(0.0, 0.0);
+                    B[s][m] = e;
+                }
+            }
+        } else {
         // branch-free: the address of the lower-triangle element is clamped, all 32 loads are independent and in flight
         // together; conjugation / real diagonal / zero padding are applied to the loaded value
 #pragma unroll
@@ -275,6 +361,7 @@ __global__ void __launch_bounds__(C64_THREADS, 2) tridiag_cta64_kernel(C64Args a
                 if (!ok) e = cmake(0.0, 0.0);
                 B[s][m] = e;
             }
+        }
         }
         PairCarry c;
         c.eval = 0.0;

@@ -42,6 +42,7 @@ struct SmallTables {
     const double* onsite = nullptr; // [n]
     const cplx* St = nullptr;       // [2n][2n]     mirrored-lower soc_mat, St[k*2n + i]
     const double* SAt = nullptr;    // [2n][2n]     Re S[i][k] - Re S[k][i], SAt[k*2n + i]
+    const int* thread_order = nullptr;   // [2][nb] slot order + conj flags of the one-matrix-per-thread kernel (heev_thread.cuh)
     double rec[9];
     double asym_bound = 0.0;
     int soc_any = 0;
@@ -712,6 +713,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_merge_kernel(const doubl
 }
 
 #include "heev_pair.cuh"
+#include "heev_thread.cuh"
 #include "heev_cta64.cuh"
 #include "heev_vec32.cuh"
 #include "heev_vec64.cuh"
@@ -767,8 +769,10 @@ static bool build_tables(const sktb_model_desc* D, const std::vector<double>& T,
     std::vector<double> bvec(D->bond_vec, D->bond_vec + (size_t)3 * nb), ons(D->onsite, D->onsite + n);
     out->n_orb = n; out->n_bonds = nb; out->soc_any = D->soc_nnz > 0;
     for (int c = 0; c < 9; ++c) out->rec[c] = D->rec_lattice[c];
+    std::vector<int> order;
+    thread_bond_order(bvec.data(), nb, &order);
     if (!up(Lt, &out->Lt, owned) || !up(Dt, &out->Dt, owned) || !up(bvec, &out->bvec, owned) || !up(ons, &out->onsite, owned) ||
-        !up(St, &out->St, owned) || !up(SAt, &out->SAt, owned)) { *why = "cudaMalloc failed"; return false; }
+        !up(St, &out->St, owned) || !up(SAt, &out->SAt, owned) || !up(order, &out->thread_order, owned)) { *why = "cudaMalloc failed"; return false; }
     return true;
 }
 
@@ -966,8 +970,10 @@ inline int padded_nc(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 12 ? 12 : 
 // 32 < N <= 64, eigenvalues only: H (K1 output, [nm][N][N]) -> tridiag_cta64_kernel -> tql_small_kernel<64>.
 // scratch: >= nm * cta64_bytes_per_k() bytes.  Returns the number of kernels launched or -1 (text in *info).
 size_t cta64_bytes_per_k();
+struct C64Build;    // heev_cta64.cuh: non-NULL -> K0 + K1 fused into tridiag_cta64 (H is ignored and may be NULL)
 int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* evals, long long ld, long long col0, int* fail, cudaStream_t st,
-                 std::string* info, int h_ld = 0, long long h_mstride = 0, long long h_off = 0, bool tridiag_only = false);
+                 std::string* info, int h_ld = 0, long long h_mstride = 0, long long h_off = 0, bool tridiag_only = false,
+                 const C64Build* build = nullptr);
 
 // N <= 32 with eigenvectors (no gate): pair-layout tridiagonalisation keeping the reflectors -> vec32_kernel
 // (QL with accumulation, sort, back-transformation).  evecs: [N][ld][N] complex (reference layout [band, k, comp]).
@@ -976,7 +982,7 @@ int launch_cta64(const cplx* H, int N, long long nm, double* scratch, double* ev
 // reflectors -> vecql64 -> vecbt64.  scratch: >= nm * vec64_bytes_per_k() bytes.  evecs [N][ld][N].
 size_t vec64_bytes_per_k();
 int launch_vec64(const cplx* H, int N, long long nm, double* evals, cplx* evecs, long long ld, long long col0, int* fail, void* scratch,
-                 cudaStream_t st, std::string* info);
+                 cudaStream_t st, std::string* info, const C64Build* build = nullptr);
 
 // sktb_heev for N <= 32: caller-supplied matrices H [nm][N][N] (lower triangle read, input not modified) through the
 // pair kernels in LOAD mode; evecs may be NULL.  scratch: >= nm * vec32_bytes_per_k() bytes.

@@ -86,6 +86,33 @@ static int launch_n2(const LaunchCtx& c) {
     return 1;
 }
 
+// N <= 8 without the gate: one matrix per thread (heev_thread.cuh).  SKTB_NO_THREAD=1: lane-group kernels (A/B, parity tests).
+template <int NC, bool SOC>
+static int launch_thread_t(const LaunchCtx& c) {
+    const size_t smem = thread_smem_bytes(NC, SOC, c.a.t.n_bonds);
+    auto kern = solve_thread_kernel<NC, SOC>;
+    if (smem > 160 * 1024) return -2;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    int dev = 0, sms = 148, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREAD_CTA, smem);
+    if (occ < 1) return -2;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((c.a.nk + THREAD_CTA - 1) / THREAD_CTA, (long long)sms * occ));
+    kern<<<grid, THREAD_CTA, smem, c.st>>>(c.a, c.evals, c.ld, c.col0, c.fail);
+    if (cudaGetLastError() != cudaSuccess) { *c.info = "launch failed"; return -1; }
+    char buf[200];
+    snprintf(buf, sizeof buf, "solve_thread<NC=%d,soc=%d> (one matrix per thread, K0+K1+K2 fused) grid=%u x %d thr smem=%zuB %d CTA/SM; N=%d", NC, (int)SOC, grid,
+             THREAD_CTA, smem, occ, c.a.N);
+    *c.info = buf;
+    return 1;
+}
+static int launch_thread(const LaunchCtx& c) {
+    const int N = c.a.N;
+    if (c.a.soc) return N <= 4 ? launch_thread_t<4, true>(c) : launch_thread_t<8, true>(c);
+    return N <= 4 ? launch_thread_t<4, false>(c) : launch_thread_t<8, false>(c);
+}
+
 int launch_solve(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N,
                  double* evals, long long ld, long long col0, int* flags, long long flag_off, int* fail, double* scratch, size_t scratch_bytes,
                  cudaStream_t st, std::string* info) {
@@ -101,6 +128,10 @@ int launch_solve(const SmallTables& tab, const double* k_d, const int32_t* nk_me
     if (N == 2 && !gate) {
         static const bool no_n2 = getenv("SKTB_NO_N2") != nullptr && getenv("SKTB_NO_N2")[0] == '1';
         if (!no_n2) { int rc = launch_n2(c); if (rc != -2) return rc; }
+    }
+    if (N <= 8 && !gate && tab.thread_order) {
+        static const bool no_thread = getenv("SKTB_NO_THREAD") != nullptr && getenv("SKTB_NO_THREAD")[0] == '1';
+        if (!no_thread) { int rc = launch_thread(c); if (rc != -2) return rc; }
     }
     switch (padded_nc(N)) {
         case 4: return launch_nc_4(c, gate);

@@ -6,20 +6,6 @@
 
 namespace sktb {
 
-// Device view of the k-independent model tables (see sktb_model_desc in include/sktb.h).
-struct PlanView {
-    int n_atoms, n_orb, n_bonds, n_pairs, soc_nnz;
-    const int* atom_start;    // [n_atoms+1]
-    const int* orb_atom;      // [n_orb]
-    const int* pair_of;       // [n_atoms*n_atoms] -> pair id or -1
-    const int* pair_begin;    // [n_pairs+1] range into the pair-sorted bond arrays
-    const double* bond_vec;   // [n_bonds][3]  (pair-sorted, image ascending inside a pair)
-    const long long* bond_off;  // [n_bonds] offset of the bond's [n_i][n_j] block in T
-    const double* T;          // packed hopping blocks
-    const double* onsite;     // [n_orb]
-    const int* soc_row; const int* soc_col; const cplx* soc_val;
-    double rec[9];            // inv(lattice).T row-major
-};
 
 // ---------------------------------------------------------------------------------------------------------
 // K0: GreensFunction._generate_kmesh (greens.py:100-111), bit-exact.
@@ -32,18 +18,6 @@ __global__ void kmesh_kernel(int n0, int n1, int n2, long long first, long long 
     }
 }
 
-// phase of one bond at fractional k: exp(2 pi i (k @ rec) . d), same operation order as calc_g
-// (hamiltonian.py:280, :311): kc = k@rec ; arg = (2*pi) * dot(kc, d).
-SKTB_D cplx bond_phase(const double* rec, double k0, double k1, double k2, const double* d) {
-    double c0 = __dadd_rn(__dadd_rn(__dmul_rn(k0, rec[0]), __dmul_rn(k1, rec[3])), __dmul_rn(k2, rec[6]));
-    double c1 = __dadd_rn(__dadd_rn(__dmul_rn(k0, rec[1]), __dmul_rn(k1, rec[4])), __dmul_rn(k2, rec[7]));
-    double c2 = __dadd_rn(__dadd_rn(__dmul_rn(k0, rec[2]), __dmul_rn(k1, rec[5])), __dmul_rn(k2, rec[8]));
-    double dot = __dadd_rn(__dadd_rn(__dmul_rn(c0, d[0]), __dmul_rn(c1, d[1])), __dmul_rn(c2, d[2]));
-    double arg = __dmul_rn(6.283185307179586, dot);
-    cplx ph;
-    sincos(arg, &ph.y, &ph.x);
-    return ph;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // K1 (materialising): one CTA per k-point.  H [nk][N][N] row-major complex128.
@@ -137,6 +111,9 @@ struct HeevArgs {
     int peel; double* peel_de;   // phase 3: run only the first `peel` steps (a multiple of NB) of the panel formulation, leave the
                         // updated trailing (N - peel)^2 block in H and write d, e of the peeled steps to peel_de[mat][2][peel]
     int phase;          // 0: whole solve; 1: tridiagonalise and park (d, e) in H; 2: QL + output from the parked (d, e)
+    cplx* vstore;       // non-NULL: keep the reflectors, vstore[mat][j][i] = v_j[i] (zero for i <= j), taustore[mat][j], and the
+    cplx* taustore;     //           tridiagonal de_out[mat][2][N] for the inverse-iteration eigenvector path (kernels_big_vec.cuh)
+    double* de_out;
 };
 
 // trailing update of one panel: M0[k][i] -= sum_s conj(V[i][s]) W[k][s] + conj(W[i][s]) V[k][s], column i, rows
@@ -292,6 +269,10 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                     if (tid == 0) e[j] = beta;
                     const cplx vi = (i == j + 1) ? cmake(1.0, 0.0) : ((mine && i > j + 1) ? cmul(x, scale) : cmake(0.0, 0.0));
                     if (mine) { v[i] = vi; Vs[t * N + i] = vi; }
+                    if (a.vstore) {
+                        if (mine) a.vstore[((size_t)mat * N + j) * N + i] = vi;
+                        if (tid == 0) a.taustore[(size_t)mat * N + j] = tau;
+                    }
                     __syncthreads();
                     // (2) y0_i = sum_{k > j} conj(M0[k][i]) v_k: read-only stream
                     cplx acc = cmake(0.0, 0.0);
@@ -390,6 +371,10 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                 if (i == 0) e[0] = beta;
                 vi = (i == 1) ? cmake(1.0, 0.0) : ((mine && i > 1) ? cmul(x, scale) : cmake(0.0, 0.0));
                 if (mine) v[i] = vi;
+                if (a.vstore) {
+                    if (mine) a.vstore[(size_t)mat * N * N + i] = vi;
+                    if (tid == 0) a.taustore[(size_t)mat * N] = tau;
+                }
                 __syncthreads();
                 cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
                 if (mine && i >= 1) {
@@ -439,6 +424,10 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                 if (i == 0) e[j + 1] = beta;
                 cplx v2i = (i == j + 2) ? cmake(1.0, 0.0) : ((mine && i > j + 2) ? cmul(x, scale) : cmake(0.0, 0.0));
                 if (mine) v2[i] = v2i;
+                if (a.vstore) {
+                    if (mine) a.vstore[((size_t)mat * N + j + 1) * N + i] = v2i;
+                    if (tid == 0) a.taustore[(size_t)mat * N + j + 1] = tau2;
+                }
                 __syncthreads();
                 // (2) rows k >= j+2: update and accumulate the next mat-vec in the same pass
                 cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
@@ -531,6 +520,11 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             __syncthreads();
             continue;
         }
+        }
+
+        if (a.de_out && a.phase != 2) {
+            double* deo = a.de_out + (size_t)mat * 2 * N;
+            for (int idx = tid; idx < N; idx += T) { deo[idx] = d[idx]; deo[N + idx] = e[idx]; }
         }
 
         // ---- tridiagonal QL ----

@@ -91,6 +91,7 @@ struct sktb_plan {
     std::vector<double> T_host_creation_order;  // hopping blocks in the caller's bond order
     std::vector<int> bond_ni, bond_nj;
     double asym_bound = 0.0;
+    const cplx* soc_dense = nullptr;          // [2n][2n] dense soc_mat (32 < 2n <= 64: fused build of tridiag_cta64)
     small::SmallTables small_tab{};           // dense tables for the register-resident path
     bool small_ok = false;
     struct WorkSet { Buf H, RT, K, S; };
@@ -235,25 +236,32 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
 
     // ---- Hermiticity-gate bound -------------------------------------------------------------------------
     // Re(H - H^dagger)[mu,nu] = sum_{b in pair(i,j)} (T_b[mu,nu] - T_rev(b)[nu,mu]) cos(phi_b), rev(b) = the bond
-    // (j,i,-d).  For i == j the bonds b and rev(b) sit in the same pair with equal cos(phi) and are combined
-    // before taking magnitudes (this is what makes odd-parity blocks such as s-p or p-f cancel exactly).
+    // (j,i,-d).  A bond b = (i,j,d) and its inversion partner inv(b) = (i,j,-d) of the SAME pair (present for every
+    // centrosymmetric neighbour shell: simple cubic, bcc-like two-atom cells, ...) carry equal cos(phi) and are combined
+    // before taking magnitudes - this is what makes odd-parity blocks such as s-p or p-f cancel exactly.
     {
         std::map<std::tuple<int, int, long long, long long, long long>, int> by_vec;
         auto key = [&](int i, int j, const double* v, double sgn) {
             return std::make_tuple(i, j, llround(sgn * v[0] * 1e7), llround(sgn * v[1] * 1e7), llround(sgn * v[2] * 1e7));
         };
         for (int b = 0; b < nb; ++b) by_vec[key(D->bond_i[b], D->bond_j[b], D->bond_vec + 3 * b, 1.0)] = b;
+        auto find = [&](int i, int j, const double* v, double sgn) {
+            auto it = by_vec.find(key(i, j, v, sgn));
+            return it == by_vec.end() ? -1 : it->second;
+        };
         auto Tb = [&](int b, int r, int c) { return b < 0 ? 0.0 : p->T_host_creation_order[off_creation[b] + (long long)r * p->bond_nj[b] + c]; };
         std::vector<double> acc((size_t)n * n, 0.0);
         for (int b = 0; b < nb; ++b) {
-            int i = D->bond_i[b], j = D->bond_j[b];
-            auto it = by_vec.find(key(j, i, D->bond_vec + 3 * b, -1.0));
-            int rb = it == by_vec.end() ? -1 : it->second;
-            if (i == j && rb >= 0 && rb < b) continue;          // handled together with its partner
+            const int i = D->bond_i[b], j = D->bond_j[b];
+            const double* d = D->bond_vec + 3 * b;
+            const int ib = find(i, j, d, -1.0);                 // inversion partner in the same pair (may be b itself for d = 0)
+            if (ib >= 0 && ib < b) continue;                    // handled together with its partner
+            const int rb = find(j, i, d, -1.0);                 // reverse of b
+            const int rib = (ib >= 0 && ib != b) ? find(j, i, d, 1.0) : -1;     // reverse of inv(b)
             for (int r = 0; r < p->bond_ni[b]; ++r)
                 for (int c = 0; c < p->bond_nj[b]; ++c) {
                     double v = Tb(b, r, c) - Tb(rb, c, r);
-                    if (i == j && rb >= 0 && rb != b) v += Tb(rb, r, c) - Tb(b, c, r);
+                    if (ib >= 0 && ib != b) v += Tb(ib, r, c) - Tb(rib, c, r);
                     acc[(size_t)(D->atom_orb_start[i] + r) * n + D->atom_orb_start[j] + c] += fabs(v);
                 }
         }
@@ -289,6 +297,12 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
     rc |= upload(p, sval.data(), sval.size(), &V.soc_val);
     if (rc) return bail(1);
     for (int c = 0; c < 9; ++c) V.rec[c] = D->rec_lattice[c];
+
+    if (2 * n > 32 && 2 * n <= 64) {          // dense soc_mat for the fused K1 of the CTA-resident 33..64 kernel
+        std::vector<cplx> dense((size_t)4 * n * n, cmake(0.0, 0.0));
+        for (int t = 0; t < D->soc_nnz; ++t) dense[(size_t)D->soc_row[t] * 2 * n + D->soc_col[t]] = sval[t];
+        if (upload(p, dense.data(), dense.size(), &p->soc_dense)) return bail(1);
+    }
 
     // ---- dense tables for the register-resident path (N <= 32) -----------------------------------------
     {
@@ -448,6 +462,19 @@ static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
 
 static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked workspaces
 
+// 32 < N <= 64: K0 + K1 fused into tridiag_cta64 (H(k) is assembled in shared memory / registers, never in HBM) whenever the
+// per-k Hermiticity flags are not needed.  SKTB_CTA64_FUSE=0: materialise H with hk_kernel as before (A/B, parity tests).
+static bool c64_fusable(const sktb_plan* p, int N, int soc, bool need_flags) {
+    static const bool off = getenv("SKTB_CTA64_FUSE") && getenv("SKTB_CTA64_FUSE")[0] == '0';
+    if (off || N <= 32 || N > 64 || need_flags) return false;
+    if (soc && !p->soc_dense) return false;
+    const size_t n = (size_t)p->n_orb;
+    return (n * (n + 1) / 2 + (size_t)p->n_bonds) * sizeof(cplx) <= 96 * 1024;
+}
+static small::C64Build c64_build(const sktb_plan* p, const double* k, const int32_t* mesh, long long first, int soc) {
+    return small::C64Build{p->view, k, mesh, first, soc, soc ? p->soc_dense : nullptr};
+}
+
 // (d,e) scratch of the register-resident path: 2*NC doubles per k-point, at most 2M k-points per launch pair.
 // The pair-layout pipeline (24 < N <= 32) keeps two chunks in flight and parks a 4 KB trailing block per k-point.
 static size_t small_scratch_bytes(int N, long long nk) {
@@ -515,31 +542,48 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
         // K1 -> tridiag_cta64 keeping the reflectors -> vecql64 -> vecbt64
         const size_t perH = (size_t)N * N * sizeof(cplx), per_k = perH + small::vec64_bytes_per_k() + 24;
         long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
-        if (W.H.ensure(perH * chunk) || W.RT.ensure(small::vec64_bytes_per_k() * chunk)) return fail("out of device memory (vec64 workspaces)");
+        if ((!c64_fusable(p, N, soc, flags_d && p->asym_bound > 0.5e-9) && W.H.ensure(perH * chunk)) || W.RT.ensure(small::vec64_bytes_per_k() * chunk))
+            return fail("out of device memory (vec64 workspaces)");
         if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
+        const bool fuse = c64_fusable(p, N, soc, flags_d && p->asym_bound > 0.5e-9);
         for (long long c0 = 0; c0 < nk; c0 += chunk) {
             long long cnt = std::min(chunk, nk - c0);
-            const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
-            if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
-            int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
-            if (rc) return rc;
-            rc = small::launch_vec64((const cplx*)W.H.p, N, cnt, evals_d, (cplx*)evecs_d, ld, k_off + c0, p->d_fail, W.RT.p, st, &g_kinfo);
+            int rc;
+            if (fuse) {
+                if (flags_d) CK(cudaMemsetAsync(flags_d + k_off + c0, 0, (size_t)cnt * sizeof(int), st));
+                const small::C64Build b = c64_build(p, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, first + c0, soc);
+                rc = small::launch_vec64(nullptr, N, cnt, evals_d, (cplx*)evecs_d, ld, k_off + c0, p->d_fail, W.RT.p, st, &g_kinfo, &b);
+            } else {
+                const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
+                if (!k_d) { rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
+                rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
+                if (rc) return rc;
+                rc = small::launch_vec64((const cplx*)W.H.p, N, cnt, evals_d, (cplx*)evecs_d, ld, k_off + c0, p->d_fail, W.RT.p, st, &g_kinfo);
+            }
             if (rc < 0) return fail("vec64 launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
         }
     } else if (!want_vecs && N > 32 && N <= 64) {
         // K1 materialises H(k) (64 KB per k at N = 64), tridiag_cta64_kernel keeps it in registers, QL per lane
-        size_t perH = (size_t)N * N * sizeof(cplx);
-        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));
-        if (W.H.ensure(perH * chunk) || W.S.ensure((size_t)chunk * small::cta64_bytes_per_k())) return fail("out of device memory (H workspace %zu B)", perH * chunk);
-        if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
+        const bool fuse = c64_fusable(p, N, soc, flags_d && p->asym_bound > 0.5e-9);
+        size_t perH = fuse ? 0 : (size_t)N * N * sizeof(cplx);
+        long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / (perH + small::cta64_bytes_per_k()))));
+        if ((!fuse && W.H.ensure(perH * chunk)) || W.S.ensure((size_t)chunk * small::cta64_bytes_per_k())) return fail("out of device memory (H workspace %zu B)", perH * chunk);
+        if (!fuse && !k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
         for (long long c0 = 0; c0 < nk; c0 += chunk) {
             long long cnt = std::min(chunk, nk - c0);
-            const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
-            if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
-            int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
-            if (rc) return rc;
-            rc = small::launch_cta64((const cplx*)W.H.p, N, cnt, (double*)W.S.p, evals_d, ld, k_off + c0, p->d_fail, st, &g_kinfo);
+            int rc;
+            if (fuse) {
+                if (flags_d) CK(cudaMemsetAsync(flags_d + k_off + c0, 0, (size_t)cnt * sizeof(int), st));
+                const small::C64Build b = c64_build(p, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, first + c0, soc);
+                rc = small::launch_cta64(nullptr, N, cnt, (double*)W.S.p, evals_d, ld, k_off + c0, p->d_fail, st, &g_kinfo, 0, 0, 0, false, &b);
+            } else {
+                const double* kk = k_d ? k_d + 3 * c0 : (const double*)W.K.p;
+                if (!k_d) { rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
+                rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
+                if (rc) return rc;
+                rc = small::launch_cta64((const cplx*)W.H.p, N, cnt, (double*)W.S.p, evals_d, ld, k_off + c0, p->d_fail, st, &g_kinfo);
+            }
             if (rc < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
         }
@@ -810,11 +854,12 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     }
     const bool use_small = n_rows == 0 && p->small_ok && small::supports(N);
     const bool use_cta64 = n_rows == 0 && !use_small && N > 32 && N <= 64;     // eigenvalues only, register-resident CTA kernel
-    size_t per_k = (size_t)N * 8 + ((use_small || use_vec32) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? 1024 : 0) +
+    const bool dos_fused = (use_vec64 || use_cta64) && c64_fusable(p, N, soc, gate);
+    size_t per_k = (size_t)N * 8 + ((use_small || use_vec32 || dos_fused) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? small::cta64_bytes_per_k() : 0) +
                    (use_vec32 ? small::vec32_bytes_per_k() : 0) + (use_vec64 ? small::vec64_bytes_per_k() : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(WS_BUDGET / per_k)));
     const int LOR_GRID = 148 * 4;
-    if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
+    if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && !dos_fused && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k()
                                                  : (use_vec64 ? (size_t)chunk * small::vec64_bytes_per_k() : (size_t)chunk * N * n_rows * 16)) ||
                     p->wsVec.ensure((size_t)chunk * N * n_rows * 16))) ||
@@ -837,6 +882,16 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                                          flags, 0, p->d_fail, (double*)p->ws[2].S.p, sbytes, st, &g_kinfo);
             if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
+        } else if ((use_vec64 || use_cta64) && c64_fusable(p, N, soc, gate)) {
+            const small::C64Build b = c64_build(p, k_d ? k_d + 3 * c0 : nullptr, nk_mesh, k_first + c0, soc);
+            int rl;
+            if (use_vec64) rl = small::launch_vec64(nullptr, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo, &b);
+            else {
+                if (p->ws[2].S.ensure((size_t)cnt * small::cta64_bytes_per_k())) return fail("out of device memory (tridiagonal scratch)");
+                rl = small::launch_cta64(nullptr, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo, 0, 0, 0, false, &b);
+            }
+            if (rl < 0) return fail("fused cta64 launch failed: %s", g_kinfo.c_str());
+            g_launches += rl;
         } else {
             const double* kk = k_d ? k_d + 3 * c0 : (const double*)p->ws[2].K.p;
             if (!k_d) { int rc = sktb_kmesh(nk_mesh, k_first + c0, cnt, (double*)p->ws[2].K.p, st); if (rc) return rc; }
@@ -939,6 +994,16 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
             }
             if (rc < 0) return fail("small-path launch failed: %s", g_kinfo.c_str());
             g_launches += rc;
+        } else if (mid_path && c64_fusable(p, N, soc, gate)) {
+            const small::C64Build b = c64_build(p, k_d + 3 * c0, nullptr, 0, soc);
+            int rl;
+            if (nr) rl = small::launch_vec64(nullptr, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo, &b);
+            else {
+                if (p->ws[2].S.ensure((size_t)cnt * small::cta64_bytes_per_k())) return fail("out of device memory (tridiagonal scratch)");
+                rl = small::launch_cta64(nullptr, N, cnt, (double*)p->ws[2].S.p, (double*)p->wsE.p, cnt, 0, p->d_fail, st, &g_kinfo, 0, 0, 0, false, &b);
+            }
+            if (rl < 0) return fail("fused mid-path launch failed: %s", g_kinfo.c_str());
+            g_launches += rl;
         } else {
             int rc = launch_hk(p, k_d + 3 * c0, cnt, soc, (cplx*)p->ws[2].H.p, flags, 0, st);
             if (rc) return rc;

@@ -72,3 +72,73 @@ def test_alternative_kernel_paths(knob):
     env[k] = v
     r = subprocess.run([sys.executable, "-c", CHECK % (ROOT, repr(CASES[knob]))], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+FUSE_CHECK = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pysktb_b200 as tb
+from pysktb_b200 import workloads as W
+out = {}
+for name, spec in (("C4", W.ce_spdf_2atom()), ("zz20", W.zigzag_ribbon(n_chains=20)), ("zz31", W.zigzag_ribbon(n_chains=31))):
+    _, ham = W.instantiate(spec, tb, tb.scaling)
+    k = np.random.default_rng(5).random((37, 3))
+    out[name] = ham.solve_kpath(list(k), soc=spec["soc"])
+    v, U = ham.solve_kpath(list(k[:5]), soc=spec["soc"], eig_vectors=True)
+    out[name + "_v"] = v
+    out[name + "_w"] = np.abs(U) ** 2
+    out[name + "_info"] = np.array(ham.last_kernel_info())
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_fused_hk_equals_materialised_hk(tmp_path):
+    """32 < N <= 64: K0 + K1 fused into tridiag_cta64 (default) against the hk_kernel -> workspace -> tridiag_cta64 path
+    (SKTB_CTA64_FUSE=0): same bond order and arithmetic, so eigenvalues are bit-identical."""
+    import numpy as np
+    res = {}
+    for fuse in ("1", "0"):
+        env = dict(os.environ, SKTB_CTA64_FUSE=fuse)
+        f = str(tmp_path / f"fuse{fuse}.npz")
+        r = subprocess.run([sys.executable, "-c", FUSE_CHECK % ROOT, f], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[fuse] = np.load(f)
+    assert "fused" in str(res["1"]["C4_info"]) and "fused" not in str(res["0"]["C4_info"]), (str(res["1"]["C4_info"]), str(res["0"]["C4_info"]))
+    for key in ("C4", "zz20", "zz31", "C4_v", "zz20_v", "zz31_v"):
+        assert np.array_equal(res["1"][key], res["0"][key]), key
+    for key in ("C4_w", "zz20_w", "zz31_w"):
+        np.testing.assert_allclose(res["1"][key], res["0"][key], rtol=0, atol=1e-12)
+
+
+THREAD_CHECK = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pysktb_b200 as tb
+from pysktb_b200 import workloads as W
+out = {}
+for name, spec in (("C1", W.cubic_sp3()), ("spchain", W.sp_chain()), ("cubic_s", W.cubic_s())):
+    _, ham = W.instantiate(spec, tb, tb.scaling)
+    k = np.random.default_rng(11).random((1001, 3)) * 2 - 0.5
+    out[name] = ham.solve_kpath(list(k), soc=spec["soc"])
+    out[name + "_nosoc"] = ham.solve_kpath(list(k[:77]), soc=False)
+    out[name + "_mesh"] = ham.solve_kmesh([7, 5, 3], soc=spec["soc"]).cpu().numpy()
+    out[name + "_info"] = np.array(ham.last_kernel_info())
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_thread_per_matrix_equals_lane_group_kernels(tmp_path):
+    """N <= 8: the one-matrix-per-thread kernel (default) against the lane-group kernels (SKTB_NO_THREAD=1): same
+    eigenvalues to 1e-12 (different summation order of the bond phases, sincospi instead of sincos(2 pi x))."""
+    import numpy as np
+    res = {}
+    for knob in ("0", "1"):
+        env = dict(os.environ, SKTB_NO_THREAD=knob)
+        f = str(tmp_path / f"thread{knob}.npz")
+        r = subprocess.run([sys.executable, "-c", THREAD_CHECK % ROOT, f], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[knob] = np.load(f)
+    assert "solve_thread" in str(res["0"]["C1_info"]) and "solve_thread" not in str(res["1"]["C1_info"]), (str(res["0"]["C1_info"]), str(res["1"]["C1_info"]))
+    for key in res["0"].files:
+        if not key.endswith("_info"):
+            np.testing.assert_allclose(res["0"][key], res["1"][key], rtol=0, atol=1e-12, err_msg=key)
