@@ -66,6 +66,12 @@ int sktb_plan_asym_bound(const sktb_plan* plan, double* bound);
 /* K4: get_hop_int for nb bonds (_params.py:36-513). V_d [nb][25], lmn_d [nb][3], out_d [nb][17][17].         */
 int sktb_sk_table(const double* V_d, const double* lmn_d, double* out_d, int32_t nb, void* stream);
 
+/* K4 with its Cartesian gradient, for Hellmann-Feynman forces (Forces.get_forces, forces.py:43-72; replaces the reference's
+ * _compute_dH_pair, forces.py:242-318, which differentiates get_hop_int numerically with eps = 1e-6): forward-mode
+ * differentiation of the same table code.  V_d [nb][25] values and dV_d [nb][25] derivatives dV/dd at the bond length,
+ * vec_d [nb][3] Cartesian bond vectors; out_d [nb][4][17][17]: table | d/dx | d/dy | d/dz.  Synchronous.                  */
+int sktb_sk_table_grad(const double* V_d, const double* dV_d, const double* vec_d, double* out_d, int32_t nb, void* stream);
+
 /* K0: GreensFunction._generate_kmesh (greens.py:100-111): flat index i*n1*n2 + j*n2 + l ->
  * (i/max(n0,1), j/max(n1,1), l/max(n2,1)), IEEE division (bit-exact). k_out_d [count][3].                    */
 int sktb_kmesh(const int32_t nk[3], int64_t first, int64_t count, double* k_out_d, void* stream);

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "sktb_plan_hoppings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "sktb_plan_asym_bound": (C.c_int, [C.c_void_p, c_f64p]),
     "sktb_sk_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "sktb_sk_table_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sktb_kmesh": (C.c_int, [c_i32p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "sktb_hk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sktb_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,

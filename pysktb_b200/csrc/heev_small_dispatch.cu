@@ -89,28 +89,52 @@ static int launch_n2(const LaunchCtx& c) {
 // N <= 8 without the gate: one matrix per thread (heev_thread.cuh).  SKTB_NO_THREAD=1: lane-group kernels (A/B, parity tests).
 template <int NC, bool SOC>
 static int launch_thread_t(const LaunchCtx& c) {
-    const size_t smem = thread_smem_bytes(NC, SOC, c.a.t.n_bonds);
-    auto kern = solve_thread_kernel<NC, SOC>;
+    // SKTB_THREAD_SPLIT=0: one fused kernel (tridiagonalisation + QL + sort in the same thread)
+    static const bool split = !(getenv("SKTB_THREAD_SPLIT") && getenv("SKTB_THREAD_SPLIT")[0] == '0');
+    constexpr int P2 = NC <= 4 ? 4 : (NC <= 8 ? 8 : 16);
+    const size_t smem = thread_smem_bytes(NC, SOC, c.a.t.n_bonds, split);
+    void (*kern)(SmallArgs, double*, long long, long long, int*) = split ? solve_thread_kernel<NC, SOC, true> : solve_thread_kernel<NC, SOC, false>;
+    void (*kB)(TqlArgs) = tql_small_kernel<NC, P2, 2>;
+    const size_t smemB = (size_t)SMALL_WARPS * 2 * NC * DSTRIDE * 8;
     if (smem > 160 * 1024) return -2;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-    int dev = 0, sms = 148, occ = 0;
+    int dev = 0, sms = 148, occ = 0, occB = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREAD_CTA, smem);
-    if (occ < 1) return -2;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((c.a.nk + THREAD_CTA - 1) / THREAD_CTA, (long long)sms * occ));
-    kern<<<grid, THREAD_CTA, smem, c.st>>>(c.a, c.evals, c.ld, c.col0, c.fail);
-    if (cudaGetLastError() != cudaSuccess) { *c.info = "launch failed"; return -1; }
-    char buf[200];
-    snprintf(buf, sizeof buf, "solve_thread<NC=%d,soc=%d> (one matrix per thread, K0+K1+K2 fused) grid=%u x %d thr smem=%zuB %d CTA/SM; N=%d", NC, (int)SOC, grid,
-             THREAD_CTA, smem, occ, c.a.N);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occB, kB, SMALL_WARPS * 32, smemB);
+    if (occ < 1 || occB < 1) return -2;
+    const long long per_k = 2LL * NC * 8;
+    const long long chunk = split ? std::max<long long>(32, std::min<long long>(c.a.nk, (long long)(c.scratch_bytes / per_k) / 32 * 32)) : c.a.nk;
+    int launches = 0;
+    unsigned grid = 0, gridB = 0;
+    for (long long c0 = 0; c0 < c.a.nk; c0 += chunk) {
+        const long long cnt = std::min(chunk, c.a.nk - c0);
+        SmallArgs a = c.a;
+        a.k = c.a.k ? c.a.k + 3 * c0 : nullptr;
+        a.first = c.a.first + c0; a.nk = cnt; a.scratch = c.scratch;
+        a.flag_off = c.a.flag_off + c0;
+        grid = (unsigned)std::max<long long>(1, std::min<long long>((cnt + THREAD_CTA - 1) / THREAD_CTA, (long long)sms * occ));
+        kern<<<grid, THREAD_CTA, smem, c.st>>>(a, c.evals, c.ld, c.col0 + c0, c.fail);
+        ++launches;
+        if (split) {
+            TqlArgs t{c.scratch, cnt, c.a.N, c.evals, c.ld, c.col0 + c0, c.fail};
+            gridB = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * occB));
+            kB<<<gridB, SMALL_WARPS * 32, smemB, c.st>>>(t);
+            ++launches;
+        }
+        if (cudaGetLastError() != cudaSuccess) { *c.info = "launch failed"; return -1; }
+    }
+    char buf[260];
+    snprintf(buf, sizeof buf, "solve_thread<NC=%d,soc=%d%s> (one matrix per thread, K0+K1+K2a fused) grid=%u x %d thr smem=%zuB %d CTA/SM%s; N=%d", NC, (int)SOC,
+             split ? ",split" : "", grid, THREAD_CTA, smem, occ, split ? " + tql_small (per-lane QL)" : "", c.a.N);
     *c.info = buf;
-    return 1;
+    return launches;
 }
 static int launch_thread(const LaunchCtx& c) {
     const int N = c.a.N;
-    if (c.a.soc) return N <= 4 ? launch_thread_t<4, true>(c) : launch_thread_t<8, true>(c);
-    return N <= 4 ? launch_thread_t<4, false>(c) : launch_thread_t<8, false>(c);
+    if (c.a.soc) return N <= 4 ? launch_thread_t<4, true>(c) : (N <= 8 ? launch_thread_t<8, true>(c) : launch_thread_t<12, true>(c));
+    return N <= 4 ? launch_thread_t<4, false>(c) : (N <= 8 ? launch_thread_t<8, false>(c) : launch_thread_t<12, false>(c));
 }
 
 int launch_solve(const SmallTables& tab, const double* k_d, const int32_t* nk_mesh, long long first, long long nk, int soc, int N,
@@ -129,7 +153,8 @@ int launch_solve(const SmallTables& tab, const double* k_d, const int32_t* nk_me
         static const bool no_n2 = getenv("SKTB_NO_N2") != nullptr && getenv("SKTB_NO_N2")[0] == '1';
         if (!no_n2) { int rc = launch_n2(c); if (rc != -2) return rc; }
     }
-    if (N <= 8 && !gate && tab.thread_order) {
+    static const int thread_max = getenv("SKTB_THREAD_MAX") ? atoi(getenv("SKTB_THREAD_MAX")) : 12;   // N = 9..12 spills ~1 KB per thread and still runs 3x faster than 16 lanes per matrix (C3: 2.6e8 -> 8.0e8 k/s)
+    if (N <= thread_max && N <= 12 && !gate && tab.thread_order) {
         static const bool no_thread = getenv("SKTB_NO_THREAD") != nullptr && getenv("SKTB_NO_THREAD")[0] == '1';
         if (!no_thread) { int rc = launch_thread(c); if (rc != -2) return rc; }
     }

@@ -65,7 +65,9 @@ SKTB_D void thread_tridiag(cplx (&A)[NC * (NC + 1) / 2], double (&d)[NC], double
     e[NC - 1] = 0.0;
 }
 
-template <int NC, bool SOC>
+// SPLIT: stop after the tridiagonalisation and leave (d, e) in a.scratch ([k][2][NC], the record tql_small_kernel reads):
+// the per-lane QL is a long dependent chain that wants many resident warps, the tridiagonalisation wants 200 registers.
+template <int NC, bool SOC, bool SPLIT>
 __global__ void __launch_bounds__(THREAD_CTA) solve_thread_kernel(SmallArgs a, double* __restrict__ evals, long long ld, long long col0, int* fail) {
     constexpr int NH = SOC ? NC / 2 : NC;               // orbital-space size bound
     constexpr int NT = NH * (NH + 1) / 2;
@@ -155,18 +157,28 @@ __global__ void __launch_bounds__(THREAD_CTA) solve_thread_kernel(SmallArgs a, d
         // ---- K2: tridiagonalisation in registers, per-lane QL on (d, e) in shared memory, sort, store ----
         double d[NC], e[NC];
         thread_tridiag<NC>(A, d, e);
+        if constexpr (SPLIT) {
+            if (kbase + lane < a.nk) {
+                double2* out = reinterpret_cast<double2*>(a.scratch + (size_t)(kbase + lane) * (2 * NC));
+#pragma unroll
+                for (int i = 0; i < NC; i += 2) { out[i / 2] = make_double2(d[i], d[i + 1]); out[NC / 2 + i / 2] = make_double2(e[i], e[i + 1]); }
+                if (a.flags) a.flags[a.flag_off + kbase + lane] = 0;
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < NC; ++i) { qd[i * DSTRIDE + lane] = d[i]; qe[i * DSTRIDE + lane] = e[i]; }
         if (tql_lane_pwk(qd + lane, qe + lane, N)) atomicAdd(fail, 1);
-        double ev[NC];
+        constexpr int P2 = NC <= 4 ? 4 : (NC <= 8 ? 8 : 16);             // the sorting network needs a power of two
+        double ev[P2];
 #pragma unroll
-        for (int q = 0; q < NC; ++q) ev[q] = (q < N) ? qd[q * DSTRIDE + lane] : __longlong_as_double(0x7ff0000000000000LL);
-        bitonic_sort<NC>(ev);
+        for (int q = 0; q < P2; ++q) ev[q] = (q < N && q < NC) ? qd[q * DSTRIDE + lane] : __longlong_as_double(0x7ff0000000000000LL);
+        bitonic_sort<P2>(ev);
         if (kbase + lane < a.nk) {
 #pragma unroll
             for (int q = 0; q < NC; ++q)
                 if (q < N) evals[(long long)q * ld + col0 + kbase + lane] = ev[q];
             if (a.flags) a.flags[a.flag_off + kbase + lane] = 0;
+        }
         }
     }
 }
@@ -193,9 +205,9 @@ inline void thread_bond_order(const double* bvec, int nb, std::vector<int>* out)
     }
 }
 
-inline size_t thread_smem_bytes(int NC, bool soc, int nb) {
+inline size_t thread_smem_bytes(int NC, bool soc, int nb, bool split) {
     const int NH = soc ? NC / 2 : NC, NT = NH * (NH + 1) / 2;
     size_t dbl = (size_t)nb * NT + 3 * (size_t)nb + NH + (nb + 1) / 2;
     dbl = (dbl + 1) & ~(size_t)1;
-    return dbl * 8 + (soc ? (size_t)NC * (NC + 1) / 2 * 16 : 0) + (size_t)(THREAD_CTA / 32) * 2 * NC * DSTRIDE * 8;
+    return dbl * 8 + (soc ? (size_t)NC * (NC + 1) / 2 * 16 : 0) + (split ? 0 : (size_t)(THREAD_CTA / 32) * 2 * NC * DSTRIDE * 8);
 }

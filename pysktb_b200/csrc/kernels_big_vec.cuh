@@ -4,14 +4,14 @@
 // tridiagonal eigenvectors from INVERSE ITERATION instead of an accumulated QL (for N = 512 the rotation replay alone
 // would stream a 2 MB Z through ~5e5 dependent rotations per matrix):
 //
-//   1. heev_generic_kernel (panel formulation, eigenvalues by bisection) additionally keeps its reflectors v_j, tau_j
-//      (4 MB per 512-orbital matrix, +0.5 % of its traffic) and the tridiagonal (d, e);
-//   2. stein_kernel: one eigenvector of the real symmetric tridiagonal per THREAD - LAPACK dstein's scheme: LU with
-//      partial pivoting of T - lambda I (dlagtf), solves with perturbed tiny pivots (dlagts, job = -1), random start,
-//      modified Gram-Schmidt inside clusters of eigenvalues closer than 1e-3 ||T||_1 (the thread of a cluster's first
-//      eigenvalue computes the cluster's vectors one after the other).  O(N^2) work per matrix.  Negligible off-diagonals
-//      are kept instead of splitting T into unreduced blocks: the solves decouple numerically (tools/proto_stein.py is
-//      the scalar model, checked on exactly degenerate, split and zero-diagonal matrices);
+//   1. heev_generic_kernel (panel formulation, phase 1: tridiagonalisation only) additionally keeps its reflectors v_j,
+//      tau_j (4 MB per 512-orbital matrix, +0.5 % of its traffic) and the tridiagonal (d, e);
+//   2. stein_kernel: one eigenpair of the real symmetric tridiagonal per THREAD - LAPACK's dstebz + dstein scheme: split
+//      into unreduced blocks, eigenvalue r of a block by bisection on the Sturm count, eigenvector by inverse iteration
+//      (LU with partial pivoting of T - lambda I as in dlagtf, solves with perturbed tiny pivots as in dlagts job -1,
+//      deterministic pseudo-random start), modified Gram-Schmidt inside TIGHT clusters, one first-order Loewdin correction
+//      over dstein's 1e-3 ||T|| clusters; global ascending order by rank.  O(N^2) work per matrix (tools/proto_stein.py is the
+//      scalar model of the iteration and of the two-level orthogonalisation);
 //   3. vecbt_big_kernel: U = H_0 H_1 ... H_{N-2} Z, one eigenvector per WARP held in registers (lane l owns components
 //      l, l+32, ...: N/32 complex values), the reflectors staged panel-wise in shared memory and shared by the CTA's
 //      warps; per reflector one fused dot product, one warp reduction, one update.  8 N^3 flops per matrix at register
@@ -25,7 +25,7 @@ namespace sktb {
 struct BigVecArgs {
     int N; long long nm;
     const double* de;         // [nm][2][N]  d | e of the tridiagonal
-    const double* evals; long long ld, col0;   // sorted eigenvalues: evals[band * ld + col0 + mat]
+    double* evals; long long ld, col0;         // out: ascending eigenvalues, evals[band * ld + col0 + mat] (stein_kernel: bisection per unreduced block)
     double* Z;                // [nm][N][N]  component-major: Z[i * N + n] = component i of tridiagonal eigenvector n
     double* lu;               // [nm][4][N][N] scratch of the factorisations (a | b | c | d2), same indexing
     unsigned char* pin;       // [nm][N][N] pivot flags
@@ -45,46 +45,98 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, T = blockDim.x, tid = threadIdx.x;
     double* d = reinterpret_cast<double*>(smem_raw);
-    double* e = d + N;
-    double* w = e + N;
+    double* e = d + N;                 // e[k] couples k, k+1; negligible entries are set to zero (block boundaries)
+    double* w = e + N;                 // eigenvalue of thread n (n-th position of its block, ascending inside the block)
+    int* blo = reinterpret_cast<int*>(w + N);   // first / last index of the unreduced block that contains index n
+    int* bhi = blo + N;
     const double eps = 2.220446049250313e-16;
     for (long long mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
         __syncthreads();
         const double* de = a.de + (size_t)mat * 2 * N;
-        for (int i = tid; i < N; i += T) { d[i] = de[i]; e[i] = (i < N - 1) ? de[N + i] : 0.0; w[i] = a.evals[(long long)i * a.ld + a.col0 + mat]; }
+        for (int i = tid; i < N; i += T) { d[i] = de[i]; e[i] = (i < N - 1) ? de[N + i] : 0.0; }
         __syncthreads();
         double onenrm = 0.0;
         for (int i = 0; i < N; ++i) onenrm = fmax(onenrm, fabs(d[i]) + (i > 0 ? fabs(e[i - 1]) : 0.0) + fabs(e[i]));
-        const double ortol = 1.0e-3 * onenrm;
-        const double tol = onenrm > 0.0 ? eps * onenrm : eps;
+        __syncthreads();
+        // ---- split into unreduced blocks (dstebz / dstein work block by block: eigenvectors of different blocks are
+        //      orthogonal by support, so exact degeneracies ACROSS blocks - diagonal, zero, decoupled matrices - cost nothing)
+        for (int i = tid; i < N - 1; i += T) if (fabs(e[i]) <= eps * onenrm) e[i] = 0.0;
+        __syncthreads();
         double* Zm = a.Z + (size_t)mat * N * N;
         double* La = a.lu + (size_t)mat * 4 * N * N;
         double* Lb = La + (size_t)N * N;
         double* Lc = Lb + (size_t)N * N;
         double* Ld = Lc + (size_t)N * N;
         unsigned char* Pn = a.pin + (size_t)mat * N * N;
-        // Two levels.  TIGHT clusters (gaps <= 1e-7 ||T||: degeneracies) are computed by the thread of their first eigenvalue,
-        // one vector after the other, with modified Gram-Schmidt inside the iteration (dstein).  Everything else runs
-        // independently, one thread per eigenvector, and ONE first-order symmetric (Loewdin) correction over the LOOSE cluster
-        // (gaps <= 1e-3 ||T||, dstein's criterion) follows: independent inverse iterations are orthogonal to
-        // ~eps ||T|| / gap <= 2e-9 there, the correction squares that.  (A serial dstein over the loose clusters of a dense
-        // 512-level spectrum would leave one thread with tens of vectors and O(c^2 N) Gram-Schmidt work.)
-        const double tight = 1.0e-7 * onenrm;
-        const bool head = tid < N && (tid == 0 || w[tid] - w[tid - 1] > tight);
-        if (head) {
+        int b0 = 0, b1 = 0;
+        double lam = 0.0;
+        if (tid < N) {
+            b0 = tid; b1 = tid;
+            while (b0 > 0 && e[b0 - 1] != 0.0) --b0;
+            while (b1 < N - 1 && e[b1] != 0.0) ++b1;
+            blo[tid] = b0; bhi[tid] = b1;
+            // ---- eigenvalue r = tid - b0 of the block by bisection on the Sturm count (dstebz recurrence) ----
+            const int r = tid - b0;
+            if (b1 == b0) lam = d[b0];
+            else {
+                double gl = 1e300, gu = -1e300, tn = 0.0;
+                for (int i = b0; i <= b1; ++i) {
+                    const double el = i > b0 ? fabs(e[i - 1]) : 0.0, er = i < b1 ? fabs(e[i]) : 0.0;
+                    gl = fmin(gl, d[i] - el - er); gu = fmax(gu, d[i] + el + er);
+                    tn = fmax(tn, fmax(fabs(d[i]), fmax(el, er)));
+                }
+                const int nbk = b1 - b0 + 1;
+                const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, tn * tn), 1e-290);
+                gl -= 2.0 * eps * tn * nbk + 2.0 * pivmin; gu += 2.0 * eps * tn * nbk + 2.0 * pivmin;
+                double lo = gl, hi = gu;
+                for (int it = 0; it < 128; ++it) {
+                    const double x = 0.5 * (lo + hi);
+                    if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
+                    int cnt = 0;
+                    double q = d[b0] - x;
+                    if (fabs(q) < pivmin) q = -pivmin;
+                    cnt += q < 0.0;
+                    for (int i = b0 + 1; i <= b1; ++i) {
+                        q = fma(-e[i - 1] * e[i - 1], fast_rcp(q), d[i] - x);
+                        if (fabs(q) < pivmin) q = -pivmin;
+                        cnt += q < 0.0;
+                    }
+                    if (cnt > r) hi = x; else lo = x;
+                }
+                lam = 0.5 * (lo + hi);
+            }
+            w[tid] = lam;
+        }
+        __syncthreads();
+        // ---- inverse iteration inside the block.  Two levels: TIGHT clusters (gaps <= 1e-7 ||T||) are computed by the thread of
+        //      their first eigenvalue, one vector after the other, with modified Gram-Schmidt inside the iteration (dstein);
+        //      everything else independently, one thread per eigenvector, followed by ONE first-order symmetric (Loewdin)
+        //      correction over the LOOSE cluster (gaps <= 1e-3 ||T||, dstein's criterion): independent inverse iterations are
+        //      orthogonal to ~eps ||T|| / gap <= 2e-9 there, the correction squares that.  (A serial dstein over the loose
+        //      clusters of a dense 512-level spectrum would leave one thread with tens of vectors and O(c^2 N) work.) ----
+        const double ortol = 1.0e-3 * onenrm, tight = 1.0e-7 * onenrm;
+        const double tol = onenrm > 0.0 ? eps * onenrm : eps;
+        const bool head = tid < N && (tid == b0 || w[tid] - w[tid - 1] > tight);
+        if (tid < N) for (int i = 0; i < N; ++i) if (i < b0 || i > b1) Zm[(size_t)i * N + tid] = 0.0;
+        if (head && b1 == b0) Zm[(size_t)b0 * N + tid] = 1.0;
+        else if (head) {
+            const int nbk = b1 - b0 + 1;
             double xjm = 0.0;
-            for (int j = tid; j < N && (j == tid || w[j] - w[j - 1] <= tight); ++j) {
+            for (int j = tid; j <= b1 && (j == tid || w[j] - w[j - 1] <= tight); ++j) {
                 double xj = w[j];
                 if (j > tid) {
-                    const double pertol = 10.0 * fabs(eps * xj);
+                    // dstein separates the shifts of a cluster by 10 eps |xj|; here with an ABSOLUTE floor (10 eps ||T||): the
+                    // bisection above runs to relative precision and returns e.g. +-1.3e-38 for the two edge states of a wide
+                    // ribbon - with (numerically) equal shifts both solves amplify the same vector and Gram-Schmidt is left with noise
+                    const double pertol = 10.0 * eps * fmax(fabs(xj), onenrm);
                     if (xj - xjm < pertol) xj = xjm + pertol;
                 }
                 xjm = xj;
-                // ---- dlagtf: T - xj I = P L U ----
-                double ak = d[0] - xj, bk = N > 1 ? e[0] : 0.0;
+                // ---- dlagtf: T_block - xj I = P L U ----
+                double ak = d[b0] - xj, bk = e[b0];
                 double scale1 = fabs(ak) + fabs(bk);
-                for (int k = 0; k < N - 1; ++k) {
-                    double ck = e[k], ak1 = d[k + 1] - xj, bk1 = (k < N - 2) ? e[k + 1] : 0.0, d2k = 0.0;
+                for (int k = b0; k < b1; ++k) {
+                    double ck = e[k], ak1 = d[k + 1] - xj, bk1 = (k < b1 - 1) ? e[k + 1] : 0.0, d2k = 0.0;
                     const double scale2 = fabs(ck) + fabs(ak1) + fabs(bk1);
                     const double piv1 = ak == 0.0 ? 0.0 : fabs(ak) / scale1;
                     unsigned char pv = 0;
@@ -100,7 +152,7 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
                         sa = ck;
                         const double temp = ak1;
                         ak1 = bk - mult * temp;
-                        if (k < N - 2) { d2k = bk1; bk1 = -mult * d2k; }
+                        if (k < b1 - 1) { d2k = bk1; bk1 = -mult * d2k; }
                         sb = temp;
                         ck = mult;
                     }
@@ -108,19 +160,19 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
                     La[at] = sa; Lb[at] = sb; Lc[at] = ck; Ld[at] = d2k; Pn[at] = pv;
                     ak = ak1; bk = bk1;
                 }
-                La[(size_t)(N - 1) * N + j] = ak;
+                La[(size_t)b1 * N + j] = ak;
                 const double a_last = ak;
                 // ---- inverse iteration ----
-                for (int i = 0; i < N; ++i) Zm[(size_t)i * N + j] = stein_uniform((unsigned)i, (unsigned)j, (unsigned)N);
+                for (int i = b0; i <= b1; ++i) Zm[(size_t)i * N + j] = stein_uniform((unsigned)i, (unsigned)j, (unsigned)N);
                 int nrmchk = 0;
-                const double dtpcrt = sqrt(0.1 / N);
+                const double dtpcrt = sqrt(0.1 / nbk);
                 for (int it = 0; it < 8; ++it) {
                     double s1 = 0.0;
-                    for (int i = 0; i < N; ++i) s1 += fabs(Zm[(size_t)i * N + j]);
-                    const double scl = (double)N * fmax(onenrm, 1e-300) * fmax(eps, fabs(a_last)) / fmax(s1, 1e-300);
+                    for (int i = b0; i <= b1; ++i) s1 += fabs(Zm[(size_t)i * N + j]);
+                    const double scl = (double)nbk * fmax(onenrm, 1e-300) * fmax(eps, fabs(a_last)) / fmax(s1, 1e-300);
                     // forward: y <- L^-1 P y (with the scaling of the start vector folded in)
-                    double yprev = Zm[j] * scl;
-                    for (int k = 1; k < N; ++k) {
+                    double yprev = Zm[(size_t)b0 * N + j] * scl;
+                    for (int k = b0 + 1; k <= b1; ++k) {
                         const size_t lk = (size_t)(k - 1) * N + j;
                         double yk = Zm[(size_t)k * N + j] * scl;
                         const double c = Lc[lk];
@@ -129,50 +181,62 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
                         Zm[(size_t)(k - 1) * N + j] = yprev;
                         yprev = yk;
                     }
-                    Zm[(size_t)(N - 1) * N + j] = yprev;
+                    Zm[(size_t)b1 * N + j] = yprev;
                     // backward: x <- U^-1 y, tiny pivots perturbed to +-tol
                     double x1 = 0.0, x2 = 0.0;
-                    for (int k = N - 1; k >= 0; --k) {
+                    for (int k = b1; k >= b0; --k) {
                         const size_t at = (size_t)k * N + j;
                         double t = Zm[at];
-                        if (k <= N - 2) t -= Lb[at] * x1;
-                        if (k <= N - 3) t -= Ld[at] * x2;
+                        if (k <= b1 - 1) t -= Lb[at] * x1;
+                        if (k <= b1 - 2) t -= Ld[at] * x2;
                         double akk = La[at];
                         if (fabs(akk) < tol) akk = akk >= 0.0 ? tol : -tol;
                         t /= akk;
+                        if (fabs(t) > 1.0e150) {       // exponentially localised vectors (edge states) span hundreds of decades: rescale
+                            for (int kk = b0; kk <= b1; ++kk) Zm[(size_t)kk * N + j] *= 1.0e-150;      // (solution so far and the right-hand side still ahead)
+                            t *= 1.0e-150; x1 *= 1.0e-150; x2 *= 1.0e-150;
+                        }
                         Zm[at] = t;
                         x2 = x1; x1 = t;
                     }
-                    // modified Gram-Schmidt against the earlier vectors of the cluster
+                    // modified Gram-Schmidt against the earlier vectors of the tight cluster
                     for (int q = tid; q < j; ++q) {
                         double dot = 0.0;
-                        for (int i = 0; i < N; ++i) dot = fma(Zm[(size_t)i * N + j], Zm[(size_t)i * N + q], dot);
-                        for (int i = 0; i < N; ++i) Zm[(size_t)i * N + j] = fma(-dot, Zm[(size_t)i * N + q], Zm[(size_t)i * N + j]);
+                        for (int i = b0; i <= b1; ++i) dot = fma(Zm[(size_t)i * N + j], Zm[(size_t)i * N + q], dot);
+                        for (int i = b0; i <= b1; ++i) Zm[(size_t)i * N + j] = fma(-dot, Zm[(size_t)i * N + q], Zm[(size_t)i * N + j]);
                     }
                     double mx = 0.0;
-                    for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(Zm[(size_t)i * N + j]));
+                    for (int i = b0; i <= b1; ++i) mx = fmax(mx, fabs(Zm[(size_t)i * N + j]));
                     if (mx >= dtpcrt && ++nrmchk >= 3) break;
                 }
+                double mxf = 0.0;
+                for (int i = b0; i <= b1; ++i) mxf = fmax(mxf, fabs(Zm[(size_t)i * N + j]));
+                const double imx = mxf > 0.0 ? 1.0 / mxf : 0.0;     // scaled 2-norm: the squares of a 1e160 entry would overflow
                 double nn = 0.0;
-                for (int i = 0; i < N; ++i) { const double z = Zm[(size_t)i * N + j]; nn = fma(z, z, nn); }
-                const double inv = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
-                for (int i = 0; i < N; ++i) Zm[(size_t)i * N + j] *= inv;
+                for (int i = b0; i <= b1; ++i) { const double z = Zm[(size_t)i * N + j] * imx; nn = fma(z, z, nn); }
+                const double inv = nn > 0.0 ? imx / sqrt(nn) : 0.0;
+                for (int i = b0; i <= b1; ++i) Zm[(size_t)i * N + j] *= inv;
             }
         }
         __syncthreads();
-        // ---- Loewdin correction over the loose cluster, into the (now free) first factor array: the final Z ----
+        // ---- global ascending rank (ties by index), Loewdin correction over the loose cluster of the block; the corrected
+        //      vector goes to column `rank` of the (now free) first factor array = the final Z, the eigenvalue to evals[rank] ----
         if (tid < N) {
             const int j = tid;
+            const double wj = w[j];
+            int rank = 0;
+            for (int m = 0; m < N; ++m) { const double wm = w[m]; rank += (wm < wj) || (wm == wj && m < j); }
+            a.evals[(long long)rank * a.ld + a.col0 + mat] = wj;
             int lo = j, hi = j;
-            while (lo > 0 && w[lo] - w[lo - 1] <= ortol) --lo;
-            while (hi < N - 1 && w[hi + 1] - w[hi] <= ortol) ++hi;
-            for (int i = 0; i < N; ++i) La[(size_t)i * N + j] = Zm[(size_t)i * N + j];
+            while (lo > b0 && w[lo] - w[lo - 1] <= ortol) --lo;
+            while (hi < b1 && w[hi + 1] - w[hi] <= ortol) ++hi;
+            for (int i = 0; i < N; ++i) La[(size_t)i * N + rank] = Zm[(size_t)i * N + j];
             for (int m = lo; m <= hi; ++m) {
                 if (m == j) continue;
                 double dot = 0.0;
-                for (int i = 0; i < N; ++i) dot = fma(Zm[(size_t)i * N + m], Zm[(size_t)i * N + j], dot);
+                for (int i = b0; i <= b1; ++i) dot = fma(Zm[(size_t)i * N + m], Zm[(size_t)i * N + j], dot);
                 const double h = -0.5 * dot;
-                for (int i = 0; i < N; ++i) La[(size_t)i * N + j] = fma(h, Zm[(size_t)i * N + m], La[(size_t)i * N + j]);
+                for (int i = b0; i <= b1; ++i) La[(size_t)i * N + rank] = fma(h, Zm[(size_t)i * N + m], La[(size_t)i * N + rank]);
             }
         }
     }
@@ -181,7 +245,7 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
 // U = H_0 ... H_{N-2} Z for BW eigenvectors per CTA (one per warp); NQ = ceil(N / 32) components per lane.
 constexpr int VBT_PANEL = 8;        // reflectors staged per shared-memory panel
 template <int NQ, int BW>
-__global__ void __launch_bounds__(BW * 32) vecbt_big_kernel(BigVecArgs a) {
+__global__ void __launch_bounds__(BW * 32, NQ <= 16 ? 2 : 1) vecbt_big_kernel(BigVecArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cplx* Vp = reinterpret_cast<cplx*>(smem_raw);                         // [VBT_PANEL][NQ * 32] reflector panel
@@ -215,19 +279,23 @@ __global__ void __launch_bounds__(BW * 32) vecbt_big_kernel(BigVecArgs a) {
             const int q0 = (jlo + 1) >> 5;                                // components below 32 q0 are untouched by this panel
             for (int s = np - 1; s >= 0; --s) {
                 const cplx* v = Vp + (size_t)s * NQ * 32 + lane;
-                constexpr int NR = NQ <= 16 ? NQ : 1;                      // NQ = 32: the reflector is re-read for the update (registers)
+                constexpr bool KEEP = NQ <= 8;                             // larger NQ: the reflector is re-read for the update (two CTAs per SM)
+                constexpr int NR = KEEP ? NQ : 1;
                 cplx vr[NR];
-                cplx dot = cmake(0.0, 0.0);
+                cplx dacc[4];                                               // four independent chains: the single accumulator was a
+#pragma unroll                                                              // 2 NQ-deep dependent DFMA chain per reflector
+                for (int c = 0; c < 4; ++c) dacc[c] = cmake(0.0, 0.0);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    if (q >= q0) { const cplx vq = v[32 * q]; if (NQ <= 16) vr[q % NR] = vq; cfmac(dot, vq, u[q]); }      // v^H u
+                    if (q >= q0) { const cplx vq = v[32 * q]; if (KEEP) vr[q % NR] = vq; cfmac(dacc[q & 3], vq, u[q]); }      // v^H u
                 }
+                cplx dot = cadd(cadd(dacc[0], dacc[1]), cadd(dacc[2], dacc[3]));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o); }
                 const cplx wv = cmul(tp[s], dot);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    if (q >= q0) cfms(u[q], wv, NQ <= 16 ? vr[q % NR] : v[32 * q]);       // u -= tau (v^H u) v
+                    if (q >= q0) cfms(u[q], wv, KEEP ? vr[q % NR] : v[32 * q]);           // u -= tau (v^H u) v
                 }
             }
         }
@@ -250,6 +318,80 @@ __global__ void __launch_bounds__(BW * 32) vecbt_big_kernel(BigVecArgs a) {
             }
             __syncwarp();
         }
+    }
+}
+
+// Selected components only (LDOS / spectral maps: a handful of rows i of U = Q Z): row i of Q = e_i^T H_0 H_1 ... H_{N-2} costs
+// one pass over the reflectors (p = Q^H e_i: p <- H_j^H p, j ascending - the same register layout and panel staging as above,
+// one ROW per warp), then U[i, n] = sum_k conj(p_k) Z[k, n] for all n.  O(|S| N^2) per matrix instead of the 8 N^3 of the full
+// back-transformation: the edge-projected LDOS of the 512-orbital ribbon needs 4 rows.
+template <int NQ, int BW>
+__global__ void __launch_bounds__(BW * 32, NQ <= 16 ? 2 : 1) rowsq_big_kernel(BigVecArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cplx* Vp = reinterpret_cast<cplx*>(smem_raw);                         // [VBT_PANEL][NQ * 32] reflector panel
+    cplx* tp = Vp + (size_t)VBT_PANEL * NQ * 32;                          // [VBT_PANEL] tau
+    static_assert(BW <= VBT_PANEL, "the staging of the finished rows aliases the reflector panel");
+    const int groups = (a.n_rows + BW - 1) / BW;
+    for (long long work = blockIdx.x; work < a.nm * groups; work += gridDim.x) {
+        const long long mat = work / groups;
+        const int r = (int)(work - mat * groups) * BW + warp;             // this warp's selected row
+        const bool live = r < a.n_rows;
+        const int irow = live ? a.rows[r] : 0;
+        const double* Zm = a.lu + (size_t)mat * 4 * N * N;
+        const cplx* Vs = a.vstore + (size_t)mat * N * N;
+        const cplx* Ts = a.taustore + (size_t)mat * N;
+        cplx u[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) u[q] = cmake((live && 32 * q + lane == irow) ? 1.0 : 0.0, 0.0);
+        for (int jlo = 0; jlo <= N - 2; jlo += VBT_PANEL) {
+            const int np = min(VBT_PANEL, N - 1 - jlo);
+            __syncthreads();
+            for (int t = tid; t < np * NQ * 32; t += BW * 32) {
+                const int s = t / (NQ * 32), i = t - s * (NQ * 32);
+                Vp[t] = i < N ? Vs[(size_t)(jlo + s) * N + i] : cmake(0.0, 0.0);
+            }
+            if (tid < np) tp[tid] = Ts[jlo + tid];
+            __syncthreads();
+            const int q0 = (jlo + 1) >> 5;
+            for (int s = 0; s < np; ++s) {
+                const cplx* v = Vp + (size_t)s * NQ * 32 + lane;
+                cplx dacc[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dacc[c] = cmake(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if (q >= q0) cfmac(dacc[q & 3], v[32 * q], u[q]);
+                }
+                cplx dot = cadd(cadd(dacc[0], dacc[1]), cadd(dacc[2], dacc[3]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o); }
+                const cplx wv = cmul(cconj(tp[s]), dot);                  // H_j^H = I - conj(tau) v v^H
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if (q >= q0) cfms(u[q], wv, v[32 * q]);
+                }
+            }
+        }
+        __syncthreads();                                                   // every warp is done with the last reflector panel
+        cplx* mine = Vp + (size_t)warp * NQ * 32;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) mine[32 * q + lane] = u[q];           // p = Q^H e_i: row i of Q is p^H
+        __syncwarp();
+        if (live) {
+            for (int n = lane; n < N; n += 32) {
+                double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+                int k = 0;
+                for (; k + 1 < N; k += 2) {
+                    const double z0 = Zm[(size_t)k * N + n], z1 = Zm[(size_t)(k + 1) * N + n];
+                    const cplx p0 = mine[k], p1 = mine[k + 1];
+                    ax = fma(p0.x, z0, ax); ay = fma(-p0.y, z0, ay); bx = fma(p1.x, z1, bx); by = fma(-p1.y, z1, by);
+                }
+                if (k < N) { const double z0 = Zm[(size_t)k * N + n]; const cplx p0 = mine[k]; ax = fma(p0.x, z0, ax); ay = fma(-p0.y, z0, ay); }
+                a.vec_out[(long long)n * a.vs_band + (a.vcol0 + mat) * a.vs_k + r] = cmake(ax + bx, ay + by);
+            }
+        }
+        __syncwarp();
     }
 }
 

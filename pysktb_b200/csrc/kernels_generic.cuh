@@ -512,6 +512,10 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
         }
         if (tid == 0) { d[N - 1] = A[(size_t)(N - 1) * N + (N - 1)].x; e[N - 1] = 0.0; }
         __syncthreads();
+        if (a.de_out) {
+            double* deo = a.de_out + (size_t)mat * 2 * N;
+            for (int idx = tid; idx < N; idx += T) { deo[idx] = d[idx]; deo[N + idx] = e[idx]; }
+        }
         if (a.phase == 1) {
             // split run (tracked rows, N > 64): the serial QL generator would leave this SM idle, so it runs in a
             // second launch with small CTAs, many matrices per SM
@@ -520,11 +524,6 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
             __syncthreads();
             continue;
         }
-        }
-
-        if (a.de_out && a.phase != 2) {
-            double* deo = a.de_out + (size_t)mat * 2 * N;
-            for (int idx = tid; idx < N; idx += T) { deo[idx] = d[idx]; deo[N + idx] = e[idx]; }
         }
 
         // ---- tridiagonal QL ----

@@ -16,12 +16,42 @@ enum VIdx {
     V_dfd, V_ffs, V_ffp, V_ffd, V_fff, V_SSs, V_sSs, V_Sps, V_Sds, V_Sfs, V_COUNT
 };
 
+// Forward-mode derivative carrier for the Hellmann-Feynman forces: value + gradient with respect to the three Cartesian
+// components of the bond vector.  sk_fill<SkDual> differentiates the table exactly as written (the reference's
+// departures from the textbook tables included), where the reference itself falls back to a forward difference
+// with eps = 1e-6 over the direction cosines (forces.py:283-297).
+struct SkDual {
+    double v, g[3];
+    __host__ __device__ SkDual() : v(0.0), g{0.0, 0.0, 0.0} {}
+    __host__ __device__ SkDual(double x) : v(x), g{0.0, 0.0, 0.0} {}
+    __host__ __device__ SkDual(double x, double a, double b, double c) : v(x), g{a, b, c} {}
+};
+__host__ __device__ inline SkDual operator+(SkDual a, SkDual b) { return SkDual(a.v + b.v, a.g[0] + b.g[0], a.g[1] + b.g[1], a.g[2] + b.g[2]); }
+__host__ __device__ inline SkDual operator-(SkDual a, SkDual b) { return SkDual(a.v - b.v, a.g[0] - b.g[0], a.g[1] - b.g[1], a.g[2] - b.g[2]); }
+__host__ __device__ inline SkDual operator-(SkDual a) { return SkDual(-a.v, -a.g[0], -a.g[1], -a.g[2]); }
+__host__ __device__ inline SkDual operator*(SkDual a, SkDual b) {
+    return SkDual(a.v * b.v, a.g[0] * b.v + a.v * b.g[0], a.g[1] * b.v + a.v * b.g[1], a.g[2] * b.v + a.v * b.g[2]);
+}
+__host__ __device__ inline SkDual operator/(SkDual a, SkDual b) {
+    const double q = a.v / b.v, ib = 1.0 / b.v;
+    return SkDual(q, (a.g[0] - q * b.g[0]) * ib, (a.g[1] - q * b.g[1]) * ib, (a.g[2] - q * b.g[2]) * ib);
+}
+__host__ __device__ inline SkDual operator+(double a, SkDual b) { return SkDual(a) + b; }
+__host__ __device__ inline SkDual operator+(SkDual a, double b) { return a + SkDual(b); }
+__host__ __device__ inline SkDual operator-(double a, SkDual b) { return SkDual(a) - b; }
+__host__ __device__ inline SkDual operator-(SkDual a, double b) { return a - SkDual(b); }
+__host__ __device__ inline SkDual operator*(double a, SkDual b) { return SkDual(a * b.v, a * b.g[0], a * b.g[1], a * b.g[2]); }
+__host__ __device__ inline SkDual operator*(SkDual a, double b) { return b * a; }
+__host__ __device__ inline SkDual operator/(SkDual a, double b) { return a * (1.0 / b); }
+__host__ __device__ inline SkDual operator/(double a, SkDual b) { return SkDual(a) / b; }
+__host__ __device__ inline bool operator>(SkDual a, double b) { return a.v > b; }
+
 // row of an s-like orbital (s or S) against p,d,f; `row` selects which orbital index it is
-__device__ __forceinline__ void sk_s_row(double* T, int row, double Vp, double Vd, double Vf, double l, double m,
-                                         double n) {
+template <class R>
+__device__ __forceinline__ void sk_s_row(R* T, int row, R Vp, R Vd, R Vf, R l, R m, R n) {
 #define TT(i, j) T[(i) * 17 + (j)]
-    const double l2 = l * l, m2 = m * m, n2 = n * n;
-    const double r3 = sqrt(3.0), r15 = sqrt(15.0);
+    const R l2 = l * l, m2 = m * m, n2 = n * n;
+    const R r3 = sqrt(3.0), r15 = sqrt(15.0);
     TT(row, 1) = l * Vp;
     TT(row, 2) = m * Vp;
     TT(row, 3) = n * Vp;
@@ -43,18 +73,19 @@ __device__ __forceinline__ void sk_s_row(double* T, int row, double Vp, double V
 #undef TT
 }
 
-__device__ inline void sk_fill(const double* __restrict__ V, double l, double m, double n, double* __restrict__ T) {
+template <class R>
+__device__ inline void sk_fill(const R* __restrict__ V, R l, R m, R n, R* __restrict__ T) {
 #define TT(i, j) T[(i) * 17 + (j)]
-    for (int i = 0; i < 289; ++i) T[i] = 0.0;
-    const double l2 = l * l, m2 = m * m, n2 = n * n;
-    const double lm = l * m, mn = m * n, nl = n * l, lmn = l * m * n;
-    const double dm = l2 - m2, sp = l2 + m2;
+    for (int i = 0; i < 289; ++i) T[i] = R(0.0);
+    const R l2 = l * l, m2 = m * m, n2 = n * n;
+    const R lm = l * m, mn = m * n, nl = n * l, lmn = l * m * n;
+    const R dm = l2 - m2, sp = l2 + m2;
     const bool off = sp > 1e-10;                 // the reference's on-axis guard
-    const double q = off ? sp : 1.0;
-    const double r2 = sqrt(2.0), r3 = sqrt(3.0), r6 = sqrt(6.0), r10 = sqrt(10.0), r30 = sqrt(30.0);
-    const double a = 5 * n2 - 1, b = 5 * n2 - 3;
-    const double x3 = l2 - 3 * m2, y3 = 3 * l2 - m2;
-    const double z2 = n2 - 0.5 * sp;
+    const R q = off ? sp : 1.0;
+    const R r2 = sqrt(2.0), r3 = sqrt(3.0), r6 = sqrt(6.0), r10 = sqrt(10.0), r30 = sqrt(30.0);
+    const R a = 5 * n2 - 1, b = 5 * n2 - 3;
+    const R x3 = l2 - 3 * m2, y3 = 3 * l2 - m2;
+    const R z2 = n2 - 0.5 * sp;
 
     // s and S rows/cols
     TT(0, 0) = V[V_sss];
@@ -65,7 +96,7 @@ __device__ inline void sk_fill(const double* __restrict__ V, double l, double m,
     TT(16, 0) = V[V_sSs];
 
     {   // p-p
-        const double s = V[V_pps], p = V[V_ppp];
+        const R s = V[V_pps], p = V[V_ppp];
         TT(1, 1) = l2 * s + (1.0 - l2) * p;
         TT(2, 2) = m2 * s + (1.0 - m2) * p;
         TT(3, 3) = n2 * s + (1.0 - n2) * p;
@@ -74,8 +105,8 @@ __device__ inline void sk_fill(const double* __restrict__ V, double l, double m,
         TT(2, 3) = TT(3, 2) = mn * (s - p);
     }
     {   // p-d
-        const double s = V[V_pds], p = V[V_pdp];
-        const double cross = lmn * (r3 * s - 2 * p);
+        const R s = V[V_pds], p = V[V_pdp];
+        const R cross = lmn * (r3 * s - 2 * p);
         TT(1, 4) = r3 * l2 * m * s + m * (1.0 - 2 * l2) * p;
         TT(1, 5) = cross;
         TT(1, 6) = r3 * l2 * n * s + n * (1.0 - 2 * l2) * p;
@@ -95,7 +126,7 @@ __device__ inline void sk_fill(const double* __restrict__ V, double l, double m,
             for (int j = 4; j < 9; ++j) TT(j, i) = -TT(i, j);
     }
     {   // p-f : the assignments that survive in the reference
-        const double s = V[V_pfs], p = V[V_pfp];
+        const R s = V[V_pfs], p = V[V_pfp];
         TT(1, 9) = r6 / 4.0 * l * a * s - r6 / 2.0 * l * n2 * p;
         TT(1, 10) = (3.0 / 4.0 * l2 * a - a / 2.0) * s + (l2 * (1 - 5 * n2 / 2.0) + n2) * p;
         TT(1, 11) = 3.0 / 4.0 * lm * a * s - 5.0 / 2.0 * lm * n2 * p;
@@ -121,8 +152,8 @@ __device__ inline void sk_fill(const double* __restrict__ V, double l, double m,
             for (int j = 9; j < 16; ++j) TT(j, i) = TT(i, j);      // same sign, as the reference does
     }
     {   // d-d
-        const double s = V[V_dds], p = V[V_ddp], d = V[V_ddd];
-        const double mix = 3 * s - 4 * p + d, pd = p - d;
+        const R s = V[V_dds], p = V[V_ddp], d = V[V_ddd];
+        const R mix = 3 * s - 4 * p + d, pd = p - d;
         TT(4, 4) = l2 * m2 * mix + (l2 + m2) * p + n2 * d;
         TT(5, 5) = m2 * n2 * mix + (m2 + n2) * p + l2 * d;
         TT(6, 6) = n2 * l2 * mix + (n2 + l2) * p + m2 * d;
@@ -140,9 +171,9 @@ __device__ inline void sk_fill(const double* __restrict__ V, double l, double m,
         TT(7, 8) = TT(8, 7) = r3 * 0.25 * dm * (n2 * (2 * s - 4 * p + d) + d - sp * s);
     }
     {   // d-f
-        const double s = V[V_dfs], p = V[V_dfp];
-        const double q2 = off ? sp * sp : 1.0;
-        const double w = a * (3 * n2 - 1) - 6 * n2;
+        const R s = V[V_dfs], p = V[V_dfp];
+        const R q2 = off ? sp * sp : 1.0;
+        const R w = a * (3 * n2 - 1) - 6 * n2;
         TT(4, 9) = r10 / 4.0 * lm * a * s - r10 / 2.0 * lm * n2 * p;
         TT(4, 10) = r30 / 8.0 * m * (l2 * a - a / 3.0) * s + r30 / 4.0 * m * (n2 - l2 * a / 3.0) * p;
         TT(4, 11) = r30 / 8.0 * l * (m2 * a - a / 3.0) * s + r30 / 4.0 * l * (n2 - m2 * a / 3.0) * p;
@@ -182,9 +213,9 @@ __device__ inline void sk_fill(const double* __restrict__ V, double l, double m,
             for (int j = 9; j < 16; ++j) TT(j, i) = -TT(i, j);
     }
     {   // f-f
-        const double s = V[V_ffs], p = V[V_ffp], d = V[V_ffd];
-        const double h = 1 - 5 * n2 / 2.0;
-        const double s3 = l2 * m2 + m2 * n2 + n2 * l2;
+        const R s = V[V_ffs], p = V[V_ffp], d = V[V_ffd];
+        const R h = 1 - 5 * n2 / 2.0;
+        const R s3 = l2 * m2 + m2 * n2 + n2 * l2;
         TT(9, 9) = n2 * (b * b) / 4.0 * s + 3.0 / 2.0 * n2 * (1 - n2) * a * p + 15.0 / 4.0 * ((1 - n2) * (1 - n2)) * d;
         // the l2*h*h / m2*h*h term carries no V factor in the reference (_params.py:397,:402)
         TT(10, 10) = 3.0 / 8.0 * l2 * (a * a) * s + l2 * (h * h) + n2 * (1 - l2) * p + (1 - l2) * (1 - n2) * d;
@@ -220,7 +251,29 @@ __global__ void sk_table_kernel(const double* __restrict__ V, const double* __re
                                 int nb) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    sk_fill(V + (size_t)b * V_COUNT, lmn[3 * b], lmn[3 * b + 1], lmn[3 * b + 2], out + (size_t)b * 289);
+    sk_fill<double>(V + (size_t)b * V_COUNT, lmn[3 * b], lmn[3 * b + 1], lmn[3 * b + 2], out + (size_t)b * 289);
+}
+
+// Table and its Cartesian gradient for the forces: V [nb][25] values, dV [nb][25] derivatives dV/dd at the bond length,
+// vec [nb][3] Cartesian bond vectors; out [nb][4][289]: T | dT/dx | dT/dy | dT/dz.  work [nb][289] SkDual scratch.
+__global__ void sk_table_grad_kernel(const double* __restrict__ V, const double* __restrict__ dV, const double* __restrict__ vec,
+                                     double* __restrict__ out, SkDual* __restrict__ work, int nb) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const double x = vec[3 * b], y = vec[3 * b + 1], z = vec[3 * b + 2];
+    const double d = sqrt(x * x + y * y + z * z), id = 1.0 / d;
+    const double c[3] = {x * id, y * id, z * id};
+    SkDual lmn[3];
+    for (int a = 0; a < 3; ++a) lmn[a] = SkDual(c[a], ((a == 0) - c[a] * c[0]) * id, ((a == 1) - c[a] * c[1]) * id, ((a == 2) - c[a] * c[2]) * id);
+    SkDual Vd[V_COUNT];
+    for (int q = 0; q < V_COUNT; ++q) {
+        const double dv = dV[(size_t)b * V_COUNT + q];
+        Vd[q] = SkDual(V[(size_t)b * V_COUNT + q], dv * c[0], dv * c[1], dv * c[2]);
+    }
+    SkDual* T = work + (size_t)b * 289;
+    sk_fill<SkDual>(Vd, lmn[0], lmn[1], lmn[2], T);
+    double* o = out + (size_t)b * 4 * 289;
+    for (int e = 0; e < 289; ++e) { o[e] = T[e].v; o[289 + e] = T[e].g[0]; o[578 + e] = T[e].g[1]; o[867 + e] = T[e].g[2]; }
 }
 
 }  // namespace sktb

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "sk_table.cuh"
 #include "kernels_generic.cuh"
+#include "kernels_big_vec.cuh"
 #include "heev_small.cuh"
 
 using namespace sktb;
@@ -135,6 +136,19 @@ extern "C" int sktb_sk_table(const double* V_d, const double* lmn_d, double* out
     if (nb <= 0) return 0;
     sk_table_kernel<<<(nb + 63) / 64, 64, 0, (cudaStream_t)stream>>>(V_d, lmn_d, out_d, nb);
     LAUNCHED();
+    return 0;
+}
+
+extern "C" int sktb_sk_table_grad(const double* V_d, const double* dV_d, const double* vec_d, double* out_d, int32_t nb, void* stream) {
+    if (nb <= 0) return 0;
+    if (!V_d || !dV_d || !vec_d || !out_d) return fail("null argument");
+    SkDual* work = nullptr;
+    CK(cudaMalloc((void**)&work, (size_t)nb * 289 * sizeof(SkDual)));
+    sk_table_grad_kernel<<<(nb + 31) / 32, 32, 0, (cudaStream_t)stream>>>(V_d, dV_d, vec_d, out_d, work, nb);
+    ++g_launches;
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(work);
+    if (e != cudaSuccess) return fail("sk_table_grad kernel failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -462,6 +476,67 @@ static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
 
 static const size_t WS_BUDGET = (size_t)3 << 30;   // per-buffer cap for chunked workspaces
 
+// ------------------------------------------------------------------------------------------------------
+// Eigenvectors for 64 < N <= 1024 (kernels_big_vec.cuh): panel tridiagonalisation keeping its reflectors + bisection,
+// inverse iteration on the tridiagonal (one eigenvector per thread), back-transformation (one eigenvector per warp).
+// H: [nm][N][N] workspace (destroyed).  vec_out[band * vs_band + (vcol0 + mat) * vs_k + r]: all components (n_rows == 0)
+// or only the components rows_d[r].  scratch: >= nm * bigvec_bytes_per_matrix(N).  SKTB_BIGVEC=0: row tracking as before.
+// ------------------------------------------------------------------------------------------------------
+static bool bigvec_enabled(int N) {
+    static const bool off = getenv("SKTB_BIGVEC") && getenv("SKTB_BIGVEC")[0] == '0';
+    return !off && N > 64 && N <= 1024;
+}
+static const size_t BIGVEC_BUDGET = (size_t)12 << 30;
+template <int NQ>
+static int launch_vecbt_big(const BigVecArgs& b, cudaStream_t st, int sms) {
+    constexpr int BW = 8;
+    const size_t smem = vecbt_big_smem(NQ);
+    void (*kern)(BigVecArgs) = b.n_rows > 0 ? rowsq_big_kernel<NQ, BW> : vecbt_big_kernel<NQ, BW>;     // selected rows of U only | all of U
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BW * 32, smem);
+    const long long work = b.nm * (((b.n_rows > 0 ? b.n_rows : b.N) + BW - 1) / BW);
+    kern<<<(unsigned)std::max<long long>(1, std::min<long long>(work, (long long)sms * std::max(occ, 1))), BW * 32, smem, st>>>(b);
+    LAUNCHED();
+    return 0;
+}
+static int launch_bigvec(sktb_plan* p, cplx* H, int N, long long nm, double* evals_d, long long ld, long long col0, cplx* vec_out,
+                         long long vs_band, long long vs_k, long long vcol0, int n_rows, const int* rows_d, void* scratch, cudaStream_t st) {
+    const size_t nn = (size_t)N * N;
+    unsigned char* base = reinterpret_cast<unsigned char*>(scratch);      // 16-byte types first: every segment stays aligned for odd N
+    cplx* vstore = reinterpret_cast<cplx*>(base);                      base += (size_t)nm * nn * 16;
+    cplx* taus = reinterpret_cast<cplx*>(base);                        base += (size_t)nm * N * 16;
+    double* Z = reinterpret_cast<double*>(base);                       base += (size_t)nm * nn * 8;
+    double* lu = reinterpret_cast<double*>(base);                      base += (size_t)nm * 4 * nn * 8;
+    double* de = reinterpret_cast<double*>(base);                      base += (size_t)nm * 2 * N * 8;
+    unsigned char* pin = base;
+    HeevArgs a{};
+    a.H = H; a.N = N; a.nm = (int)nm;
+    a.evals = evals_d; a.ld = ld; a.col0 = col0;
+    a.vstore = vstore; a.taustore = taus; a.de_out = de;
+    int rc = launch_heev_generic_phase(p, a, st, 1);                  // tridiagonalisation only: (d, e) and the reflectors are kept
+    if (rc) return rc;
+    const std::string first = g_kinfo;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    BigVecArgs b{};
+    b.N = N; b.nm = nm; b.de = de; b.evals = evals_d; b.ld = ld; b.col0 = col0;
+    b.Z = Z; b.lu = lu; b.pin = pin; b.vstore = vstore; b.taustore = taus;
+    b.vec_out = vec_out; b.vs_band = vs_band; b.vs_k = vs_k; b.vcol0 = vcol0; b.n_rows = n_rows; b.rows = rows_d;
+    const int T = (N + 31) / 32 * 32;
+    stein_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, (size_t)4 * N * 8, st>>>(b);
+    LAUNCHED();
+    if (N <= 128) rc = launch_vecbt_big<4>(b, st, sms);
+    else if (N <= 256) rc = launch_vecbt_big<8>(b, st, sms);
+    else if (N <= 512) rc = launch_vecbt_big<16>(b, st, sms);
+    else rc = launch_vecbt_big<32>(b, st, sms);
+    if (rc) return rc;
+    g_kinfo = first + " (reflectors kept) + stein (bisection + inverse iteration, 1 eigenpair/thread) + " +
+              (n_rows > 0 ? "rowsq_big (selected rows of Q, then rows of U = Q Z)" : "vecbt_big (1 eigenvector/warp)");
+    return 0;
+}
+
 // 32 < N <= 64: K0 + K1 fused into tridiag_cta64 (H(k) is assembled in shared memory / registers, never in HBM) whenever the
 // per-k Hermiticity flags are not needed.  SKTB_CTA64_FUSE=0: materialise H with hk_kernel as before (A/B, parity tests).
 static bool c64_fusable(const sktb_plan* p, int N, int soc, bool need_flags) {
@@ -589,9 +664,11 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
         }
     } else {
         size_t perH = (size_t)N * N * sizeof(cplx);
+        const bool bigvec = want_vecs && bigvec_enabled(N);
         long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / perH)));
+        if (bigvec) chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(BIGVEC_BUDGET / (perH + bigvec_bytes_per_matrix(N)))));
         if (W.H.ensure(perH * chunk)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
-        if (want_vecs && W.RT.ensure(perH * chunk)) return fail("out of device memory (RT workspace)");
+        if (want_vecs && W.RT.ensure(bigvec ? bigvec_bytes_per_matrix(N) * chunk : perH * chunk)) return fail("out of device memory (RT workspace)");
         const bool peel = !want_vecs && N > 64 && N <= PEEL_MAX;
         if (peel && W.S.ensure(peel_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
         if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
@@ -601,6 +678,11 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
             if (!k_d) { int rc = sktb_kmesh(nk_mesh, first + c0, cnt, (double*)W.K.p, st); if (rc) return rc; }
             int rc = launch_hk(p, kk, cnt, soc, (cplx*)W.H.p, flags_d, k_off + c0, st);
             if (rc) return rc;
+            if (bigvec) {
+                rc = launch_bigvec(p, (cplx*)W.H.p, N, cnt, evals_d, ld, k_off + c0, (cplx*)evecs_d, ld * N, N, k_off + c0, 0, nullptr, W.RT.p, st);
+                if (rc) return rc;
+                continue;
+            }
             HeevArgs a{};
             a.H = (cplx*)W.H.p; a.N = N; a.nm = (int)cnt;
             a.evals = evals_d; a.ld = ld; a.col0 = k_off + c0;
@@ -720,12 +802,20 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
         return 0;
     }
     long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / perH)));
-    if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(perH * chunk))) return fail("out of device memory (heev workspace)");
+    const bool bigvec = evecs_d && bigvec_enabled(N) && !heev_generic_only;
+    if (bigvec) chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(BIGVEC_BUDGET / (perH + bigvec_bytes_per_matrix(N)))));
+    if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(bigvec ? bigvec_bytes_per_matrix(N) * chunk : perH * chunk)))
+        return fail("out of device memory (heev workspace)");
     const bool peel = !evecs_d && N > 64 && N <= PEEL_MAX && !heev_generic_only;
     if (peel && p->ws[2].S.ensure(peel_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
     for (long long c0 = 0; c0 < nm; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)nm - c0);
         CK(cudaMemcpyAsync(p->ws[2].H.p, (const cplx*)H_d + (size_t)c0 * N * N, perH * cnt, cudaMemcpyDeviceToDevice, st));
+        if (bigvec) {
+            int rc = launch_bigvec(p, (cplx*)p->ws[2].H.p, N, cnt, evals_d, nm, c0, (cplx*)evecs_d, (long long)nm * N, N, c0, 0, nullptr, p->ws[2].RT.p, st);
+            if (rc) return rc;
+            continue;
+        }
         HeevArgs a{};
         a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
         a.evals = evals_d; a.ld = nm; a.col0 = c0;
@@ -855,13 +945,15 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     const bool use_small = n_rows == 0 && p->small_ok && small::supports(N);
     const bool use_cta64 = n_rows == 0 && !use_small && N > 32 && N <= 64;     // eigenvalues only, register-resident CTA kernel
     const bool dos_fused = (use_vec64 || use_cta64) && c64_fusable(p, N, soc, gate);
+    const bool dos_bigvec = n_rows > 0 && !use_vec32 && !use_vec64 && bigvec_enabled(N);
     size_t per_k = (size_t)N * 8 + ((use_small || use_vec32 || dos_fused) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? small::cta64_bytes_per_k() : 0) +
-                   (use_vec32 ? small::vec32_bytes_per_k() : 0) + (use_vec64 ? small::vec64_bytes_per_k() : 0);
-    long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(WS_BUDGET / per_k)));
+                   (use_vec32 ? small::vec32_bytes_per_k() : 0) + (use_vec64 ? small::vec64_bytes_per_k() : 0) + (dos_bigvec ? bigvec_bytes_per_matrix(N) : 0);
+    long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)((dos_bigvec ? BIGVEC_BUDGET : WS_BUDGET) / per_k)));
     const int LOR_GRID = 148 * 4;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && !dos_fused && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k()
-                                                 : (use_vec64 ? (size_t)chunk * small::vec64_bytes_per_k() : (size_t)chunk * N * n_rows * 16)) ||
+                                                 : (use_vec64 ? (size_t)chunk * small::vec64_bytes_per_k()
+                                                              : (dos_bigvec ? (size_t)chunk * bigvec_bytes_per_matrix(N) : (size_t)chunk * N * n_rows * 16))) ||
                     p->wsVec.ensure((size_t)chunk * N * n_rows * 16))) ||
         (!k_d && !use_small && !use_vec32 && p->ws[2].K.ensure((size_t)chunk * 24)) || (gate && p->wsFlag.ensure((size_t)chunk * 4)) ||
         p->wsPart.ensure((size_t)LOR_GRID * ng * nE * 8))
@@ -904,7 +996,11 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = n_rows; a.rows = d_rows;
                 a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * n_rows; a.vs_k = n_rows; a.vcol0 = 0;
             }
-            if (use_vec64) {
+            if (dos_bigvec) {
+                rc = launch_bigvec(p, (cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, cnt, 0, (cplx*)p->wsVec.p, cnt * n_rows, n_rows, 0, n_rows, d_rows,
+                                   p->ws[2].RT.p, st);
+                if (rc) return rc;
+            } else if (use_vec64) {
                 int rl = small::launch_vec64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
                 if (rl < 0) return fail("vec64 launch failed: %s", g_kinfo.c_str());
                 g_launches += rl;
@@ -970,13 +1066,15 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
     const bool mid_path = N > 32 && N <= 64;
     const bool full_vec = nr > 0 && (small_path || mid_path);
     const int vstride = full_vec ? N : nr;
+    const bool sp_bigvec = nr > 0 && !small_path && !mid_path && bigvec_enabled(N);
     size_t per_k = (size_t)N * 8 + ((small_path) ? 0 : (size_t)N * N * 16) + (size_t)N * vstride * 32 + 4 +
-                   (small_path ? (nr ? small::vec32_bytes_per_k() : 1024) : 0) + (mid_path ? small::vec64_bytes_per_k() : 0);
-    long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(WS_BUDGET / per_k)));
+                   (small_path ? (nr ? small::vec32_bytes_per_k() : 1024) : 0) + (mid_path ? small::vec64_bytes_per_k() : 0) + (sp_bigvec ? bigvec_bytes_per_matrix(N) : 0);
+    long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)((sp_bigvec ? BIGVEC_BUDGET : WS_BUDGET) / per_k)));
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!small_path && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (nr && p->wsVec.ensure((size_t)chunk * N * vstride * 16)) ||
         (nr && p->ws[2].RT.ensure(small_path ? (size_t)chunk * small::vec32_bytes_per_k()
-                                             : (mid_path ? (size_t)chunk * small::vec64_bytes_per_k() : (size_t)chunk * N * nr * 16))) ||
+                                             : (mid_path ? (size_t)chunk * small::vec64_bytes_per_k()
+                                                         : (sp_bigvec ? (size_t)chunk * bigvec_bytes_per_matrix(N) : (size_t)chunk * N * nr * 16)))) ||
         (gate && p->wsFlag.ensure((size_t)chunk * 4)))
         return fail("out of device memory (spectral workspaces)");
     for (long long c0 = 0; c0 < nk; c0 += chunk) {
@@ -1020,6 +1118,10 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                 HeevArgs a{};
                 a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
                 a.evals = (double*)p->wsE.p; a.ld = cnt; a.col0 = 0;
+                if (sp_bigvec) {
+                    rc = launch_bigvec(p, (cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, cnt, 0, (cplx*)p->wsVec.p, cnt * nr, nr, 0, nr, d_rows, p->ws[2].RT.p, st);
+                    if (rc) return rc;
+                } else {
                 if (nr) {
                     a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = nr; a.rows = d_rows;
                     a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * nr; a.vs_k = nr; a.vcol0 = 0;
@@ -1029,6 +1131,7 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                 }
                 rc = launch_heev_generic(p, a, st);
                 if (rc) return rc;
+                }
             }
         }
         if (gate) { any_flag_kernel<<<64, 256, 0, st>>>(flags, cnt, p->d_any); LAUNCHED(); }

@@ -1,13 +1,21 @@
-"""Total energy of a tight-binding model (reference: pysktb/forces.py:367-425).
+"""Total energy and Hellmann-Feynman forces of a tight-binding model (reference: pysktb/forces.py).
 
-`get_total_energy`: the band energy runs on the device (mesh eigenvalues through the C ABI, reduced by
-`sktb_band_energy`), the repulsive pair energy is summed on the host exactly as the reference does.
+`get_total_energy` (forces.py:367-425): the band energy runs on the device (mesh eigenvalues through the C ABI, reduced
+by `sktb_band_energy`), the repulsive pair energy is summed on the host exactly as the reference does.
 
-`get_forces`: the reference's implementation raises TypeError as shipped, so its
-semantics are taken from its docstrings (forces.py:3-4, 43-58): F[a] = -dE_tot/dR_a in eV/Angstrom, shape
-(n_atoms, 3), E_tot = E_band + E_rep of `get_total_energy`.  Here the derivative is a central difference of that
-total energy over Cartesian displacements of one atom (6 n_atoms mesh solves, each one k-sharded device call), which
-includes every dependence of H(k) on the positions: scaling laws, direction cosines and the Bloch phases.
+`get_forces` (forces.py:43-72): the reference's implementation raises TypeError as shipped (SURVEY.md section 2, row 11:
+`get_hop_int() got an unexpected keyword argument 'repulsive'`, list arithmetic at :301-303), so its semantics are taken
+from its docstrings (forces.py:3-4, 43-58, 130, 145-149): F[a] = -dE_tot/dR_a in eV/Angstrom, shape (n_atoms, 3),
+    F_band[a] = - w sum_k sum_n f_n(k) <psi_n(k)| dH(k)/dR_a |psi_n(k)>     (x 2 for soc=False),   F = F_band + F_rep.
+Here this is ANALYTIC: the eigenvectors come from the device solver (sktb_solve), dH/dR from the exact gradient of the
+Slater-Koster tables (sktb_sk_table_grad: forward-mode differentiation of the same table code; the reference takes a
+forward difference with eps = 1e-6 over the direction cosines, forces.py:283-297), the chain rule through the distance
+laws (`ScalingLaw.deriv1`) and the Bloch phases exp(2 pi i k.d).  H(k) is read the way the eigensolver reads it (lower
+triangle, LAPACK UPLO='L'), so the forces are the exact derivative of the energies `get_total_energy` returns, also for
+the reference's non-Hermitian f-orbital blocks.  Occupations: at temperature = 0 the n lowest states of every k-point
+(the filling `get_total_energy` uses); at temperature > 0 Fermi-Dirac with the chemical potential that holds n_electrons
+on the mesh (or the caller's mu) - the forces are then the derivative of the Mermin free energy `get_free_energy`.
+`get_forces_numeric` keeps the central difference of the total energy (6 n_atoms re-built models) as a cross-check.
 """
 import numpy as np
 
@@ -67,12 +75,151 @@ class Forces:
                         e += float(rep(st.dist_mat[im, i, j]))
         return e
 
-    def get_forces(self, n_electrons, nk=[10, 10, 10], temperature=0.0, mu=None, soc=True, parallel=True, step=1e-4):
-        """-> f64 (n_atoms, 3), eV/Angstrom (forces.py:43-72 signature; `parallel` is accepted and ignored, the mesh
-        solve always runs on the device).  Zero electronic temperature only; `step` is the displacement in Angstrom
-        of the central difference (error O(step^2))."""
-        if temperature != 0.0 or mu is not None:
-            raise NotImplementedError("get_forces: only temperature=0 with the filling fixed by n_electrons")
+    # -- analytic Hellmann-Feynman forces ---------------------------------------------------------------
+    def _bond_gradients(self):
+        """Per directed bond b = (image, i, j): T_b [n_i, n_j] and dT_b/d(x,y,z) [3, n_i, n_j] with respect to the Cartesian
+        bond vector d_b = r_i(+image) - r_j, from the device (K4 with forward-mode gradients)."""
+        import torch
+        from .atom import Atom
+        from .scaling import ScalingLaw
+        ham, st, sy = self.ham, self.structure, self.system
+        names = _lib.v_names()
+        col = {n: i for i, n in enumerate(names)}
+        bl = ham._bonds
+        nb = len(bl)
+        V, dV, vec = np.zeros((nb, len(names))), np.zeros((nb, len(names))), np.zeros((nb, 3))
+        for b, (im, i, j) in enumerate(bl):
+            pair = sy._get_pair(st.atoms[i].element, st.atoms[j].element)
+            d = st.dist_mat[im, i, j]
+            for key, val in sy.params[pair].items():
+                if not key.startswith("V_"):
+                    continue
+                if isinstance(val, ScalingLaw):
+                    V[b, col[key]], dV[b, col[key]] = val(d), val.deriv1(d)
+                else:
+                    V[b, col[key]] = val
+            vec[b] = st.dist_mat_vec[im, i, j, :]
+        out = np.zeros((nb, 4, 17, 17))
+        if nb:
+            with torch.cuda.device(ham._device):
+                Vd, dVd, vd = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (V, dV, vec))
+                od = torch.empty((nb, 4, 17, 17), dtype=torch.float64, device="cuda")
+                _lib.check(_lib.lib().sktb_sk_table_grad(Vd.data_ptr(), dVd.data_ptr(), vd.data_ptr(), od.data_ptr(), nb, ham._stream()))
+                out = od.cpu().numpy()
+        kinds = [[Atom.ORBITALS_ALL.index(o) for o in a.orbitals] for a in st.atoms]
+        T = [out[b, 0][np.ix_(kinds[i], kinds[j])] for b, (im, i, j) in enumerate(bl)]
+        dT = [out[b, 1:][:, kinds[i]][:, :, kinds[j]] for b, (im, i, j) in enumerate(bl)]
+        return vec, T, dT
+
+    def _mesh_eigenpairs(self, kpts, soc):
+        """Device eigenvalues [N, nk] and eigenvectors [N, nk, N] (rows = eigenvectors) of the mesh, in k-chunks."""
+        ham = self.ham
+        N = self.n_orbitals * 2 if soc else self.n_orbitals
+        chunk = max(1, int(2e8 // (16 * N * N)))
+        vals, vecs = [], []
+        for c0 in range(0, len(kpts), chunk):
+            v, u = ham.solve_kpath(np.ascontiguousarray(kpts[c0:c0 + chunk]), eig_vectors=True, soc=soc)
+            vals.append(np.array(v)); vecs.append(np.array(u))
+        return np.concatenate(vals, axis=1), np.concatenate(vecs, axis=1)
+
+    @staticmethod
+    def _fermi(ev, mu, temperature):
+        x = np.clip((ev - mu) / temperature, -700.0, 700.0)
+        return 1.0 / (1.0 + np.exp(x))
+
+    def _occupations(self, ev, n_electrons, temperature, mu, soc):
+        """f[band, k] in [0, 1] per explicit state (soc=False: per spin-degenerate level, weight 2 applied by the caller)."""
+        N, nk = ev.shape
+        n_target = float(n_electrons) if soc else float(n_electrons) / 2.0
+        if temperature <= 0.0:
+            n_occ = min(int(n_electrons) if soc else int(n_electrons) // 2, N)      # forces.py:381-395: the same filling at every k
+            f = np.zeros_like(ev)
+            f[:n_occ, :] = 1.0
+            return f, None
+        if mu is None:
+            lo, hi = float(ev.min()) - 30.0 * temperature - 1.0, float(ev.max()) + 30.0 * temperature + 1.0
+            for _ in range(200):
+                mu = 0.5 * (lo + hi)
+                if self._fermi(ev, mu, temperature).sum() / nk > n_target:
+                    hi = mu
+                else:
+                    lo = mu
+                if hi - lo < 1e-14 * max(1.0, abs(mu)):
+                    break
+        return self._fermi(ev, mu, temperature), mu
+
+    def get_free_energy(self, n_electrons, nk=[10, 10, 10], temperature=0.0, mu=None, soc=True):
+        """-> (F, mu): Mermin free energy E_band - T S + E_rep at fixed electron number (the quantity whose derivative the
+        finite-temperature forces are); temperature = 0 gives `get_total_energy`'s E_total."""
+        kpts = self._get_kpoint_mesh(nk)
+        ev = np.array(self.ham.solve_kpath(np.ascontiguousarray(kpts), soc=bool(soc)))
+        f, mu_out = self._occupations(ev, n_electrons, temperature, mu, bool(soc))
+        g = 1.0 if soc else 2.0
+        e_band = g * float((f * ev).sum()) / len(kpts)
+        ts = 0.0
+        if temperature > 0.0:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ent = -(np.where(f > 0, f * np.log(f), 0.0) + np.where(f < 1, (1 - f) * np.log1p(-f), 0.0))
+            ts = g * temperature * float(ent.sum()) / len(kpts)
+        return e_band - ts + self._get_repulsive_energy(), mu_out
+
+    def _get_repulsive_forces(self):
+        """forces.py:320-365: -dE_rep/dR over bonded pairs i < j; the pair potential's `deriv1` (or a central difference)."""
+        f = np.zeros((self.n_atoms, 3))
+        st, sy = self.structure, self.system
+        for i in range(self.n_atoms):
+            for j in range(i + 1, self.n_atoms):
+                pair = sy._get_pair(st.atoms[i].element, st.atoms[j].element)
+                rep = sy.params[pair].get("repulsive") if pair in sy.params else None
+                if rep is None or not callable(rep):
+                    continue
+                for im in range(st.max_image):
+                    if st.bond_mat[im, i, j]:
+                        d = float(st.dist_mat[im, i, j])
+                        dv = float(rep.deriv1(d)) if hasattr(rep, "deriv1") else float((rep(d + 1e-6) - rep(d - 1e-6)) / 2e-6)
+                        u = st.dist_mat_vec[im, i, j, :] / d                      # d_vec = r_i(+image) - r_j
+                        f[i] -= dv * u
+                        f[j] += dv * u
+        return f
+
+    def get_forces(self, n_electrons, nk=[10, 10, 10], temperature=0.0, mu=None, soc=True, parallel=True):
+        """-> f64 (n_atoms, 3), eV/Angstrom (forces.py:43-72 signature; `parallel` is accepted and ignored: the mesh solve
+        runs on the device).  Analytic Hellmann-Feynman forces, see the module docstring."""
+        ham, st = self.ham, self.structure
+        soc = bool(soc)
+        kpts = np.asarray(self._get_kpoint_mesh(nk), dtype=float)
+        n_k = len(kpts)
+        ev, U = self._mesh_eigenpairs(kpts, soc)                    # U[band, k, comp]
+        f, _ = self._occupations(ev, n_electrons, float(temperature), mu, soc)
+        # occupied density matrix per k, folded to orbital space: rho[k, nu, mu] = sum_n f_n conj(U_n,nu) U_n,mu  (+ spins)
+        rho = np.einsum("nk,nka,nkb->kab", f, U.conj(), U, optimize=True)      # rho[k, a, b] = sum_n f conj(psi_a) psi_b
+        n = self.n_orbitals
+        if soc:
+            rho = rho[:, 0::2, 0::2] + rho[:, 1::2, 1::2]            # kron(h, I2): only equal spins see the hoppings
+        starts = ham._starts
+        vec, T, dT = self._bond_gradients()
+        kc = kpts @ st.lattice.get_rec_lattice()                     # hamiltonian.py:279-280
+        forces = np.zeros((self.n_atoms, 3))
+        g = (1.0 if soc else 2.0) / n_k
+        for b, (im, i, j) in enumerate(ham._bonds):
+            if i == j:
+                continue                                             # both ends move together: d_b does not change
+            ph = np.exp(2.0j * np.pi * (kc @ vec[b]))               # [nk]
+            ri, rj = np.arange(starts[i], starts[i + 1]), np.arange(starts[j], starts[j + 1])
+            low = (ri[:, None] > rj[None, :]).astype(float)          # the eigensolver reads the lower triangle:
+            dia = (ri[:, None] == rj[None, :]).astype(float)         #   A = tril(H,-1) + tril(H,-1)^H + Re diag(H)
+            r = rho[:, ri[:, None], rj[None, :]]                     # rho[k, mu, nu] = sum_n f conj(psi_mu) psi_nu
+            for a in range(3):
+                M = (dT[b][a][None, :, :] + (2.0j * np.pi * kc[:, a])[:, None, None] * T[b][None, :, :]) * ph[:, None, None]   # d(T e^{i phi})/d d_a
+                val = (2.0 * low + dia)[None] * (r * M).real
+                s = g * float(val.sum())
+                forces[i, a] -= s                                    # dd_b/dr_i = +1
+                forces[j, a] += s                                    # dd_b/dr_j = -1
+        return forces + self._get_repulsive_forces()
+
+    def get_forces_numeric(self, n_electrons, nk=[10, 10, 10], soc=True, step=1e-4):
+        """Central difference of `get_total_energy` over Cartesian displacements (6 n_atoms re-built models; error
+        O(step^2)): the cross-check of `get_forces` at temperature = 0."""
         from .atom import Atom
         from .structure import Structure
         from .hamiltonian import Hamiltonian

@@ -68,7 +68,11 @@ def lagts(a, b, c, d2, pin, y, tol):
         ak = a[k]
         if abs(ak) < tol:
             ak = tol if ak >= 0 else -tol
-        y[k] = t / ak
+        t = t / ak
+        if abs(t) > 1e150:          # exponentially localised vectors (edge states) span hundreds of decades: rescale the column
+            y *= 1e-150
+            t *= 1e-150
+        y[k] = t
     return y
 
 
@@ -92,7 +96,7 @@ def stein(d, e, w, seed=0, tight_rel=1e-7):
         if j > 0 and w[j] - w[j - 1] > tight:
             head = j
         if j > head:
-            pertol = 10.0 * abs(EPS * xj)
+            pertol = 10.0 * EPS * max(abs(xj), onenrm)      # ABSOLUTE floor: bisection to relative precision can return a pair +-1e-38
             if xj - xjm < pertol:
                 xj = xjm + pertol
         xjm = xj
@@ -108,7 +112,8 @@ def stein(d, e, w, seed=0, tight_rel=1e-7):
                 nrmchk += 1
                 if nrmchk >= 3:
                     break
-        Z[:, j] = x / np.linalg.norm(x)
+        mx = np.abs(x).max()
+        Z[:, j] = (x / mx) / np.linalg.norm(x / mx)
     Z2 = Z.copy()
     for j in range(n):
         lo = j
