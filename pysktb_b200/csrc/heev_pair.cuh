@@ -475,7 +475,10 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 2) pair_wide32_kernel(SmallAr
 
 // TAIL kernel: tridiagonalisation of the trailing 16x16 blocks (steps 16..30), two matrices per warp, d[16..31] and
 // e[16..30] into the (d,e) scratch.  Few registers: co-resides with the wide kernel of the next chunk.
-template <int S, bool VEC = false>
+// STOP8 (eigenvalue path): run only the two-slot phases (steps 16..23) and hand the trailing 8 x 8 block (updated through
+// step 23, column-major [q][i], 1 KB - written over the head of this matrix's own 4 KB input block) to tail8_thread_kernel:
+// the last 7 steps are all fixed per-step cost in a lane-group layout, and none in a one-matrix-per-thread layout.
+template <int S, bool VEC = false, bool STOP8 = false>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const cplx* __restrict__ blocks, double* __restrict__ scratch, long long nk,
                                                                           int out_stride, int d_off, int e_off, cplx* __restrict__ vstore = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -507,12 +510,40 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, 4) pair_tail16_kernel(const c
         PairCarry c;
         pair_prologue<16, VEC>(B, c, L, S_);
         int j = 0;
-        pair_phases<16, 8, 0, S, VEC>(B, c, j, L, S_);
+        pair_phases<16, 8, STOP8 ? 4 : 0, S, VEC>(B, c, j, L, S_);
         if (k_ok) {
             double* out = scratch + (size_t)kq * out_stride;
-            out[d_off + 16 + L.l] = S_.D[(L.l & 1) * 16 + L.l]; out[e_off + 16 + L.l] = c.eval;
+            out[d_off + 16 + L.l] = S_.D[(L.l & 1) * 16 + L.l]; out[e_off + 16 + L.l] = c.eval;      // STOP8: entries 8.. are rewritten by tail8
+            if (STOP8 && L.r < 8) {       // slot B = rows 15 - r = 8..15; registers 0..3 hold columns 8 + 2m + h (base = 8 after 8 steps)
+                cplx* b8 = const_cast<cplx*>(blk) + (7 - L.r);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) b8[(2 * m + L.h) * 8] = B[1][m];
+            }
         }
         __syncwarp();
+    }
+}
+
+// Steps 24..30 of the 32 x 32 reduction: one trailing 8 x 8 block per THREAD (thread_tridiag<8>, heev_thread.cuh): lower
+// triangle of the block pair_tail16<STOP8> left, d[24..31] and e[24..30] into the (d, e) record.
+template <int UNUSED>
+__global__ void __launch_bounds__(128) tail8_thread_kernel(const cplx* __restrict__ blocks, double* __restrict__ scratch, long long nk, int out_stride,
+                                                           int d_off, int e_off) {
+    for (long long kq = (long long)blockIdx.x * blockDim.x + threadIdx.x; kq < nk; kq += (long long)gridDim.x * blockDim.x) {
+        const cplx* blk = blocks + (size_t)kq * 256;
+        cplx A[36];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int i = j; i < 8; ++i) A[i * (i + 1) / 2 + j] = blk[j * 8 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) A[i * (i + 1) / 2 + i].y = 0.0;
+        double d[8], e[8];
+        thread_tridiag<8>(A, d, e);
+        double* out = scratch + (size_t)kq * out_stride;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { out[d_off + 24 + i] = d[i]; out[e_off + 24 + i] = e[i]; }
     }
 }
 

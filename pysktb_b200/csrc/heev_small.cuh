@@ -712,6 +712,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) tql_merge_kernel(const doubl
     }
 }
 
+template <int NC> SKTB_D void thread_tridiag(cplx (&A)[NC * (NC + 1) / 2], double (&d)[NC], double (&e)[NC]);   // heev_thread.cuh
 #include "heev_pair.cuh"
 #include "heev_thread.cuh"
 #include "heev_cta64.cuh"
@@ -831,7 +832,12 @@ static int launch_pair(const LaunchCtx& c) {
     constexpr int SRC = SOC ? PAIR_SRC_SOC : PAIR_SRC_NOSOC;
     if (mode == 0) kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, true> : pair_wide32_kernel<SRC, 4, true>;
     else kW = pair_s == 8 ? pair_wide32_kernel<SRC, 8, false> : pair_wide32_kernel<SRC, 4, false>;
-    void (*kT)(const cplx*, double*, long long, int, int, int, cplx*) = tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>;
+    // SKTB_TAIL8=1: one-matrix-per-thread stage for the last 8 x 8 block (pair_tail16 stops after its two-slot phases).
+    // Measured (same box, T 256^3): 3.69e7 k/s against 3.76e7 with all 15 tail steps in pair_tail16 - the 1 KB per-thread
+    // block hand-off and the 196-register thread kernel cost more than the 7 lane-group steps they replace; kept as a knob.
+    static const bool tail8 = getenv("SKTB_TAIL8") && getenv("SKTB_TAIL8")[0] == '1';
+    void (*kT)(const cplx*, double*, long long, int, int, int, cplx*) =
+        tail8 ? (tail_s == 8 ? pair_tail16_kernel<8, false, true> : pair_tail16_kernel<4, false, true>) : (tail_s == 8 ? pair_tail16_kernel<8> : pair_tail16_kernel<4>);
     const int tql_mode = tql_mode_env();
     void (*kB)(TqlArgs) = tql_mode == 2 ? tql_small_kernel<NC, 32, 2> : (tql_mode == 1 ? tql_small_kernel<NC, 32, 1> : tql_small_kernel<NC, 32, 0>);
     if (smemW > 48 * 1024 && cudaFuncSetAttribute(kW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW) != cudaSuccess) {
@@ -880,6 +886,10 @@ static int launch_pair(const LaunchCtx& c) {
             gridT = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 1) / 2 + PAIR_WARPS - 1) / PAIR_WARPS, (long long)sms * 8));
             kT<<<gridT, PAIR_WARPS * 32, smemT, sT>>>(blocks, de, cnt, 2 * NC, 0, NC, nullptr);
             ++launches;
+            if (tail8) {
+                tail8_thread_kernel<0><<<(unsigned)std::max<long long>(1, std::min<long long>((cnt + 127) / 128, (long long)sms * 8)), 128, 0, sT>>>(blocks, de, cnt, 2 * NC, 0, NC);
+                ++launches;
+            }
         }
         TqlArgs t{de, cnt, N, c.evals, c.ld, c.col0 + c0, c.fail};
         gridB = (unsigned)std::max<long long>(1, std::min<long long>(((cnt + 31) / 32 + SMALL_WARPS - 1) / SMALL_WARPS, (long long)sms * occB));
@@ -895,8 +905,8 @@ static int launch_pair(const LaunchCtx& c) {
         if (ci >= 2) cudaStreamWaitEvent(c.st, ps->evDone[(int)(ci % nbuf)], 0);
     }
     char buf[400];
-    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,S=%d,mode=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + pair_tail16 grid=%u smem=%zuB + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
-             (int)SOC, pair_s, mode, gridW, WWr * 32, smemW, occW, gridT, smemT, gridB, smemB, occB, N, chunk);
+    snprintf(buf, sizeof buf, "pair_wide32<soc=%d,S=%d,mode=%d> grid=%u x %d thr smem=%zuB %d CTA/SM + pair_tail16%s grid=%u smem=%zuB + tql_small grid=%u smem=%zuB %d CTA/SM; N=%d, chunk=%lld k",
+             (int)SOC, pair_s, mode, gridW, WWr * 32, smemW, occW, tail8 ? "<stop8> + tail8_thread" : "", gridT, smemT, gridB, smemB, occB, N, chunk);
     *c.info = buf;
     return launches;
 }

@@ -142,3 +142,36 @@ def test_thread_per_matrix_equals_lane_group_kernels(tmp_path):
     for key in res["0"].files:
         if not key.endswith("_info"):
             np.testing.assert_allclose(res["0"][key], res["1"][key], rtol=0, atol=1e-12, err_msg=key)
+
+
+TAIL8_CHECK = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pysktb_b200 as tb
+from pysktb_b200 import workloads as W
+out = {}
+for name, spec in (("T", W.ce_spdf_1atom()), ("ce13", W.ce_partial(n_orb=13)), ("zz16", W.zigzag_ribbon(n_chains=16))):
+    _, ham = W.instantiate(spec, tb, tb.scaling)
+    k = np.random.default_rng(2).random((777, 3)) * 2 - 0.5
+    out[name] = ham.solve_kpath(list(k), soc=spec["soc"])
+    out[name + "_mesh"] = ham.solve_kmesh([9, 7, 5], soc=spec["soc"]).cpu().numpy()
+    out[name + "_info"] = np.array(ham.last_kernel_info())
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_tail8_thread_stage_equals_lane_group_tail(tmp_path):
+    """24 < N <= 32 eigenvalue path: the one-matrix-per-thread stage for the trailing 8 x 8 block (default) against the
+    lane-group tail kernel doing all 15 steps (SKTB_TAIL8=0)."""
+    import numpy as np
+    res = {}
+    for knob in ("1", "0"):
+        env = dict(os.environ, SKTB_TAIL8=knob)
+        f = str(tmp_path / f"tail8_{knob}.npz")
+        r = subprocess.run([sys.executable, "-c", TAIL8_CHECK % ROOT, f], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[knob] = np.load(f)
+    assert "tail8_thread" in str(res["1"]["T_info"]) and "tail8_thread" not in str(res["0"]["T_info"]), (str(res["1"]["T_info"]), str(res["0"]["T_info"]))
+    for key in res["0"].files:
+        if not key.endswith("_info"):
+            np.testing.assert_allclose(res["1"][key], res["0"][key], rtol=0, atol=1e-12, err_msg=key)
