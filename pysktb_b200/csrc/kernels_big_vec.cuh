@@ -108,13 +108,14 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
             w[tid] = lam;
         }
         __syncthreads();
-        // ---- inverse iteration inside the block.  Two levels: TIGHT clusters (gaps <= 1e-7 ||T||) are computed by the thread of
-        //      their first eigenvalue, one vector after the other, with modified Gram-Schmidt inside the iteration (dstein);
-        //      everything else independently, one thread per eigenvector, followed by ONE first-order symmetric (Loewdin)
-        //      correction over the LOOSE cluster (gaps <= 1e-3 ||T||, dstein's criterion): independent inverse iterations are
-        //      orthogonal to ~eps ||T|| / gap <= 2e-9 there, the correction squares that.  (A serial dstein over the loose
-        //      clusters of a dense 512-level spectrum would leave one thread with tens of vectors and O(c^2 N) work.) ----
-        const double ortol = 1.0e-3 * onenrm, tight = 1.0e-7 * onenrm;
+        // ---- inverse iteration inside the block.  Two levels: TIGHT clusters (gaps <= 1e-10 ||T||: degeneracies that survive the
+        //      block splitting) are computed by the thread of their first eigenvalue, one vector after the other, with modified
+        //      Gram-Schmidt inside the iteration (dstein); everything else independently, one thread per eigenvector, followed
+        //      by TWO first-order symmetric (Loewdin) corrections over the PAIRWISE window |w_m - w_n| <= 2e-4 ||T||:
+        //      independent inverse iterations overlap by ~eps ||T|| / gap (below 1e-12 outside the window, up to 2e-6 inside),
+        //      each correction squares the overlap of a window.  (dstein's serial Gram-Schmidt over its 1e-3 ||T|| clusters
+        //      would leave one thread with tens of vectors for the dense spectrum of a 512-orbital ribbon.) ----
+        const double ptol = 2.0e-4 * onenrm, tight = 1.0e-10 * onenrm;
         const double tol = onenrm > 0.0 ? eps * onenrm : eps;
         const bool head = tid < N && (tid == b0 || w[tid] - w[tid - 1] > tight);
         if (tid < N) for (int i = 0; i < N; ++i) if (i < b0 || i > b1) Zm[(size_t)i * N + tid] = 0.0;
@@ -219,24 +220,36 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
             }
         }
         __syncthreads();
-        // ---- global ascending rank (ties by index), Loewdin correction over the loose cluster of the block; the corrected
-        //      vector goes to column `rank` of the (now free) first factor array = the final Z, the eigenvalue to evals[rank] ----
+        // ---- two Loewdin passes (Zm -> Lb -> final), global ascending rank (ties by index): the corrected vector goes to
+        //      column `rank` of the (now free) first factor array = the final Z, the eigenvalue to evals[rank] ----
+        int wlo = tid, whi = tid;
+        if (tid < N) {
+            const int j = tid;
+            while (wlo > b0 && w[j] - w[wlo - 1] <= ptol) --wlo;
+            while (whi < b1 && w[whi + 1] - w[j] <= ptol) ++whi;
+            for (int i = 0; i < N; ++i) Lb[(size_t)i * N + j] = Zm[(size_t)i * N + j];
+            for (int m = wlo; m <= whi; ++m) {
+                if (m == j) continue;
+                double dot = 0.0;
+                for (int i = b0; i <= b1; ++i) dot = fma(Zm[(size_t)i * N + m], Zm[(size_t)i * N + j], dot);
+                const double h = -0.5 * dot;
+                for (int i = b0; i <= b1; ++i) Lb[(size_t)i * N + j] = fma(h, Zm[(size_t)i * N + m], Lb[(size_t)i * N + j]);
+            }
+        }
+        __syncthreads();
         if (tid < N) {
             const int j = tid;
             const double wj = w[j];
             int rank = 0;
             for (int m = 0; m < N; ++m) { const double wm = w[m]; rank += (wm < wj) || (wm == wj && m < j); }
             a.evals[(long long)rank * a.ld + a.col0 + mat] = wj;
-            int lo = j, hi = j;
-            while (lo > b0 && w[lo] - w[lo - 1] <= ortol) --lo;
-            while (hi < b1 && w[hi + 1] - w[hi] <= ortol) ++hi;
-            for (int i = 0; i < N; ++i) La[(size_t)i * N + rank] = Zm[(size_t)i * N + j];
-            for (int m = lo; m <= hi; ++m) {
+            for (int i = 0; i < N; ++i) La[(size_t)i * N + rank] = Lb[(size_t)i * N + j];
+            for (int m = wlo; m <= whi; ++m) {
                 if (m == j) continue;
                 double dot = 0.0;
-                for (int i = b0; i <= b1; ++i) dot = fma(Zm[(size_t)i * N + m], Zm[(size_t)i * N + j], dot);
+                for (int i = b0; i <= b1; ++i) dot = fma(Lb[(size_t)i * N + m], Lb[(size_t)i * N + j], dot);
                 const double h = -0.5 * dot;
-                for (int i = b0; i <= b1; ++i) La[(size_t)i * N + rank] = fma(h, Zm[(size_t)i * N + m], La[(size_t)i * N + rank]);
+                for (int i = b0; i <= b1; ++i) La[(size_t)i * N + rank] = fma(h, Lb[(size_t)i * N + m], La[(size_t)i * N + rank]);
             }
         }
     }

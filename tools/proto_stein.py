@@ -76,7 +76,7 @@ def lagts(a, b, c, d2, pin, y, tol):
     return y
 
 
-def stein(d, e, w, seed=0, tight_rel=1e-7):
+def stein(d, e, w, seed=0, tight_rel=1e-10):
     """Two-level scheme of the kernel: TIGHT clusters (gaps <= tight_rel ||T||) are computed one vector after the other
     with modified Gram-Schmidt inside the iteration (dstein); everything else independently (one thread each), followed by
     ONE first-order symmetric (Loewdin) correction x_n -= 1/2 sum_m (x_m.x_n) x_m over the LOOSE cluster (gaps <= 1e-3
@@ -114,17 +114,20 @@ def stein(d, e, w, seed=0, tight_rel=1e-7):
                     break
         mx = np.abs(x).max()
         Z[:, j] = (x / mx) / np.linalg.norm(x / mx)
-    Z2 = Z.copy()
-    for j in range(n):
-        lo = j
-        while lo > 0 and w[lo] - w[lo - 1] <= ortol:
-            lo -= 1
-        hi = j
-        while hi < n - 1 and w[hi + 1] - w[hi] <= ortol:
-            hi += 1
-        for m in range(lo, hi + 1):
-            if m != j:
-                Z2[:, j] -= 0.5 * (Z[:, m] @ Z[:, j]) * Z[:, m]
+    ptol = 2e-4 * onenrm          # PAIRWISE window: the overlap of two independent vectors is ~eps ||T|| / |gap|, below 1e-12 beyond it
+    for sweep in range(2):        # two passes: E -> ~(c E)^2 -> ~(c E)^4 for a window of c vectors
+        Z2 = Z.copy()
+        for j in range(n):
+            lo = j
+            while lo > 0 and w[j] - w[lo - 1] <= ptol:
+                lo -= 1
+            hi = j
+            while hi < n - 1 and w[hi + 1] - w[j] <= ptol:
+                hi += 1
+            for m in range(lo, hi + 1):
+                if m != j:
+                    Z2[:, j] -= 0.5 * (Z[:, m] @ Z[:, j]) * Z[:, m]
+        Z = Z2
     return Z2
 
 
