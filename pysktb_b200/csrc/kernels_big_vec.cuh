@@ -257,27 +257,29 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
 
 // U = H_0 ... H_{N-2} Z for BW eigenvectors per CTA (one per warp); NQ = ceil(N / 32) components per lane.
 constexpr int VBT_PANEL = 8;        // reflectors staged per shared-memory panel
-template <int NQ, int BW>
-__global__ void __launch_bounds__(BW * 32, NQ <= 16 ? 2 : 1) vecbt_big_kernel(BigVecArgs a) {
+// EV eigenvectors per warp: every reflector entry read from shared memory feeds EV dot products and EV updates (with one
+// vector per warp the kernel is shared-memory-bandwidth bound: ncu showed the LSU data pipe 75 % busy against 49 % FP64).
+template <int NQ, int BW, int EV>
+__global__ void __launch_bounds__(BW * 32, (NQ * EV <= 16) ? 2 : 1) vecbt_big_kernel(BigVecArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cplx* Vp = reinterpret_cast<cplx*>(smem_raw);                         // [VBT_PANEL][NQ * 32] reflector panel
     cplx* tp = Vp + (size_t)VBT_PANEL * NQ * 32;                          // [VBT_PANEL] tau
-    static_assert(BW <= VBT_PANEL, "the staging of finished eigenvectors aliases the reflector panel");
-    cplx* ub = Vp;                                                        // [BW][NQ * 32] staging of finished eigenvectors (row selection)
-    const int groups = (N + BW - 1) / BW;
+    const int groups = (N + BW * EV - 1) / (BW * EV);
     for (long long work = blockIdx.x; work < a.nm * groups; work += gridDim.x) {
         const long long mat = work / groups;
-        const int n = (int)(work - mat * groups) * BW + warp;             // this warp's eigenvector
-        const bool live = n < N;
+        const int n0 = ((int)(work - mat * groups) * BW + warp) * EV;     // this warp's first eigenvector
         const double* Zm = a.lu + (size_t)mat * 4 * N * N;               // stein_kernel's final (corrected) vectors
         const cplx* Vs = a.vstore + (size_t)mat * N * N;
         const cplx* Ts = a.taustore + (size_t)mat * N;
-        cplx u[NQ];
+        cplx u[EV][NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int i = 32 * q + lane;
-            u[q] = cmake((live && i < N) ? Zm[(size_t)i * N + n] : 0.0, 0.0);
+        for (int ev = 0; ev < EV; ++ev) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int i = 32 * q + lane;
+                u[ev][q] = cmake((n0 + ev < N && i < N) ? Zm[(size_t)i * N + n0 + ev] : 0.0, 0.0);
+            }
         }
         // reflectors N-2 ... 0 in panels of VBT_PANEL (descending)
         for (int jhi = N - 2; jhi >= 0; jhi -= VBT_PANEL) {
@@ -292,44 +294,47 @@ __global__ void __launch_bounds__(BW * 32, NQ <= 16 ? 2 : 1) vecbt_big_kernel(Bi
             const int q0 = (jlo + 1) >> 5;                                // components below 32 q0 are untouched by this panel
             for (int s = np - 1; s >= 0; --s) {
                 const cplx* v = Vp + (size_t)s * NQ * 32 + lane;
-                constexpr bool KEEP = NQ <= 8;                             // larger NQ: the reflector is re-read for the update (two CTAs per SM)
+                constexpr bool KEEP = NQ * EV <= 8;                        // else the reflector is re-read for the update (registers)
                 constexpr int NR = KEEP ? NQ : 1;
                 cplx vr[NR];
-                cplx dacc[4];                                               // four independent chains: the single accumulator was a
-#pragma unroll                                                              // 2 NQ-deep dependent DFMA chain per reflector
-                for (int c = 0; c < 4; ++c) dacc[c] = cmake(0.0, 0.0);
+                cplx dacc[EV][2];                                           // independent chains (a single accumulator is a 2 NQ-deep
+#pragma unroll                                                              // dependent DFMA chain per reflector)
+                for (int ev = 0; ev < EV; ++ev) dacc[ev][0] = dacc[ev][1] = cmake(0.0, 0.0);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    if (q >= q0) { const cplx vq = v[32 * q]; if (KEEP) vr[q % NR] = vq; cfmac(dacc[q & 3], vq, u[q]); }      // v^H u
+                    if (q >= q0) {
+                        const cplx vq = v[32 * q];
+                        if (KEEP) vr[q % NR] = vq;
+#pragma unroll
+                        for (int ev = 0; ev < EV; ++ev) cfmac(dacc[ev][q & 1], vq, u[ev][q]);                        // v^H u
+                    }
                 }
-                cplx dot = cadd(cadd(dacc[0], dacc[1]), cadd(dacc[2], dacc[3]));
+                cplx wv[EV];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o); }
-                const cplx wv = cmul(tp[s], dot);
+                for (int ev = 0; ev < EV; ++ev) {
+                    cplx dot = cadd(dacc[ev][0], dacc[ev][1]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o); }
+                    wv[ev] = cmul(tp[s], dot);
+                }
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    if (q >= q0) cfms(u[q], wv, KEEP ? vr[q % NR] : v[32 * q]);           // u -= tau (v^H u) v
+                    if (q >= q0) {
+                        const cplx vq = KEEP ? vr[q % NR] : v[32 * q];
+#pragma unroll
+                        for (int ev = 0; ev < EV; ++ev) cfms(u[ev][q], wv[ev], vq);                                  // u -= tau (v^H u) v
+                    }
                 }
             }
         }
-        // ---- output: the reference's [band, k, component] layout, or the selected components only ----
-        if (a.n_rows == 0) {
-            if (live) {
-                cplx* out = a.vec_out + (long long)n * a.vs_band + (a.vcol0 + mat) * a.vs_k;
+        // ---- output: the reference's [band, k, component] layout ----
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) { const int i = 32 * q + lane; if (i < N) out[i] = u[q]; }
-            }
-        } else {
-            __syncthreads();                                               // every warp is done with the last reflector panel
-            cplx* mine = ub + (size_t)warp * NQ * 32;
+        for (int ev = 0; ev < EV; ++ev) {
+            if (n0 + ev < N) {
+                cplx* out = a.vec_out + (long long)(n0 + ev) * a.vs_band + (a.vcol0 + mat) * a.vs_k;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) mine[32 * q + lane] = u[q];
-            __syncwarp();
-            if (live) {
-                cplx* out = a.vec_out + (long long)n * a.vs_band + (a.vcol0 + mat) * a.vs_k;
-                for (int r = lane; r < a.n_rows; r += 32) out[r] = mine[a.rows[r]];
+                for (int q = 0; q < NQ; ++q) { const int i = 32 * q + lane; if (i < N) out[i] = u[ev][q]; }
             }
-            __syncwarp();
         }
     }
 }

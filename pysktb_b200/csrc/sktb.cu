@@ -491,11 +491,14 @@ template <int NQ>
 static int launch_vecbt_big(const BigVecArgs& b, cudaStream_t st, int sms) {
     constexpr int BW = 8;
     const size_t smem = vecbt_big_smem(NQ);
-    void (*kern)(BigVecArgs) = b.n_rows > 0 ? rowsq_big_kernel<NQ, BW> : vecbt_big_kernel<NQ, BW>;     // selected rows of U only | all of U
+    constexpr int EV = NQ == 8 ? 2 : 1;          // eigenvectors per warp (SKTB_VBT_EV=1: one). Measured: N=256 1.73e4 -> 2.02e4 matrices/s; N=512 (234 registers, one CTA per SM) slower
+    static const bool ev1 = getenv("SKTB_VBT_EV") && getenv("SKTB_VBT_EV")[0] == '1';
+    void (*kern)(BigVecArgs) = b.n_rows > 0 ? rowsq_big_kernel<NQ, BW> : (ev1 ? vecbt_big_kernel<NQ, BW, 1> : vecbt_big_kernel<NQ, BW, EV>);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BW * 32, smem);
-    const long long work = b.nm * (((b.n_rows > 0 ? b.n_rows : b.N) + BW - 1) / BW);
+    const int per_cta = b.n_rows > 0 ? BW : BW * (ev1 ? 1 : EV);
+    const long long work = b.nm * (((b.n_rows > 0 ? b.n_rows : b.N) + per_cta - 1) / per_cta);
     kern<<<(unsigned)std::max<long long>(1, std::min<long long>(work, (long long)sms * std::max(occ, 1))), BW * 32, smem, st>>>(b);
     LAUNCHED();
     return 0;
