@@ -102,6 +102,14 @@ int sktb_solve_mesh(sktb_plan* plan, const int32_t nk_mesh[3], int64_t first, in
 int sktb_heev(sktb_plan* plan, const double* H_d, int32_t N, int64_t nm, double* evals_d, double* evecs_d,
               int32_t* nonherm_d, void* stream);
 
+/* Diagnostic entry of the two-stage tridiagonalisation that sktb_heev / sktb_solve* use for eigenvalues of large matrices
+ * (N >= 352 by default; csrc/heev_twostage.cuh): stage 1 reduces H to a Hermitian band of width 16 (blocked Householder,
+ * GEMMs on the FP64 tensor instruction), stage 2 chases the band to tridiagonal form.  Same input convention as sktb_heev.
+ * band_d NULL or [nm][N][32] complex: band after stage 1, band[j][d] = A[j+d][j] (d <= 16, rest zero);
+ * de_d NULL or [nm][2][N]: diagonal and sub-diagonal of the tridiagonal matrix.  Used by the parity tests to check each
+ * stage against LAPACK (the eigenvalues of the band and of the tridiagonal equal those of H).                          */
+int sktb_heev_twostage(sktb_plan* plan, const double* H_d, int32_t N, int64_t nm, double* band_d, double* de_d, void* stream);
+
 /* Host-buffer front end of sktb_solve: pinned staging, H2D of k / compute / D2H of results overlapped in
  * chunks on internal streams.  k_h [nk][3], evals_h [N][nk], evecs_h NULL or [N][nk][N] are HOST pointers.
  * *nonherm_any = 1 if any k tripped the Hermiticity gate.  Synchronous.                                      */

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "sktb_solve_mesh": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_void_p]),
     "sktb_heev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sktb_heev_twostage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sktb_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, c_i32p]),
     "sktb_dos": (C.c_int, [C.c_void_p, C.c_void_p, c_i32p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_double,
                            C.c_int32, c_i32p, c_i32p, C.c_void_p, c_i32p, C.c_void_p]),

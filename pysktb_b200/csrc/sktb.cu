@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "sk_table.cuh"
 #include "kernels_generic.cuh"
+#include "heev_twostage.cuh"
 #include "kernels_big_vec.cuh"
 #include "heev_small.cuh"
 
@@ -464,7 +465,36 @@ static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     return 0;
 }
 
+// Two-stage tridiagonalisation (heev_twostage.cuh: dense -> band 16 on DMMA, band -> tridiagonal by bulge chasing) + bisection:
+// eigenvalues only, N >= SKTB_TWOSTAGE_MIN.  The one-stage kernels read the trailing matrix once per reflector and are HBM-bound
+// from N ~ 300 up; here the matrix is read twice and written once per 16 reflectors.
+static int twostage_min() { static const int v = getenv("SKTB_TWOSTAGE_MIN") ? atoi(getenv("SKTB_TWOSTAGE_MIN")) : 352; return v; }
+static bool use_twostage(int N) { return N >= twostage_min() && twostage::supported(N); }
+// scratch per matrix of the eigenvalues-only paths above N = 64 (HeevArgs::peel_ws): peeled run or two-stage
+static size_t evals_ws_bytes_per_k(int N) {
+    if (N <= 64) return 0;
+    if (use_twostage(N)) return twostage::scratch_bytes_per_matrix(N);
+    return N <= PEEL_MAX ? peel_bytes_per_k(N) : 0;
+}
+static int launch_heev_twostage(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+    const int N = a.N;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(a.peel_ws);
+    double* de = reinterpret_cast<double*>(ws + (size_t)a.nm * (twostage::scratch_bytes_per_matrix(N) - (size_t)2 * N * sizeof(double)));
+    char info[320];
+    const int rl = twostage::launch_tridiag(a.H, N, a.nm, ws, de, st, info, sizeof info);
+    if (rl < 0) return fail("two-stage tridiagonalisation does not support N = %d", N);
+    g_launches += rl;
+    { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail("two-stage launch: %s", cudaGetErrorString(e_)); }
+    const int T = (N + 31) / 32 * 32;
+    const size_t smem = ((size_t)2 * N + 96) * sizeof(double);
+    bisect_merge_kernel<<<(unsigned)std::min<long long>(a.nm, 148LL * 8), T, smem, st>>>(de, N, de, 0, a.nm, a.evals, a.ld, a.col0);
+    LAUNCHED();
+    g_kinfo = std::string(info) + " | bisect_merge";
+    return 0;
+}
+
 static int launch_heev_generic(sktb_plan* p, HeevArgs a, cudaStream_t st) {
+    if (a.n_rows == 0 && !a.vstore && a.peel_ws && use_twostage(a.N)) return launch_heev_twostage(p, a, st);
     if (a.n_rows == 0 && a.peel_ws && a.N > 64 && a.N <= PEEL_MAX) return launch_heev_peel(p, a, st);
     static const bool no_split = getenv("SKTB_GENERIC_SPLIT") != nullptr && getenv("SKTB_GENERIC_SPLIT")[0] == '0';
     if (a.n_rows > 0 && a.N > 64 && a.N <= 1024 && !no_split) {
@@ -672,8 +702,8 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
         if (bigvec) chunk = std::max<long long>(1, std::min<long long>(nk, (long long)(BIGVEC_BUDGET / (perH + bigvec_bytes_per_matrix(N)))));
         if (W.H.ensure(perH * chunk)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
         if (want_vecs && W.RT.ensure(bigvec ? bigvec_bytes_per_matrix(N) * chunk : perH * chunk)) return fail("out of device memory (RT workspace)");
-        const bool peel = !want_vecs && N > 64 && N <= PEEL_MAX;
-        if (peel && W.S.ensure(peel_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
+        const bool peel = !want_vecs && evals_ws_bytes_per_k(N) > 0;
+        if (peel && W.S.ensure(evals_ws_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
         if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
         for (long long c0 = 0; c0 < nk; c0 += chunk) {
             long long cnt = std::min(chunk, nk - c0);
@@ -809,8 +839,8 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
     if (bigvec) chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(BIGVEC_BUDGET / (perH + bigvec_bytes_per_matrix(N)))));
     if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(bigvec ? bigvec_bytes_per_matrix(N) * chunk : perH * chunk)))
         return fail("out of device memory (heev workspace)");
-    const bool peel = !evecs_d && N > 64 && N <= PEEL_MAX && !heev_generic_only;
-    if (peel && p->ws[2].S.ensure(peel_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
+    const bool peel = !evecs_d && evals_ws_bytes_per_k(N) > 0 && !heev_generic_only;
+    if (peel && p->ws[2].S.ensure(evals_ws_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
     for (long long c0 = 0; c0 < nm; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)nm - c0);
         CK(cudaMemcpyAsync(p->ws[2].H.p, (const cplx*)H_d + (size_t)c0 * N * N, perH * cnt, cudaMemcpyDeviceToDevice, st));
@@ -829,6 +859,36 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
         }
         int rc = launch_heev_generic(p, a, st);
         if (rc) return rc;
+    }
+    return 0;
+}
+
+// Diagnostic / test entry of the two-stage tridiagonalisation (heev_twostage.cuh): band_d (NULL or [nm][N][32] complex) receives
+// the band matrix after stage 1, AB[j][d] = A[j+d][j], d <= 16; de_d (NULL or [nm][2][N]) the tridiagonal after stage 2.
+extern "C" int sktb_heev_twostage(sktb_plan* p, const double* H_d, int32_t N, int64_t nm, double* band_d, double* de_d, void* stream) {
+    if (!p || !H_d) return fail("null argument");
+    if (!twostage::supported(N)) return fail("two-stage tridiagonalisation: N = %d is not supported (32 <= N, panel must fit shared memory)", N);
+    if (nm <= 0) return 0;
+    ON_DEVICE(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t perH = (size_t)N * N * sizeof(cplx), perS = twostage::scratch_bytes_per_matrix(N);
+    const long long chunk = std::max<long long>(1, std::min<long long>(nm, (long long)(WS_BUDGET / perH)));
+    if (p->ws[2].H.ensure(perH * chunk) || p->ws[2].S.ensure(perS * chunk)) return fail("out of device memory (two-stage workspace)");
+    for (long long c0 = 0; c0 < nm; c0 += chunk) {
+        const long long cnt = std::min(chunk, (long long)nm - c0);
+        CK(cudaMemcpyAsync(p->ws[2].H.p, (const cplx*)H_d + (size_t)c0 * N * N, perH * cnt, cudaMemcpyDeviceToDevice, st));
+        unsigned char* ws = reinterpret_cast<unsigned char*>(p->ws[2].S.p);
+        double* de = reinterpret_cast<double*>(ws + (size_t)cnt * (perS - (size_t)2 * N * sizeof(double)));
+        char info[320];
+        if (twostage::launch_tridiag((cplx*)p->ws[2].H.p, N, cnt, ws, de, st, info, sizeof info, 1) < 0) return fail("two-stage stage 1 launch failed");
+        LAUNCHED();
+        if (band_d) CK(cudaMemcpyAsync((cplx*)band_d + (size_t)c0 * N * twostage::ABW, twostage::band_of(ws), (size_t)cnt * N * twostage::ABW * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+        if (de_d) {
+            if (twostage::launch_tridiag((cplx*)p->ws[2].H.p, N, cnt, ws, de, st, info, sizeof info, 2) < 0) return fail("two-stage stage 2 launch failed");
+            LAUNCHED();
+            CK(cudaMemcpyAsync(de_d + (size_t)c0 * 2 * N, de, (size_t)cnt * 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+        g_kinfo = info;
     }
     return 0;
 }
@@ -1013,8 +1073,8 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 if (rl < 0) return fail("cta64 launch failed: %s", g_kinfo.c_str());
                 g_launches += rl;
             } else {
-                if (!n_rows && N > 64 && N <= PEEL_MAX) {
-                    if (p->ws[2].S.ensure((size_t)cnt * peel_bytes_per_k(N))) return fail("out of device memory (peel workspace)");
+                if (!n_rows && evals_ws_bytes_per_k(N) > 0) {
+                    if (p->ws[2].S.ensure((size_t)cnt * evals_ws_bytes_per_k(N))) return fail("out of device memory (peel workspace)");
                     a.peel_ws = p->ws[2].S.p;
                 }
                 rc = launch_heev_generic(p, a, st);
@@ -1128,8 +1188,8 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                 if (nr) {
                     a.RT = (cplx*)p->ws[2].RT.p; a.n_rows = nr; a.rows = d_rows;
                     a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * nr; a.vs_k = nr; a.vcol0 = 0;
-                } else if (N > 64 && N <= PEEL_MAX) {
-                    if (p->ws[2].S.ensure((size_t)cnt * peel_bytes_per_k(N))) return fail("out of device memory (peel workspace)");
+                } else if (evals_ws_bytes_per_k(N) > 0) {
+                    if (p->ws[2].S.ensure((size_t)cnt * evals_ws_bytes_per_k(N))) return fail("out of device memory (peel workspace)");
                     a.peel_ws = p->ws[2].S.p;
                 }
                 rc = launch_heev_generic(p, a, st);
