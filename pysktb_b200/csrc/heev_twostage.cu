@@ -17,11 +17,11 @@ int launch_tridiag(cplx* H, int N, long long nm, void* scratch, double* de, cuda
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
     Stage1Args a1{};
     a1.H = H; a1.N = N; a1.nm = nm; a1.NR = NR;
-    a1.mp = (((N - SB + 7) / 8) * 8) | 1;
+    a1.mp = stage1_mp(N);
     a1.AB = reinterpret_cast<cplx*>(base);                 base += (size_t)nm * N * ABW * sizeof(cplx);
-    a1.Vg = reinterpret_cast<cplx*>(base);                 base += (size_t)nm * NR * SB * sizeof(cplx);
-    a1.Vt = reinterpret_cast<cplx*>(base);                 base += (size_t)nm * NR * SB * sizeof(cplx);
+    a1.Yp = reinterpret_cast<cplx*>(base);                 base += (size_t)nm * YP_MAX * NR * SB * sizeof(cplx);
     a1.Wg = reinterpret_cast<cplx*>(base);                 base += (size_t)nm * NR * SB * sizeof(cplx);
+    a1.Gg = reinterpret_cast<cplx*>(base);                 base += (size_t)nm * S1_WARPS * SB * SB * sizeof(cplx);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -31,13 +31,38 @@ int launch_tridiag(cplx* H, int N, long long nm, void* scratch, double* de, cuda
     if (stages & 1) stage1_kernel<<<grid1, S1_THREADS, smem1, st>>>(a1);
     Stage2Args a2{};
     a2.AB = a1.AB; a2.N = N; a2.nm = nm; a2.de = de;
-    const size_t smem2 = (size_t)S2_WARPS * 3 * SB * sizeof(cplx) + (size_t)N * sizeof(int);
-    const unsigned grid2 = (unsigned)std::min<long long>(nm, 2LL * sms);
+    const size_t smem2 = stage2_smem_bytes(N);
+    if (smem2 > 48 * 1024 && cudaFuncSetAttribute(stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) return -1;
+    int occ2 = 2;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, stage2_kernel, S2_WARPS * 32, smem2);
+    const unsigned grid2 = (unsigned)std::min<long long>(nm, (long long)std::max(occ2, 1) * sms);
     if (stages & 2) stage2_kernel<<<grid2, S2_WARPS * 32, smem2, st>>>(a2);
     if (info) snprintf(info, info_len, "two-stage: stage1_kernel (band %d, DMMA) grid=%u x %d thr smem=%zuB + stage2_kernel (bulge chase) grid=%u x %d thr",
                        SB, grid1, S1_THREADS, smem1, grid2, S2_WARPS * 32);
     return ((stages & 1) ? 1 : 0) + ((stages & 2) ? 1 : 0);
 }
 
+int launch_bisect(const double* de, int N, long long nm, double* evals, long long ld, long long col0, cudaStream_t st) {
+    if (N > 1024 || nm <= 0) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int T = (N + 31) / 32 * 32;
+    const size_t smem = ((size_t)2 * N + 96) * sizeof(double);
+    bisect_prod_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, smem, st>>>(de, N, nm, evals, ld, col0);
+    return 1;
+}
+
 }  // namespace twostage
 }  // namespace sktb
+
+#ifdef SKTB_TS_PROFILE
+// profile builds only (make TSPROF=1): phase clocks of stage1_kernel, read and reset
+extern "C" int sktb_ts_profile(unsigned long long* out32) {
+    cudaDeviceSynchronize();
+    unsigned long long z[32] = {0};
+    cudaMemcpyFromSymbol(out32, sktb::twostage::g_s1_prof, sizeof(z));
+    cudaMemcpyToSymbol(sktb::twostage::g_s1_prof, z, sizeof(z));
+    return 0;
+}
+#endif

@@ -26,24 +26,28 @@ constexpr int ABW = 2 * SB;       // stored diagonals per column (d = 0 .. 2 SB 
 constexpr int S1_WARPS = 16;
 constexpr int S1_THREADS = S1_WARPS * 32;
 
+constexpr int YP_MAX = 8;        // column parts of the X = A V product (load balance; partial sums go through global memory)
+
 struct Stage1Args {
     cplx* H; int N; long long nm;   // [nm][N][N] row-major, lower triangle read (zheevd UPLO='L'), destroyed
     cplx* AB;                       // [nm][N][ABW]
-    cplx* Vg; cplx* Vt; cplx* Wg;   // [nm][NR][SB] each (NR = N rounded up to 8): V, V T and X / W of the current panel
-    int NR, mp;                     // mp: column stride of the panel in shared memory (odd)
+    cplx* Yp;                       // [nm][YP_MAX][NR][SB]: partial products A22 V per column part
+    cplx* Wg;                       // [nm][NR][SB]: X = A22 V T, then W
+    cplx* Gg;                       // [nm][S1_WARPS][SB*SB]: per-warp partial sums of G = V^H X
+    int NR, mp;                     // NR = N rounded up to 8; mp: column stride of the panel in shared memory (odd)
 };
 struct Stage2Args {
     cplx* AB; int N; long long nm;
     double* de;                     // [nm][2][N]: d, then e (N - 1 entries)
 };
 
+SKTB_HD int stage1_mp(int N) { return (((N - SB + 7) / 8) * 8) | 1; }
 SKTB_HD size_t stage1_smem_bytes(int N) {
-    const int mp = (((N - SB + 7) / 8) * 8) | 1;
-    return ((size_t)SB * mp + 3 * SB * SB + (size_t)S1_WARPS * SB * SB + 4 * SB) * sizeof(cplx) + 64;
+    return ((size_t)(SB + 2) * stage1_mp(N) + 4 * SB * SB + 3 * SB) * sizeof(cplx) + 64;
 }
 SKTB_HD size_t scratch_bytes_per_matrix(int N) {
     const size_t NR = (size_t)(N + 7) / 8 * 8;
-    return ((size_t)N * ABW + 3 * NR * SB) * sizeof(cplx) + (size_t)2 * N * sizeof(double);
+    return ((size_t)N * ABW + (YP_MAX + 1) * NR * SB + (size_t)S1_WARPS * SB * SB) * sizeof(cplx) + (size_t)2 * N * sizeof(double);
 }
 
 // host: stage 1 + stage 2 on `nm` matrices; de[mat][2][N] receives the tridiagonal.  scratch: nm * scratch_bytes_per_matrix(N).
@@ -52,6 +56,8 @@ SKTB_HD size_t scratch_bytes_per_matrix(int N) {
 int launch_tridiag(cplx* H, int N, long long nm, void* scratch, double* de, cudaStream_t st, char* info, size_t info_len, int stages = 3);
 inline cplx* band_of(void* scratch) { return reinterpret_cast<cplx*>(scratch); }
 bool supported(int N);
+// eigenvalues of the tridiagonal matrices de[mat][2][N] by bisection (product-form Sturm sequence), ascending: evals[n*ld + col0 + mat]
+int launch_bisect(const double* de, int N, long long nm, double* evals, long long ld, long long col0, cudaStream_t st);
 
 #if defined(__CUDACC__) && defined(SKTB_TWOSTAGE_KERNELS)      // the kernels live in heev_twostage.cu only
 // D(8x8) += A(8x4) B(4x8) in FP64; lane = 4 g + q: a = A[g][q], b = B[q][g], c0/c1 = C[g][2q], C[g][2q+1]
@@ -62,10 +68,75 @@ SKTB_D double dneg(double x) { return __hiloint2double(__double2hiint(x) ^ 0x800
 SKTB_D cplx ldcg(const cplx* p) { return __ldcg(p); }
 SKTB_D cplx cwarp_sum(cplx v) { return cmake(warp_sum(v.x), warp_sum(v.y)); }
 
+// zlarfg without the safmin loop, reciprocal square root / reciprocal by hardware seed + Newton (full double precision)
+SKTB_D void fast_householder(cplx alpha, double xnorm2, double& beta, cplx& tau, cplx& scale) {
+    if (xnorm2 == 0.0 && alpha.y == 0.0) { beta = alpha.x; tau = cmake(0.0, 0.0); scale = cmake(0.0, 0.0); return; }
+    const double n2 = alpha.x * alpha.x + alpha.y * alpha.y + xnorm2;
+    const double irt = fast_rsqrt(n2);
+    const double nrm = n2 * irt;
+    const bool neg = alpha.x >= 0.0;
+    beta = neg ? -nrm : nrm;
+    const double ib = neg ? -irt : irt;                                   // 1 / beta
+    tau = cmake((beta - alpha.x) * ib, -alpha.y * ib);
+    const double dx = alpha.x - beta, dy = alpha.y;
+    const double id = fast_rcp(dx * dx + dy * dy);
+    scale = cmake(dx * id, -dy * id);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 1
 // ---------------------------------------------------------------------------------------------------------------------
+// X tile (8 rows x 16 columns, complex) += A-operand (two k-steps a0, a1; CONJ: use conj(a)) times the B-operand rows
+// 8J+2q, 8J+2q+1 of V (shared memory, column-major: V[row][n] = Ps[n*mp + row])
+template <bool CONJ>
+SKTB_D void s1_xtile(double (&Xr)[2][2], double (&Xi)[2][2], double (&Zr)[2][2], double (&Zi)[2][2], cplx a0, cplx a1,
+                     const cplx* __restrict__ Ps, int mp, int rowB, int g) {
+    // X = Xr + Zr + i (Xi + Zi): the two k-steps accumulate into separate registers (8 independent DMMA chains per warp)
+    const cplx* bp = Ps + (size_t)g * mp + rowB;
+    const cplx b00 = bp[0], b10 = bp[1], b01 = bp[(size_t)8 * mp], b11 = bp[(size_t)8 * mp + 1];
+    const double a0i = CONJ ? a0.y : dneg(a0.y), a0j = CONJ ? dneg(a0.y) : a0.y;     // Xr += a.x b.x + a0i b.y ; Xi += a.x b.y + a0j b.x
+    const double a1i = CONJ ? a1.y : dneg(a1.y), a1j = CONJ ? dneg(a1.y) : a1.y;
+    dmma(Xr[0][0], Xr[0][1], a0.x, b00.x); dmma(Xi[0][0], Xi[0][1], a0.x, b00.y);
+    dmma(Xr[1][0], Xr[1][1], a0.x, b01.x); dmma(Xi[1][0], Xi[1][1], a0.x, b01.y);
+    dmma(Zr[0][0], Zr[0][1], a1.x, b10.x); dmma(Zi[0][0], Zi[0][1], a1.x, b10.y);
+    dmma(Zr[1][0], Zr[1][1], a1.x, b11.x); dmma(Zi[1][0], Zi[1][1], a1.x, b11.y);
+    dmma(Xr[0][0], Xr[0][1], a0i, b00.y);  dmma(Xi[0][0], Xi[0][1], a0j, b00.x);
+    dmma(Xr[1][0], Xr[1][1], a0i, b01.y);  dmma(Xi[1][0], Xi[1][1], a0j, b01.x);
+    dmma(Zr[0][0], Zr[0][1], a1i, b10.y);  dmma(Zi[0][0], Zi[0][1], a1j, b10.x);
+    dmma(Zr[1][0], Zr[1][1], a1i, b11.y);  dmma(Zi[1][0], Zi[1][1], a1j, b11.x);
+}
+
+// rank-2k tile update helpers: P = V_I W_J^H + W_I V_J^H accumulated as Pr (real part), Pp - Pm (imaginary part)
+SKTB_D void s1_r2k(double (&Pr)[2], double (&Pp)[2], double (&Pm)[2], double (&Qr)[2], double (&Qp)[2], double (&Qm)[2], cplx vI, cplx wI,
+                   cplx v2, cplx w2) {
+    dmma(Pr[0], Pr[1], vI.x, w2.x); dmma(Pp[0], Pp[1], vI.y, w2.x); dmma(Pm[0], Pm[1], vI.x, w2.y);
+    dmma(Qr[0], Qr[1], wI.x, v2.x); dmma(Qp[0], Qp[1], wI.y, v2.x); dmma(Qm[0], Qm[1], wI.x, v2.y);
+    dmma(Pr[0], Pr[1], vI.y, w2.y); dmma(Qr[0], Qr[1], wI.y, v2.y);
+}
+SKTB_D void s1_prefetch(const cplx* A22, const cplx* Wg, int N, int m, int I, int J, int g, int q, cplx& c0, cplx& c1, cplx& w0, cplx& w1,
+                        cplx& w2, cplx& w3) {
+    const int row = 8 * I + g, col = 8 * J + 2 * q;
+    const cplx* cp = A22 + (size_t)row * N + col;
+    c0 = (row < m && col < m) ? ldcg(cp) : cmake(0.0, 0.0);
+    c1 = (row < m && col + 1 < m) ? ldcg(cp + 1) : cmake(0.0, 0.0);
+    const cplx* wj = Wg + (size_t)(8 * J + g) * SB + 2 * q;      // k index of (q, s) = 2q + (s & 1) + 8 (s >> 1)
+    w0 = wj[0]; w1 = wj[1]; w2 = wj[8]; w3 = wj[9];
+}
+
+#ifdef SKTB_TS_PROFILE
+__device__ unsigned long long g_s1_prof[32];
+#define S1_MARK(i) { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_s1_prof[i], (unsigned long long)(now_ - tmark_)); tmark_ = now_; } }
+#define S1_WMARK(i) { if (lane == 0) { const long long now_ = clock64(); atomicAdd(&g_s1_prof[i], (unsigned long long)(now_ - wmark_)); } }
+#define S1_WSTART() { wmark_ = clock64(); }
+#else
+#define S1_MARK(i)
+#define S1_WMARK(i)
+#define S1_WSTART()
+#endif
 __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
+#ifdef SKTB_TS_PROFILE
+    long long tmark_ = clock64(), wmark_ = 0;
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, mp = a.mp, NR = a.NR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -73,19 +144,18 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
     cplx* Ps = reinterpret_cast<cplx*>(smem_raw);            // [SB][mp] panel, column-major; V after the QR
     cplx* Ts = Ps + (size_t)SB * mp;                         // [SB][SB] T (upper triangular), Ts[k*SB+n]
     cplx* Rs = Ts + SB * SB;                                 // [SB][SB] R, Rs[r*SB+c]
-    cplx* Ss = Rs + SB * SB;                                 // [SB][SB] G, then S = T^H G
-    cplx* Gp = Ss + SB * SB;                                 // [S1_WARPS][SB*SB] per-warp partials of G
-    cplx* dots = Gp + (size_t)S1_WARPS * SB * SB;            // [SB]
-    cplx* zs = dots + SB;                                    // [SB]
-    cplx* taus = zs + SB;                                    // [SB]
-    cplx* scs = taus + SB;                                   // [SB] scale of column c (the betas go straight into the diagonal of Rs)
+    cplx* Ss = Rs + SB * SB;                                 // [SB][SB] G, then 1/2 S = 1/2 T^H G
+    cplx* Zs = Ss + SB * SB;                                 // [SB][SB] Zs[w*SB+c] = V_w^H v_c (w < c), for T
+    cplx* dots = Zs + SB * SB;                               // [2][SB] raw dots with the pivot column (double-buffered)
+    cplx* taus = dots + 2 * SB;                              // [SB]
+    cplx* shadow = taus + SB;                                // [2][mp] the current pivot column, updated and unscaled
 
     for (long long mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
         cplx* A = a.H + (size_t)mat * N * N;
         cplx* AB = a.AB + (size_t)mat * N * ABW;
-        cplx* Vg = a.Vg + (size_t)mat * NR * SB;
-        cplx* Vt = a.Vt + (size_t)mat * NR * SB;
+        cplx* Yp = a.Yp + (size_t)mat * YP_MAX * NR * SB;
         cplx* Wg = a.Wg + (size_t)mat * NR * SB;
+        cplx* Gg = a.Gg + (size_t)mat * S1_WARPS * SB * SB;
         int c0 = 0;
         for (;; c0 += SB) {
             const int m = N - c0 - SB;                       // rows below the band of this panel
@@ -93,76 +163,99 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
             const int mr = (m + 7) / 8 * 8;
             const int nt = mr / 8;
             cplx* A22 = A + (size_t)(c0 + SB) * N + (c0 + SB);
-            // ---- 1. panel -> shared memory (column-major) ----
+            // ---- 1. panel -> shared memory (column-major), rows m .. mr-1 zero ----
             __syncthreads();
-            for (int idx = tid; idx < m * SB; idx += S1_THREADS) {
+            S1_MARK(0)
+            for (int idx = tid; idx < mr * SB; idx += S1_THREADS) {
                 const int r = idx >> 4, c = idx & 15;
-                Ps[(size_t)c * mp + r] = ldcg(A + (size_t)(c0 + SB + r) * N + c0 + c);
+                Ps[(size_t)c * mp + r] = r < m ? ldcg(A + (size_t)(c0 + SB + r) * N + c0 + c) : cmake(0.0, 0.0);
             }
-            for (int idx = tid; idx < 3 * SB * SB; idx += S1_THREADS) Ts[idx] = cmake(0.0, 0.0);   // T, R, S
+            for (int idx = tid; idx < 4 * SB * SB; idx += S1_THREADS) Ts[idx] = cmake(0.0, 0.0);   // T, R, S, Z
             __syncthreads();
-            // ---- 2. Householder QR of the panel, one warp per column ----
+            S1_MARK(1)
+            // ---- 2. Householder QR of the panel, one warp per column, ONE barrier per column: after the barrier every warp knows
+            //         the reflector of column c (alpha, norm from the dots), updates its own column and - with the updated pivot
+            //         column c+1 recomputed on the fly from the not-yet-overwritten data - accumulates the dot it needs for step c+1.
+            //         The pivot column lives in a shadow buffer (warp c+1 writes it there), R entries go straight to Rs. ----
             cplx* myc = Ps + (size_t)warp * mp;
             const int ncol = m < SB ? m : SB;                 // columns that have a diagonal row
-            for (int c = 0; c < ncol; ++c) {
-                const cplx* pc = Ps + (size_t)c * mp;
-                if (c > 0 && warp == c - 1) {                 // finalise column c-1: V entries below the diagonal
-                    const cplx sc = scs[c - 1];
-                    for (int r = c + lane; r < m; r += 32) myc[r] = cmul(myc[r], sc);
-                    if (lane < c - 1) { Rs[lane * SB + (c - 1)] = myc[lane]; }
-                    __syncwarp();
-                    if (lane < c - 1) myc[lane] = cmake(0.0, 0.0);
-                    if (lane == 0) myc[c - 1] = cmake(1.0, 0.0);
-                    __syncwarp();
-                }
-                // raw_w = sum_{r>c} conj(P[r][c]) P[r][w]
-                cplx acc = cmake(0.0, 0.0);
-                for (int r = c + 1 + lane; r < m; r += 32) cfmac(acc, pc[r], myc[r]);
-                acc = cwarp_sum(acc);
+            {
+                if (warp == 0) for (int r = lane; r < m; r += 32) shadow[r] = Ps[r];
+                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
+                int r = 1 + lane;
+                for (; r + 32 < m; r += 64) { cfmac(acc, Ps[r], myc[r]); cfmac(acc2, Ps[r + 32], myc[r + 32]); }
+                if (r < m) cfmac(acc, Ps[r], myc[r]);
+                acc = cwarp_sum(cadd(acc, acc2));
                 if (lane == 0) dots[warp] = acc;
-                __syncthreads();
-                const cplx alpha = pc[c];
+            }
+            __syncthreads();
+            for (int c = 0; c < ncol; ++c) {
+                const cplx* pc = shadow + (size_t)(c & 1) * mp;
+                cplx* nxt = shadow + (size_t)((c + 1) & 1) * mp;
+                const cplx* D = dots + (c & 1) * SB;
+                cplx* Dn = dots + ((c + 1) & 1) * SB;
+                const bool has_next = c + 1 < ncol;
                 double beta; cplx tau, scale;
-                householder(alpha, dots[c].x, beta, tau, scale);
+                fast_householder(pc[c], D[c].x, beta, tau, scale);
                 const cplx ctau = cconj(tau);
-                const cplx mydot = dots[warp];              // (dots is rewritten only after the barrier that ends this step)
+                const cplx* pn = Ps + (size_t)(c + 1) * mp;                           // column c+1 before this step's update
+                cplx csn = cmake(0.0, 0.0);
+                if (has_next) csn = cmul(cmul(ctau, cadd(pn[c], cmulc(scale, D[c + 1]))), scale);
+                cplx acc = cmake(0.0, 0.0);
                 if (warp > c) {
-                    const cplx s = cadd(myc[c], cmulc(scale, mydot));            // v^H a_w = a_w[c] + conj(scale) raw_w
-                    const cplx coef = cmul(ctau, s);
+                    const cplx coef = cmul(ctau, cadd(myc[c], cmulc(scale, D[warp])));   // conj(tau) v^H a_w
                     const cplx cs2 = cmul(coef, scale);
-                    for (int r = c + 1 + lane; r < m; r += 32) cfms(myc[r], cs2, pc[r]);
-                    __syncwarp();
-                    if (lane == 0) myc[c] = csub(myc[c], coef);
-                } else if (warp < c) {
-                    if (lane == 0) zs[warp] = cadd(cconj(myc[c]), cmul(scale, cconj(mydot)));   // V_w^H v_c
+                    if (lane == 0) Rs[c * SB + warp] = csub(myc[c], coef);
+                    if (warp == c + 1) {
+                        for (int r = c + 1 + lane; r < m; r += 32) {
+                            cplx an = myc[r]; cfms(an, cs2, pc[r]);
+                            nxt[r] = an;
+                            if (r > c + 1) acc.x += an.x * an.x + an.y * an.y;
+                        }
+                    } else {
+                        for (int r = c + 1 + lane; r < m; r += 32) {
+                            const cplx pr = pc[r];
+                            cplx aw = myc[r]; cfms(aw, cs2, pr);
+                            myc[r] = aw;
+                            if (has_next && r > c + 1) { cplx an = pn[r]; cfms(an, csn, pr); cfmac(acc, an, aw); }
+                        }
+                    }
+                } else if (warp == c) {
+                    for (int r = c + 1 + lane; r < m; r += 32) {
+                        const cplx pr = pc[r];
+                        const cplx vr = cmul(pr, scale);
+                        myc[r] = vr;
+                        if (has_next && r > c + 1) { cplx an = pn[r]; cfms(an, csn, pr); cfmac(acc, an, vr); }
+                    }
+                    if (lane < c) myc[lane] = cmake(0.0, 0.0);
+                    if (lane == 0) { myc[c] = cmake(1.0, 0.0); taus[c] = tau; Rs[c * SB + c] = cmake(beta, 0.0); }
                 } else {
-                    if (lane == 0) { taus[c] = tau; scs[c] = scale; Rs[c * SB + c] = cmake(beta, 0.0); }
+                    if (lane == 0) Zs[warp * SB + c] = cadd(cconj(myc[c]), cmul(scale, cconj(D[warp])));   // V_w^H v_c
+                    if (has_next)
+                        for (int r = c + 2 + lane; r < m; r += 32) { cplx an = pn[r]; cfms(an, csn, pc[r]); cfmac(acc, an, myc[r]); }
+                }
+                if (has_next) {
+                    acc = cwarp_sum(acc);
+                    if (lane == 0) Dn[warp] = acc;
                 }
                 __syncthreads();
-                // T[:c][c] = -tau T[:c][:c] z, T[c][c] = tau
-                if (tid < c) {
-                    cplx t = cmake(0.0, 0.0);
-                    for (int k = tid; k < c; ++k) cfma(t, Ts[tid * SB + k], zs[k]);
-                    Ts[tid * SB + c] = cmul(cmake(-tau.x, -tau.y), t);
-                } else if (tid == c) Ts[c * SB + c] = tau;
             }
-            __syncthreads();
-            // finalise the columns the loop has not: w >= ncol - 1
-            if (warp >= ncol - 1) {
-                if (warp < ncol) {                            // last column with a diagonal row
-                    const cplx sc = scs[warp];
-                    for (int r = warp + 1 + lane; r < m; r += 32) myc[r] = cmul(myc[r], sc);
-                    if (lane < warp) Rs[lane * SB + warp] = myc[lane];
+            // columns without a diagonal row (m < SB) are R only: their V column is zero
+            if (warp >= ncol) for (int r = lane; r < m; r += 32) myc[r] = cmake(0.0, 0.0);
+            if (ncol < SB) __syncthreads();                   // (uniform) the zeroed columns are operands of step 4
+            // T[:c][c] = -tau_c T[:c][:c] z_c, T[c][c] = tau_c (warp 0; the band output below overlaps with it)
+            if (warp == 0) {
+                for (int c = 0; c < ncol; ++c) {
+                    const cplx tau = taus[c];
+                    if (lane < c) {
+                        cplx t = cmake(0.0, 0.0);
+                        for (int k = lane; k < c; ++k) cfma(t, Ts[lane * SB + k], Zs[k * SB + c]);
+                        Ts[lane * SB + c] = cmul(cmake(-tau.x, -tau.y), t);
+                    } else if (lane == c) Ts[c * SB + c] = tau;
                     __syncwarp();
-                    if (lane < warp) myc[lane] = cmake(0.0, 0.0);
-                    if (lane == 0) myc[warp] = cmake(1.0, 0.0);
-                } else {                                      // no diagonal row (m < SB): the column is R, V column is zero
-                    if (lane < m) Rs[lane * SB + warp] = myc[lane];
-                    __syncwarp();
-                    if (lane < m) myc[lane] = cmake(0.0, 0.0);
                 }
             }
-            __syncthreads();
+            S1_MARK(2)
             // ---- 3. band output of the 16 columns of this panel: diagonal block (lower) + R; the rest of the column is zero ----
             {
                 const int c = tid >> 5, d = tid & 31;
@@ -177,100 +270,130 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                 }
                 AB[(size_t)j * ABW + d] = val;
             }
-            // ---- 4. V and V~ = V T to global memory, row-major [row][16] ----
-            for (int r = tid; r < mr; r += S1_THREADS) {
-                cplx v[SB];
-#pragma unroll
-                for (int k = 0; k < SB; ++k) v[k] = r < m ? Ps[(size_t)k * mp + r] : cmake(0.0, 0.0);
-#pragma unroll
-                for (int k = 0; k < SB; ++k) Vg[(size_t)r * SB + k] = v[k];
-#pragma unroll
-                for (int n = 0; n < SB; ++n) {
-                    cplx t = cmake(0.0, 0.0);
-#pragma unroll
-                    for (int k = 0; k <= n; ++k) cfma(t, v[k], Ts[k * SB + n]);
-                    Vt[(size_t)r * SB + n] = t;
+            S1_MARK(3)
+            S1_WSTART()
+            // ---- 4. Y = A22 V (lower triangle of A22 read: tile (I,J) for J <= I, tile (J,I)^H for J > I).  Work units: (row tile
+            //         I, column part p) dealt round-robin to the warps; P parts so that the last round is nearly full ----
+            int P = 1;
+            {
+                int best = 1 << 30;
+                for (int pp = 1; pp <= YP_MAX && pp <= nt; ++pp) {
+                    const int units = nt * pp, rounds = (units + S1_WARPS - 1) / S1_WARPS;
+                    const int idle = (rounds * S1_WARPS - units) * 1024 / (rounds * S1_WARPS) + pp * 8;   // idle share (x1024) + a price per part
+                    if (idle < best) { best = idle; P = pp; }
                 }
             }
-            __syncthreads();
-            // ---- 5. X = A22 V~ (lower triangle of A22 read: tile (I,J) for J <= I, tile (J,I)^H for J > I) ----
-            const int np = (nt + 1) / 2;
-            for (int pi = warp; pi < np; pi += S1_WARPS) {
-                for (int half = 0; half < 2; ++half) {
-                    const int I = half ? nt - 1 - pi : pi;
-                    if (half && I == pi) break;
-                    double Xr[2][2] = {{0, 0}, {0, 0}}, Xi[2][2] = {{0, 0}, {0, 0}};
-                    const int row = 8 * I + g;
-                    const bool rok = row < m;
-                    // row orientation, J < I
-#pragma unroll 2
-                    for (int J = 0; J < I; ++J) {
-                        const cplx* ap = A22 + (size_t)row * N + 8 * J + 2 * q;
-                        cplx a0 = rok ? ldcg(ap) : cmake(0.0, 0.0), a1 = rok ? ldcg(ap + 1) : cmake(0.0, 0.0);
-                        const cplx* bp = Vt + (size_t)(8 * J + 2 * q) * SB + g;
-                        const cplx b00 = bp[0], b01 = bp[8], b10 = bp[SB], b11 = bp[SB + 8];
-                        dmma(Xr[0][0], Xr[0][1], a0.x, b00.x); dmma(Xr[0][0], Xr[0][1], dneg(a0.y), b00.y);
-                        dmma(Xi[0][0], Xi[0][1], a0.x, b00.y); dmma(Xi[0][0], Xi[0][1], a0.y, b00.x);
-                        dmma(Xr[1][0], Xr[1][1], a0.x, b01.x); dmma(Xr[1][0], Xr[1][1], dneg(a0.y), b01.y);
-                        dmma(Xi[1][0], Xi[1][1], a0.x, b01.y); dmma(Xi[1][0], Xi[1][1], a0.y, b01.x);
-                        dmma(Xr[0][0], Xr[0][1], a1.x, b10.x); dmma(Xr[0][0], Xr[0][1], dneg(a1.y), b10.y);
-                        dmma(Xi[0][0], Xi[0][1], a1.x, b10.y); dmma(Xi[0][0], Xi[0][1], a1.y, b10.x);
-                        dmma(Xr[1][0], Xr[1][1], a1.x, b11.x); dmma(Xr[1][0], Xr[1][1], dneg(a1.y), b11.y);
-                        dmma(Xi[1][0], Xi[1][1], a1.x, b11.y); dmma(Xi[1][0], Xi[1][1], a1.y, b11.x);
-                    }
-                    // diagonal tile
-                    {
-                        cplx av[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int col = 8 * I + 2 * q + e;
-                            cplx x = cmake(0.0, 0.0);
-                            if (row < m && col < m) {
-                                if (row > col) x = ldcg(A22 + (size_t)row * N + col);
-                                else if (row < col) x = cconj(ldcg(A22 + (size_t)col * N + row));
-                                else x = cmake(ldcg(A22 + (size_t)row * N + row).x, 0.0);
-                            }
-                            av[e] = x;
+            for (int u = warp; u < nt * P; u += S1_WARPS) {
+                const int I = u / P, p = u - I * P;
+                const int J0 = (int)((long long)p * nt / P), J1 = (int)((long long)(p + 1) * nt / P);
+                double Xr[2][2] = {{0, 0}, {0, 0}}, Xi[2][2] = {{0, 0}, {0, 0}}, Zr[2][2] = {{0, 0}, {0, 0}}, Zi[2][2] = {{0, 0}, {0, 0}};
+                const int row = 8 * I + g;
+                const bool rok = row < m;
+                // row orientation, J < I (columns < 8I <= m - 1: no column guard)
+                {
+                    const int Ja = J0, Jb = J1 < I ? J1 : I;
+                    const cplx* ap = A22 + (size_t)row * N + 2 * q;
+                    const cplx z = cmake(0.0, 0.0);
+                    // three tiles in flight, each buffer re-loaded right after its use (no register rotation: a move out of a
+                    // register with a pending load would wait for that load)
+                    cplx n0 = z, n1 = z, f0 = z, f1 = z, h0 = z, h1 = z;
+                    if (Ja < Jb && rok) { n0 = ldcg(ap + 8 * Ja); n1 = ldcg(ap + 8 * Ja + 1); }
+                    if (Ja + 1 < Jb && rok) { f0 = ldcg(ap + 8 * Ja + 8); f1 = ldcg(ap + 8 * Ja + 9); }
+                    if (Ja + 2 < Jb && rok) { h0 = ldcg(ap + 8 * Ja + 16); h1 = ldcg(ap + 8 * Ja + 17); }
+                    for (int J = Ja; J < Jb; J += 3) {
+                        s1_xtile<false>(Xr, Xi, Zr, Zi, n0, n1, Ps, mp, 8 * J + 2 * q, g);
+                        if (J + 3 < Jb && rok) { n0 = ldcg(ap + 8 * J + 24); n1 = ldcg(ap + 8 * J + 25); }
+                        if (J + 1 < Jb) {
+                            s1_xtile<false>(Xr, Xi, Zr, Zi, f0, f1, Ps, mp, 8 * J + 8 + 2 * q, g);
+                            if (J + 4 < Jb && rok) { f0 = ldcg(ap + 8 * J + 32); f1 = ldcg(ap + 8 * J + 33); }
                         }
-                        const cplx* bp = Vt + (size_t)(8 * I + 2 * q) * SB + g;
-                        const cplx b00 = bp[0], b01 = bp[8], b10 = bp[SB], b11 = bp[SB + 8];
-                        const cplx a0 = av[0], a1 = av[1];
-                        dmma(Xr[0][0], Xr[0][1], a0.x, b00.x); dmma(Xr[0][0], Xr[0][1], dneg(a0.y), b00.y);
-                        dmma(Xi[0][0], Xi[0][1], a0.x, b00.y); dmma(Xi[0][0], Xi[0][1], a0.y, b00.x);
-                        dmma(Xr[1][0], Xr[1][1], a0.x, b01.x); dmma(Xr[1][0], Xr[1][1], dneg(a0.y), b01.y);
-                        dmma(Xi[1][0], Xi[1][1], a0.x, b01.y); dmma(Xi[1][0], Xi[1][1], a0.y, b01.x);
-                        dmma(Xr[0][0], Xr[0][1], a1.x, b10.x); dmma(Xr[0][0], Xr[0][1], dneg(a1.y), b10.y);
-                        dmma(Xi[0][0], Xi[0][1], a1.x, b10.y); dmma(Xi[0][0], Xi[0][1], a1.y, b10.x);
-                        dmma(Xr[1][0], Xr[1][1], a1.x, b11.x); dmma(Xr[1][0], Xr[1][1], dneg(a1.y), b11.y);
-                        dmma(Xi[1][0], Xi[1][1], a1.x, b11.y); dmma(Xi[1][0], Xi[1][1], a1.y, b11.x);
+                        if (J + 2 < Jb) {
+                            s1_xtile<false>(Xr, Xi, Zr, Zi, h0, h1, Ps, mp, 8 * J + 16 + 2 * q, g);
+                            if (J + 5 < Jb && rok) { h0 = ldcg(ap + 8 * J + 40); h1 = ldcg(ap + 8 * J + 41); }
+                        }
                     }
-                    // column orientation, J > I: A-operand [g][k = 2q+e] = conj(A22[8J+2q+e][8I+g])
-                    const int colI = 8 * I + g;
-                    const bool cok = colI < m;
-#pragma unroll 2
-                    for (int J = I + 1; J < nt; ++J) {
-                        const int r0 = 8 * J + 2 * q;
-                        const cplx* ap = A22 + (size_t)r0 * N + colI;
-                        cplx a0 = (cok && r0 < m) ? ldcg(ap) : cmake(0.0, 0.0), a1 = (cok && r0 + 1 < m) ? ldcg(ap + N) : cmake(0.0, 0.0);
-                        const cplx* bp = Vt + (size_t)r0 * SB + g;
-                        const cplx b00 = bp[0], b01 = bp[8], b10 = bp[SB], b11 = bp[SB + 8];
-                        // conj(a): re = a.x, im = -a.y
-                        dmma(Xr[0][0], Xr[0][1], a0.x, b00.x); dmma(Xr[0][0], Xr[0][1], a0.y, b00.y);
-                        dmma(Xi[0][0], Xi[0][1], a0.x, b00.y); dmma(Xi[0][0], Xi[0][1], dneg(a0.y), b00.x);
-                        dmma(Xr[1][0], Xr[1][1], a0.x, b01.x); dmma(Xr[1][0], Xr[1][1], a0.y, b01.y);
-                        dmma(Xi[1][0], Xi[1][1], a0.x, b01.y); dmma(Xi[1][0], Xi[1][1], dneg(a0.y), b01.x);
-                        dmma(Xr[0][0], Xr[0][1], a1.x, b10.x); dmma(Xr[0][0], Xr[0][1], a1.y, b10.y);
-                        dmma(Xi[0][0], Xi[0][1], a1.x, b10.y); dmma(Xi[0][0], Xi[0][1], dneg(a1.y), b10.x);
-                        dmma(Xr[1][0], Xr[1][1], a1.x, b11.x); dmma(Xr[1][0], Xr[1][1], a1.y, b11.y);
-                        dmma(Xi[1][0], Xi[1][1], a1.x, b11.y); dmma(Xi[1][0], Xi[1][1], dneg(a1.y), b11.x);
-                    }
-                    // X tile -> Wg (C layout: row g, columns 8t + 2q, 8t + 2q + 1)
-                    cplx* xp = Wg + (size_t)row * SB + 2 * q;
-                    xp[0] = cmake(Xr[0][0], Xi[0][0]); xp[1] = cmake(Xr[0][1], Xi[0][1]);
-                    xp[8] = cmake(Xr[1][0], Xi[1][0]); xp[9] = cmake(Xr[1][1], Xi[1][1]);
                 }
+                // diagonal tile
+                if (J0 <= I && I < J1) {
+                    cplx av[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * I + 2 * q + e;
+                        cplx x = cmake(0.0, 0.0);
+                        if (row < m && col < m) {
+                            if (row > col) x = ldcg(A22 + (size_t)row * N + col);
+                            else if (row < col) x = cconj(ldcg(A22 + (size_t)col * N + row));
+                            else x = cmake(ldcg(A22 + (size_t)row * N + row).x, 0.0);
+                        }
+                        av[e] = x;
+                    }
+                    s1_xtile<false>(Xr, Xi, Zr, Zi, av[0], av[1], Ps, mp, 8 * I + 2 * q, g);
+                }
+                // column orientation, J > I: A-operand [g][k = 2q+e] = conj(A22[8J+2q+e][8I+g])
+                {
+                    const int Ja = J0 > I + 1 ? J0 : I + 1, Jb = J1;
+                    const cplx* ap = A22 + (size_t)(2 * q) * N + 8 * I + g;      // column 8I+g < m always (I < nt - 1 here)
+                    const cplx z = cmake(0.0, 0.0);
+                    auto ld2 = [&](int J, cplx& x0, cplx& x1) {
+                        const int r0 = 8 * J + 2 * q;
+                        x0 = r0 < m ? ldcg(ap + (size_t)8 * J * N) : z;
+                        x1 = r0 + 1 < m ? ldcg(ap + (size_t)(8 * J + 1) * N) : z;
+                    };
+                    cplx n0 = z, n1 = z, f0 = z, f1 = z, h0 = z, h1 = z;
+                    if (Ja < Jb) ld2(Ja, n0, n1);
+                    if (Ja + 1 < Jb) ld2(Ja + 1, f0, f1);
+                    if (Ja + 2 < Jb) ld2(Ja + 2, h0, h1);
+                    for (int J = Ja; J < Jb; J += 3) {
+                        s1_xtile<true>(Xr, Xi, Zr, Zi, n0, n1, Ps, mp, 8 * J + 2 * q, g);
+                        if (J + 3 < Jb) ld2(J + 3, n0, n1);
+                        if (J + 1 < Jb) {
+                            s1_xtile<true>(Xr, Xi, Zr, Zi, f0, f1, Ps, mp, 8 * J + 8 + 2 * q, g);
+                            if (J + 4 < Jb) ld2(J + 4, f0, f1);
+                        }
+                        if (J + 2 < Jb) {
+                            s1_xtile<true>(Xr, Xi, Zr, Zi, h0, h1, Ps, mp, 8 * J + 16 + 2 * q, g);
+                            if (J + 5 < Jb) ld2(J + 5, h0, h1);
+                        }
+                    }
+                }
+                // partial Y tile -> Yp[p] (C layout: row g, columns 8t + 2q, 8t + 2q + 1)
+                cplx* xp = Yp + ((size_t)p * NR + row) * SB + 2 * q;
+                xp[0] = cmake(Xr[0][0] + Zr[0][0], Xi[0][0] + Zi[0][0]); xp[1] = cmake(Xr[0][1] + Zr[0][1], Xi[0][1] + Zi[0][1]);
+                xp[8] = cmake(Xr[1][0] + Zr[1][0], Xi[1][0] + Zi[1][0]); xp[9] = cmake(Xr[1][1] + Zr[1][1], Xi[1][1] + Zi[1][1]);
+            }
+            S1_WMARK(10)
+            __syncthreads();
+            S1_MARK(4)
+            // ---- 5. X = (sum of the parts) T: 8 x 16 row tiles on DMMA, k index of (lane q, k-step s) = 2q + (s & 1) + 8 (s >> 1) ----
+            for (int I = warp; I < nt; I += S1_WARPS) {
+                const int row = 8 * I + g;
+                cplx y[4];
+                {
+                    const cplx* yp = Yp + (size_t)row * SB + 2 * q;
+                    y[0] = yp[0]; y[1] = yp[1]; y[2] = yp[8]; y[3] = yp[9];
+                    for (int p = 1; p < P; ++p) {
+                        const cplx* y2 = yp + (size_t)p * NR * SB;
+                        y[0] = cadd(y[0], y2[0]); y[1] = cadd(y[1], y2[1]); y[2] = cadd(y[2], y2[8]); y[3] = cadd(y[3], y2[9]);
+                    }
+                }
+                double Xr[2][2] = {{0, 0}, {0, 0}}, Xi[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int k = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
+#pragma unroll
+                    for (int t2 = 0; t2 < 2; ++t2) {
+                        if (s4 >= 2 && t2 == 0) continue;                          // T is upper triangular: rows 8.. of columns ..7 are zero
+                        const cplx tb = Ts[k * SB + g + 8 * t2];
+                        dmma(Xr[t2][0], Xr[t2][1], y[s4].x, tb.x); dmma(Xi[t2][0], Xi[t2][1], y[s4].x, tb.y);
+                        dmma(Xr[t2][0], Xr[t2][1], dneg(y[s4].y), tb.y); dmma(Xi[t2][0], Xi[t2][1], y[s4].y, tb.x);
+                    }
+                }
+                cplx* xp = Wg + (size_t)row * SB + 2 * q;
+                xp[0] = cmake(Xr[0][0], Xi[0][0]); xp[1] = cmake(Xr[0][1], Xi[0][1]);
+                xp[8] = cmake(Xr[1][0], Xi[1][0]); xp[9] = cmake(Xr[1][1], Xi[1][1]);
             }
             __syncthreads();
+            S1_MARK(5)
             // ---- 6. G = V^H X (16x16), per-warp partial sums over the warp's rows, then S = T^H G ----
             {
                 double Gr[2][2][2], Gi[2][2][2];
@@ -278,21 +401,23 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                 for (int t1 = 0; t1 < 2; ++t1)
 #pragma unroll
                     for (int t2 = 0; t2 < 2; ++t2) { Gr[t1][t2][0] = Gr[t1][t2][1] = Gi[t1][t2][0] = Gi[t1][t2][1] = 0.0; }
-                for (int ks = warp; ks < mr / 4; ks += S1_WARPS) {
-                    const int rk = 4 * ks + q;
-                    const cplx va = Vg[(size_t)rk * SB + g], vb = Vg[(size_t)rk * SB + g + 8];
-                    const cplx xa = Wg[(size_t)rk * SB + g], xb = Wg[(size_t)rk * SB + g + 8];
-                    const cplx vv[2] = {va, vb}, xx[2] = {xa, xb};
+                for (int kk = warp; kk < mr / 8; kk += S1_WARPS) {
 #pragma unroll
-                    for (int t1 = 0; t1 < 2; ++t1)
+                    for (int e = 0; e < 2; ++e) {
+                        const int rk = 8 * kk + 2 * q + e;                  // rows 2q + e: conflict-free with the odd column stride
+                        const cplx vv[2] = {Ps[(size_t)g * mp + rk], Ps[(size_t)(g + 8) * mp + rk]};
+                        const cplx xx[2] = {Wg[(size_t)rk * SB + g], Wg[(size_t)rk * SB + g + 8]};
 #pragma unroll
-                        for (int t2 = 0; t2 < 2; ++t2) {
-                            // conj(v) x: re = vr xr + vi xi, im = vr xi - vi xr
-                            dmma(Gr[t1][t2][0], Gr[t1][t2][1], vv[t1].x, xx[t2].x); dmma(Gr[t1][t2][0], Gr[t1][t2][1], vv[t1].y, xx[t2].y);
-                            dmma(Gi[t1][t2][0], Gi[t1][t2][1], vv[t1].x, xx[t2].y); dmma(Gi[t1][t2][0], Gi[t1][t2][1], dneg(vv[t1].y), xx[t2].x);
-                        }
+                        for (int t1 = 0; t1 < 2; ++t1)
+#pragma unroll
+                            for (int t2 = 0; t2 < 2; ++t2) {
+                                // conj(v) x: re = vr xr + vi xi, im = vr xi - vi xr
+                                dmma(Gr[t1][t2][0], Gr[t1][t2][1], vv[t1].x, xx[t2].x); dmma(Gr[t1][t2][0], Gr[t1][t2][1], vv[t1].y, xx[t2].y);
+                                dmma(Gi[t1][t2][0], Gi[t1][t2][1], vv[t1].x, xx[t2].y); dmma(Gi[t1][t2][0], Gi[t1][t2][1], dneg(vv[t1].y), xx[t2].x);
+                            }
+                    }
                 }
-                cplx* gp = Gp + (size_t)warp * SB * SB;
+                cplx* gp = Gg + (size_t)warp * SB * SB;
 #pragma unroll
                 for (int t1 = 0; t1 < 2; ++t1)
 #pragma unroll
@@ -304,7 +429,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
             __syncthreads();
             if (tid < SB * SB) {
                 cplx s = cmake(0.0, 0.0);
-                for (int w = 0; w < S1_WARPS; ++w) s = cadd(s, Gp[(size_t)w * SB * SB + tid]);
+                for (int w = 0; w < S1_WARPS; ++w) s = cadd(s, Gg[(size_t)w * SB * SB + tid]);
                 Ss[tid] = s;
             }
             __syncthreads();
@@ -316,56 +441,86 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
             __syncthreads();
             if (tid < SB * SB) Ss[tid] = cscale(0.5, sval);   // 1/2 S
             __syncthreads();
-            // ---- 7. W = X - 1/2 V S, one row per thread ----
-            for (int r = tid; r < mr; r += S1_THREADS) {
-                cplx x[SB];
+            S1_MARK(6)
+            // ---- 7. W = X - V (1/2 S) on DMMA, same tiling as step 5 ----
+            for (int I = warp; I < nt; I += S1_WARPS) {
+                const int row = 8 * I + g;
+                cplx* xp = Wg + (size_t)row * SB + 2 * q;
+                const cplx x00 = xp[0], x01 = xp[1], x10 = xp[8], x11 = xp[9];
+                double Xr[2][2] = {{x00.x, x01.x}, {x10.x, x11.x}}, Xi[2][2] = {{x00.y, x01.y}, {x10.y, x11.y}};
 #pragma unroll
-                for (int n = 0; n < SB; ++n) x[n] = Wg[(size_t)r * SB + n];
-                if (r < m) {
-                    for (int k = 0; k < SB; ++k) {
-                        const cplx vk = Ps[(size_t)k * mp + r];
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int k = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
+                    const cplx v = Ps[(size_t)k * mp + row];
+                    const double nvx = dneg(v.x), nvy = dneg(v.y);
 #pragma unroll
-                        for (int n = 0; n < SB; ++n) cfms(x[n], vk, Ss[k * SB + n]);
+                    for (int t2 = 0; t2 < 2; ++t2) {
+                        const cplx sb = Ss[k * SB + g + 8 * t2];
+                        // X -= v s: re -= vx sx - vy sy, im -= vx sy + vy sx
+                        dmma(Xr[t2][0], Xr[t2][1], nvx, sb.x); dmma(Xi[t2][0], Xi[t2][1], nvx, sb.y);
+                        dmma(Xr[t2][0], Xr[t2][1], v.y, sb.y); dmma(Xi[t2][0], Xi[t2][1], nvy, sb.x);
                     }
                 }
-#pragma unroll
-                for (int n = 0; n < SB; ++n) Wg[(size_t)r * SB + n] = x[n];
+                xp[0] = cmake(Xr[0][0], Xi[0][0]); xp[1] = cmake(Xr[0][1], Xi[0][1]);
+                xp[8] = cmake(Xr[1][0], Xi[1][0]); xp[9] = cmake(Xr[1][1], Xi[1][1]);
             }
             __syncthreads();
-            // ---- 8. A22 -= V W^H + W V^H on the lower tiles ----
-            for (int pi = warp; pi < np; pi += S1_WARPS) {
-                for (int half = 0; half < 2; ++half) {
-                    const int I = half ? nt - 1 - pi : pi;
-                    if (half && I == pi) break;
-                    const int row = 8 * I + g;
-                    const bool rok = row < m;
-                    cplx vI[4], wI[4];
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) { vI[s] = Vg[(size_t)row * SB + 4 * s + q]; wI[s] = Wg[(size_t)row * SB + 4 * s + q]; }
-#pragma unroll 2
-                    for (int J = 0; J <= I; ++J) {
-                        const int col = 8 * J + 2 * q;
-                        cplx* cp = A22 + (size_t)row * N + col;
-                        const bool ok0 = rok && col < m, ok1 = rok && col + 1 < m;
-                        cplx c0v = ok0 ? ldcg(cp) : cmake(0.0, 0.0), c1v = ok1 ? ldcg(cp + 1) : cmake(0.0, 0.0);
-                        double Pr[2] = {0, 0}, Pp[2] = {0, 0}, Pm[2] = {0, 0};
-                        const cplx* vj = Vg + (size_t)(8 * J + g) * SB + q;
-                        const cplx* wj = Wg + (size_t)(8 * J + g) * SB + q;
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const cplx v2 = vj[4 * s], w2 = wj[4 * s];
-                            dmma(Pr[0], Pr[1], vI[s].x, w2.x); dmma(Pr[0], Pr[1], vI[s].y, w2.y);
-                            dmma(Pr[0], Pr[1], wI[s].x, v2.x); dmma(Pr[0], Pr[1], wI[s].y, v2.y);
-                            dmma(Pp[0], Pp[1], vI[s].y, w2.x); dmma(Pp[0], Pp[1], wI[s].y, v2.x);
-                            dmma(Pm[0], Pm[1], vI[s].x, w2.y); dmma(Pm[0], Pm[1], wI[s].x, v2.y);
-                        }
-                        c0v.x -= Pr[0]; c0v.y -= Pp[0] - Pm[0];
-                        c1v.x -= Pr[1]; c1v.y -= Pp[1] - Pm[1];
-                        if (ok0) cp[0] = c0v;
-                        if (ok1) cp[1] = c1v;
+            S1_MARK(7)
+            S1_WSTART()
+            // ---- 8. A22 -= V W^H + W V^H on the lower tiles; the linearised tile list is cut into 16 equal ranges ----
+            {
+                const int T = nt * (nt + 1) / 2;
+                int t = (int)((long long)warp * T / S1_WARPS);
+                const int t1 = (int)((long long)(warp + 1) * T / S1_WARPS);
+                int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((I + 1) * (I + 2) / 2 <= t) ++I;
+                while (I * (I + 1) / 2 > t) --I;
+                int J = t - I * (I + 1) / 2;
+                int In = I, Jn = J;                                      // position of the tile to prefetch next
+                cplx cA0, cA1, wA0, wA1, wA2, wA3;                       // buffer A: C entries and the W_J operands of a tile
+                cplx cB0, cB1, wB0, wB1, wB2, wB3;                       // buffer B
+                cA0 = cA1 = wA0 = wA1 = wA2 = wA3 = cB0 = cB1 = wB0 = wB1 = wB2 = wB3 = cmake(0.0, 0.0);
+                if (t < t1) s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cA0, cA1, wA0, wA1, wA2, wA3);
+                if (++Jn > In) { ++In; Jn = 0; }
+                if (t + 1 < t1) s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cB0, cB1, wB0, wB1, wB2, wB3);
+                if (++Jn > In) { ++In; Jn = 0; }
+                int Irow = -1;
+                cplx vI0, vI1, vI2, vI3, wI0, wI1, wI2, wI3;
+                vI0 = vI1 = vI2 = vI3 = wI0 = wI1 = wI2 = wI3 = cmake(0.0, 0.0);
+#define SKTB_S1_TILE(C0, C1, W0, W1, W2, W3)                                                                              \
+                    {                                                                                                      \
+                        if (I != Irow) {                                                                                   \
+                            const int rw = 8 * I + g;                                                                      \
+                            vI0 = Ps[(size_t)(2 * q) * mp + rw]; vI1 = Ps[(size_t)(2 * q + 1) * mp + rw];                  \
+                            vI2 = Ps[(size_t)(2 * q + 8) * mp + rw]; vI3 = Ps[(size_t)(2 * q + 9) * mp + rw];              \
+                            const cplx* wp = Wg + (size_t)rw * SB + 2 * q;                                                 \
+                            wI0 = wp[0]; wI1 = wp[1]; wI2 = wp[8]; wI3 = wp[9];                                            \
+                            Irow = I;                                                                                      \
+                        }                                                                                                  \
+                        const int row = 8 * I + g, col = 8 * J + 2 * q;                                                    \
+                        double Pr[2] = {0, 0}, Pp[2] = {0, 0}, Pm[2] = {0, 0}, Qr[2] = {0, 0}, Qp[2] = {0, 0}, Qm[2] = {0, 0};      \
+                        const cplx* vp = Ps + (size_t)(2 * q) * mp + 8 * J + g;                                            \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI0, wI0, vp[0], W0);                                                           \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI1, wI1, vp[mp], W1);                                                          \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI2, wI2, vp[(size_t)8 * mp], W2);                                              \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI3, wI3, vp[(size_t)9 * mp], W3);                                              \
+                        cplx* cp = A22 + (size_t)row * N + col;                                                            \
+                        if (row < m && col < m) cp[0] = cmake(C0.x - (Pr[0] + Qr[0]), C0.y - ((Pp[0] + Qp[0]) - (Pm[0] + Qm[0])));  \
+                        if (row < m && col + 1 < m) cp[1] = cmake(C1.x - (Pr[1] + Qr[1]), C1.y - ((Pp[1] + Qp[1]) - (Pm[1] + Qm[1])));  \
+                        if (++J > I) { ++I; J = 0; }                                                                       \
+                    }
+                for (; t < t1; t += 2) {
+                    SKTB_S1_TILE(cA0, cA1, wA0, wA1, wA2, wA3)
+                    if (t + 2 < t1) { s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cA0, cA1, wA0, wA1, wA2, wA3); if (++Jn > In) { ++In; Jn = 0; } }
+                    if (t + 1 < t1) {
+                        SKTB_S1_TILE(cB0, cB1, wB0, wB1, wB2, wB3)
+                        if (t + 3 < t1) { s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cB0, cB1, wB0, wB1, wB2, wB3); if (++Jn > In) { ++In; Jn = 0; } }
                     }
                 }
+#undef SKTB_S1_TILE
+                S1_WMARK(11)
             }
+            S1_MARK(8)
         }
         // ---- remaining columns c0 .. N-1: inside the band already ----
         __syncthreads();
@@ -383,27 +538,41 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 2: bulge chasing.  One warp per sweep; lane = (r = lane & 15, hh = lane >> 4) owns row r, columns 8hh .. 8hh+7 of
-// the 16 x 16 blocks.  prog[s] = hops completed by sweep s (1 << 30 when finished); sweep s may run hop h once sweep s-1
-// has completed hop h + 2.
+// the 16 x 16 blocks.  prog[s] = hops completed by sweep s (1 << 30 when finished).  Hop h >= 1 of sweep s touches rows
+// s+16h+1 .. s+16h+16 and columns s+16h-15 .. s+16h+16; hop h+1 of sweep s-1 reaches row s+16h+16 in those columns, hop h+2 of
+// sweep s-1 starts at row s+16h+32: sweep s may run hop h once sweep s-1 has completed hop h + 1 (all synchronisation is inside one
+// CTA: block-scope fences).  Per hop a warp loads the off-diagonal block B (registers) and the lower triangle of the diagonal
+// block D (into its shared-memory slab, mirrored from there) in one go, applies the previous reflector from the right, builds the
+// new one from B's first column, applies it from the left and to D from both sides.  Latency-bound by design: 3 CTAs x 8 warps/SM.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int S2_WARPS = 8;
 constexpr int S2_DONE = 1 << 30;
+constexpr int S2_DS = SB + 1;                       // row stride of the D slab (conflict-free rows and columns)
+constexpr int S2_SLAB = SB * S2_DS + 3 * SB;        // per warp: D block, v_a, v_b, w
+SKTB_HD size_t stage2_smem_bytes(int N) { return (size_t)S2_WARPS * S2_SLAB * sizeof(cplx) + (size_t)N * sizeof(int); }
 
-struct HopVec { cplx* v; cplx* w; };
-
-// A <- H^H A H on the diagonal block rows/cols r1 .. r1+L-1 (lower storage), reflector v (shared, length 16, zero padded), tau
-SKTB_D void s2_two_sided(cplx* AB, int r1, int L, const cplx* vS, cplx* wS, cplx tau, int r, int hh) {
-    cplx D[8];
-    const bool rok = r < L;
+// lower triangle of the diagonal block rows/cols r1 .. r1+L-1 -> slab Ds[r][c] (c <= r), zero padded to 16 x 16
+template <bool FULL>
+SKTB_D void s2_load_diag(const cplx* __restrict__ AB, int r1, int L, int r, int hh, cplx* Ds) {
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
         const int c = 8 * hh + cc;
-        cplx x = cmake(0.0, 0.0);
-        if (rok && c < L) {
-            if (r >= c) { x = ldcg(AB + (size_t)(r1 + c) * ABW + (r - c)); if (r == c) x.y = 0.0; }
-            else x = cconj(ldcg(AB + (size_t)(r1 + r) * ABW + (c - r)));
+        if (c <= r) {
+            cplx x = cmake(0.0, 0.0);
+            if (FULL || (r < L && c < L)) x = ldcg(AB + (r1 + c) * ABW + (r - c));
+            if (c == r) x.y = 0.0;
+            Ds[r * S2_DS + c] = x;
         }
-        D[cc] = x;
+    }
+}
+// A <- H^H A H on the diagonal block held in the slab, reflector v (shared, zero padded), tau; stores the lower part
+template <bool FULL>
+SKTB_D void s2_two_sided(cplx* __restrict__ AB, int r1, int L, const cplx* vS, cplx* wS, const cplx* Ds, cplx tau, int r, int hh) {
+    cplx D[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+        const int c = 8 * hh + cc;
+        D[cc] = c <= r ? Ds[r * S2_DS + c] : cconj(Ds[c * S2_DS + r]);
     }
     cplx y = cmake(0.0, 0.0);
 #pragma unroll
@@ -416,17 +585,18 @@ SKTB_D void s2_two_sided(cplx* AB, int r1, int L, const cplx* vS, cplx* wS, cplx
     for (int o = 8; o > 0; o >>= 1) { dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o); }
     const cplx alpha = cmul(cmake(-0.5 * tau.x, -0.5 * tau.y), dot);
     cplx w = x; cfma(w, alpha, vr);
-    __syncwarp();
     if (hh == 0) wS[r] = w;
     __syncwarp();
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
         const int c = 8 * hh + cc;
-        const cplx wc = wS[c], vc = vS[c];
-        // D[r][c] -= v_r conj(w_c) + w_r conj(v_c)
-        D[cc].x -= vr.x * wc.x + vr.y * wc.y + w.x * vc.x + w.y * vc.y;
-        D[cc].y -= vr.y * wc.x - vr.x * wc.y + w.y * vc.x - w.x * vc.y;
-        if (rok && c <= r) __stcg(AB + (size_t)(r1 + c) * ABW + (r - c), D[cc]);
+        if (c <= r) {
+            const cplx wc = wS[c], vc = vS[c];
+            // D[r][c] -= v_r conj(w_c) + w_r conj(v_c)
+            D[cc].x -= vr.x * wc.x + vr.y * wc.y + w.x * vc.x + w.y * vc.y;
+            D[cc].y -= vr.y * wc.x - vr.x * wc.y + w.y * vc.x - w.x * vc.y;
+            if (FULL || r < L) __stcg(AB + (r1 + c) * ABW + (r - c), D[cc]);
+        }
     }
 }
 
@@ -438,19 +608,74 @@ SKTB_D cplx s2_reflector(cplx x, int r, int L, double& beta, cplx& tau) {
     n2 = __shfl_sync(0xffffffffu, n2, 0);
     const cplx alpha = cmake(__shfl_sync(0xffffffffu, x.x, 0), __shfl_sync(0xffffffffu, x.y, 0));
     cplx scale;
-    householder(alpha, n2, beta, tau, scale);
+    fast_householder(alpha, n2, beta, tau, scale);
     cplx v = r == 0 ? cmake(1.0, 0.0) : ((r < L) ? cmul(x, scale) : cmake(0.0, 0.0));
     v.x = __shfl_sync(0xffffffffu, v.x, r); v.y = __shfl_sync(0xffffffffu, v.y, r);   // lanes hh == 1 take the value of lane r
     return v;
 }
 
-__global__ void __launch_bounds__(S2_WARPS * 32, 2) stage2_kernel(Stage2Args a) {
+// one chase hop: B = A[r1 .. r1+L2-1][r0 .. r0+L-1], D = A[r1.., r1..]; in: reflector (vS, tau) of rows r0..; out: (v2S, tau2) of rows r1..
+template <bool FULL>
+SKTB_D void s2_hop(cplx* __restrict__ AB, int r0, int L, int r1, int L2, const cplx* vS, cplx* v2S, cplx* wS, cplx* Ds, cplx tau, cplx& tau2,
+                   int r, int hh) {
+    cplx Bk[8];
+    const bool rok = FULL || r < L2;
+    const int boff = r0 * ABW + L + r;                         // element (r, c) at boff + c * (ABW - 1)
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+        const int c = 8 * hh + cc;
+        Bk[cc] = (FULL || (rok && c < L)) ? ldcg(AB + boff + c * (ABW - 1)) : cmake(0.0, 0.0);
+    }
+    s2_load_diag<FULL>(AB, r1, L2, r, hh, Ds);                 // independent of B: all loads of the hop are in flight together
+    // B <- B H = B - tau (B v) v^H
+    cplx t = cmake(0.0, 0.0);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) cfma(t, Bk[cc], vS[8 * hh + cc]);
+    t.x += __shfl_xor_sync(0xffffffffu, t.x, 16); t.y += __shfl_xor_sync(0xffffffffu, t.y, 16);
+    const cplx tt = cmul(tau, t);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+        const cplx vc = vS[8 * hh + cc];                       // B[r][c] -= tt conj(v_c)
+        Bk[cc].x -= tt.x * vc.x + tt.y * vc.y;
+        Bk[cc].y -= tt.y * vc.x - tt.x * vc.y;
+    }
+    // new reflector from column 0 of B
+    double beta2;
+    const cplx v2 = s2_reflector(hh == 0 ? Bk[0] : cmake(0.0, 0.0), r, L2, beta2, tau2);
+    if (hh == 0) v2S[r] = v2;
+    // B <- H2^H B = B - conj(tau2) v2 (v2^H B), four columns at a time
+    const cplx cv = cmul(cconj(tau2), v2);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        cplx u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = cmulc(v2, Bk[4 * half + k]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { u[k].x += __shfl_xor_sync(0xffffffffu, u[k].x, o); u[k].y += __shfl_xor_sync(0xffffffffu, u[k].y, o); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cfms(Bk[4 * half + k], cv, u[k]);
+    }
+    if (hh == 0) Bk[0] = r == 0 ? cmake(beta2, 0.0) : cmake(0.0, 0.0);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+        const int c = 8 * hh + cc;
+        if (FULL || (rok && c < L)) __stcg(AB + boff + c * (ABW - 1), Bk[cc]);
+    }
+    __syncwarp();                                              // v2S and the D slab are complete
+    s2_two_sided<FULL>(AB, r1, L2, v2S, wS, Ds, tau2, r, hh);
+}
+
+__global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane & 15, hh = lane >> 4;
-    cplx* slab = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * 3 * SB;     // v_a, v_b, w
-    volatile int* prog = reinterpret_cast<volatile int*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)S2_WARPS * 3 * SB);
+    cplx* Ds = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * S2_SLAB;
+    cplx* vecs = Ds + SB * S2_DS;                              // v_a, v_b, w
+    volatile int* prog = reinterpret_cast<volatile int*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)S2_WARPS * S2_SLAB);
 
     for (long long mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
         cplx* AB = a.AB + (size_t)mat * N * ABW;
@@ -458,79 +683,40 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) stage2_kernel(Stage2Args a) 
         for (int s = tid; s < N; s += S2_WARPS * 32) prog[s] = 0;
         __syncthreads();
         for (int s = warp; s < N - 1; s += S2_WARPS) {
-            cplx* vS = slab; cplx* v2S = slab + SB; cplx* wS = slab + 2 * SB;
+            cplx* vS = vecs; cplx* v2S = vecs + SB; cplx* wS = vecs + 2 * SB;
             int h = 0;
             auto wait_for = [&](int need) {
                 if (s > 0) { while (prog[s - 1] < need) { } }
                 __syncwarp();
-                __threadfence();
+                __threadfence_block();
             };
             auto publish = [&](int done) {
-                __threadfence();
+                __threadfence_block();
                 __syncwarp();
                 if (lane == 0) prog[s] = done;
             };
             // ---- hop 0: annihilate column s below the subdiagonal ----
             int L = min(SB, N - 1 - s);
-            wait_for(h + 3);
-            cplx x = (hh == 0 && r < L) ? ldcg(AB + (size_t)s * ABW + 1 + r) : cmake(0.0, 0.0);
+            wait_for(h + 2);
+            cplx x = (hh == 0 && r < L) ? ldcg(AB + s * ABW + 1 + r) : cmake(0.0, 0.0);
+            s2_load_diag<false>(AB, s + 1, L, r, hh, Ds);
             double beta; cplx tau;
             cplx v = s2_reflector(x, r, L, beta, tau);
-            if (hh == 0 && r < L) __stcg(AB + (size_t)s * ABW + 1 + r, r == 0 ? cmake(beta, 0.0) : cmake(0.0, 0.0));
-            __syncwarp();
+            if (hh == 0 && r < L) __stcg(AB + s * ABW + 1 + r, r == 0 ? cmake(beta, 0.0) : cmake(0.0, 0.0));
             if (hh == 0) vS[r] = v;
             __syncwarp();
             int r0 = s + 1;
-            s2_two_sided(AB, r0, L, vS, wS, tau, r, hh);
+            s2_two_sided<false>(AB, r0, L, vS, wS, Ds, tau, r, hh);
             publish(++h);
             // ---- hops 1..: chase the bulge ----
             while (true) {
                 const int r1 = r0 + L;
                 if (r1 >= N) break;
                 const int L2 = min(SB, N - r1);
-                wait_for(h + 3);
-                cplx Bk[8];
-                const bool rok = r < L2;
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    const int c = 8 * hh + cc;
-                    Bk[cc] = (rok && c < L) ? ldcg(AB + (size_t)(r0 + c) * ABW + (L - c + r)) : cmake(0.0, 0.0);
-                }
-                // B <- B H = B - tau (B v) v^H
-                cplx t = cmake(0.0, 0.0);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) cfma(t, Bk[cc], vS[8 * hh + cc]);
-                t.x += __shfl_xor_sync(0xffffffffu, t.x, 16); t.y += __shfl_xor_sync(0xffffffffu, t.y, 16);
-                const cplx tt = cmul(tau, t);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    const cplx vc = vS[8 * hh + cc];                 // B[r][c] -= tt conj(v_c)
-                    Bk[cc].x -= tt.x * vc.x + tt.y * vc.y;
-                    Bk[cc].y -= tt.y * vc.x - tt.x * vc.y;
-                }
-                // new reflector from column 0 of B
-                double beta2; cplx tau2;
-                const cplx v2 = s2_reflector(hh == 0 ? Bk[0] : cmake(0.0, 0.0), r, L2, beta2, tau2);
-                __syncwarp();
-                if (hh == 0) v2S[r] = v2;
-                // B <- H2^H B = B - conj(tau2) v2 (v2^H B)
-                cplx u[8];
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    u[cc] = cmulc(v2, Bk[cc]);
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) { u[cc].x += __shfl_xor_sync(0xffffffffu, u[cc].x, o); u[cc].y += __shfl_xor_sync(0xffffffffu, u[cc].y, o); }
-                }
-                const cplx cv = cmul(cconj(tau2), v2);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    const int c = 8 * hh + cc;
-                    cfms(Bk[cc], cv, u[cc]);
-                    if (c == 0) Bk[cc] = r == 0 ? cmake(beta2, 0.0) : cmake(0.0, 0.0);
-                    if (rok && c < L) __stcg(AB + (size_t)(r0 + c) * ABW + (L - c + r), Bk[cc]);
-                }
-                __syncwarp();
-                s2_two_sided(AB, r1, L2, v2S, wS, tau2, r, hh);
+                wait_for(h + 2);
+                cplx tau2;
+                if (L == SB && L2 == SB) s2_hop<true>(AB, r0, L, r1, L2, vS, v2S, wS, Ds, tau, tau2, r, hh);
+                else s2_hop<false>(AB, r0, L, r1, L2, vS, v2S, wS, Ds, tau, tau2, r, hh);
                 publish(++h);
                 cplx* tmp = vS; vS = v2S; v2S = tmp;
                 tau = tau2; L = L2; r0 = r1;
@@ -542,6 +728,81 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) stage2_kernel(Stage2Args a) 
         for (int j = tid; j < N; j += S2_WARPS * 32) {
             de[j] = __ldcg(AB + (size_t)j * ABW).x;
             de[N + j] = j < N - 1 ? __ldcg(AB + (size_t)j * ABW + 1).x : 0.0;
+        }
+    }
+}
+// ---------------------------------------------------------------------------------------------------------------------
+// Bisection on the tridiagonal matrix, one eigenvalue per thread, one CTA per matrix.  The Sturm count uses the PRODUCT form
+// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (3 FP64 operations per row; the quotient form q_i = d_i - x - e^2 / q_{i-1} of dstebz costs a
+// division, ~10 FP64 operations with a Newton reciprocal - at N = 512 the bisection was as expensive as the band reduction).  The matrix is
+// scaled by an exact power of two so that |d|, |e| <= 1, (p_{i-1}, p_i) are renormalised by a power of two whenever the exponent leaves
+// +-300 (integer test per row), an exact zero is replaced by -2^-100 p_{i-1} (counted as a sign change, dstebz's pivmin rule).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bisect_prod_kernel(const double* __restrict__ de, int N, long long nm, double* __restrict__ evals,
+                                                           long long ld, long long col0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* d = reinterpret_cast<double*>(smem_raw);
+    double* e2 = d + N;
+    double* red = e2 + N;                                                 // [3][32]
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (long long mat = blockIdx.x; mat < nm; mat += gridDim.x) {
+        const double* hd = de + (size_t)mat * 2 * N;
+        __syncthreads();
+        double di = 0.0, el = 0.0, er = 0.0;
+        if (tid < N) {
+            di = hd[tid];
+            el = tid > 0 ? fabs(hd[N + tid - 1]) : 0.0;
+            er = tid < N - 1 ? fabs(hd[N + tid]) : 0.0;
+        }
+        double emax = fmax(fabs(di), fmax(el, er));
+        for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+        if ((tid & 31) == 0) red[64 + (tid >> 5)] = emax;
+        __syncthreads();
+        const int nw = (T + 31) >> 5;
+        double tn = 0.0;
+        for (int q = 0; q < nw; ++q) tn = fmax(tn, red[64 + q]);
+        // exact power-of-two scale: 2^-ex with 2^(ex-1) <= tn < 2^ex  (tn = 0: no scaling)
+        int ex = 0;
+        if (tn > 0.0) frexp(tn, &ex);
+        const double sc = scalbn(1.0, -ex), isc = scalbn(1.0, ex);
+        di *= sc; el *= sc; er *= sc;
+        double lo_b = 1e300, hi_b = -1e300;
+        if (tid < N) { d[tid] = di; e2[tid] = er * er; lo_b = di - el - er; hi_b = di + el + er; }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo_b = fmin(lo_b, __shfl_xor_sync(0xffffffffu, lo_b, o));
+            hi_b = fmax(hi_b, __shfl_xor_sync(0xffffffffu, hi_b, o));
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { red[tid >> 5] = lo_b; red[32 + (tid >> 5)] = hi_b; }
+        __syncthreads();
+        double gl = 1e300, gu = -1e300;
+        for (int q = 0; q < nw; ++q) { gl = fmin(gl, red[q]); gu = fmax(gu, red[32 + q]); }
+        const double eps = 2.220446049250313e-16;
+        const double pivmin = 1e-290;                                     // scaled units (|T| <= 1)
+        gl -= 2.0 * eps * N + 2.0 * pivmin; gu += 2.0 * eps * N + 2.0 * pivmin;
+        if (tid < N) {
+            double lo = gl, hi = gu;
+            for (int it = 0; it < 128; ++it) {
+                const double x = 0.5 * (lo + hi);
+                if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
+                double p0 = 1.0, p1 = d[0] - x;
+                if (p1 == 0.0) p1 = -7.888609052210118e-31;               // -2^-100 p0
+                int cnt = p1 < 0.0;
+                for (int r = 1; r < N; ++r) {
+                    double pn = fma(d[r] - x, p1, -(e2[r - 1] * p0));
+                    if (pn == 0.0) pn = -7.888609052210118e-31 * p1;
+                    const int hn = __double2hiint(pn);
+                    cnt += (unsigned)(hn ^ __double2hiint(p1)) >> 31;
+                    p0 = p1; p1 = pn;
+                    const int exq = ((hn >> 20) & 0x7ff) - 1023;
+                    if (exq > 300 || exq < -300) {                        // renormalise the pair by 2^-exq (exact)
+                        const double rs = __hiloint2double((1023 - exq) << 20, 0);
+                        p0 *= rs; p1 *= rs;
+                    }
+                }
+                if (cnt > tid) hi = x; else lo = x;
+            }
+            evals[(long long)tid * ld + col0 + mat] = 0.5 * (lo + hi) * isc;
         }
     }
 }

@@ -485,11 +485,14 @@ static int launch_heev_twostage(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     if (rl < 0) return fail("two-stage tridiagonalisation does not support N = %d", N);
     g_launches += rl;
     { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail("two-stage launch: %s", cudaGetErrorString(e_)); }
-    const int T = (N + 31) / 32 * 32;
-    const size_t smem = ((size_t)2 * N + 96) * sizeof(double);
-    bisect_merge_kernel<<<(unsigned)std::min<long long>(a.nm, 148LL * 8), T, smem, st>>>(de, N, de, 0, a.nm, a.evals, a.ld, a.col0);
+    static const bool old_bisect = getenv("SKTB_TWOSTAGE_BISECT") && getenv("SKTB_TWOSTAGE_BISECT")[0] == '0';   // A/B: quotient-form Sturm count
+    if (old_bisect) {
+        const int T = (N + 31) / 32 * 32;
+        const size_t smem = ((size_t)2 * N + 96) * sizeof(double);
+        bisect_merge_kernel<<<(unsigned)std::min<long long>(a.nm, 148LL * 8), T, smem, st>>>(de, N, de, 0, a.nm, a.evals, a.ld, a.col0);
+    } else if (twostage::launch_bisect(de, N, a.nm, a.evals, a.ld, a.col0, st) < 0) return fail("bisection launch failed (N = %d)", N);
     LAUNCHED();
-    g_kinfo = std::string(info) + " | bisect_merge";
+    g_kinfo = std::string(info) + (old_bisect ? " | bisect_merge" : " | bisect_prod (product-form Sturm count)");
     return 0;
 }
 

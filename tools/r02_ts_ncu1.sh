@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu --set full of one two-stage kernel (N = 512, 296 matrices): r02_ts_ncu1.sh TAG KERNEL
+O=gpurun_out; mkdir -p $O
+TAG=$1; kn=$2
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s 1 -c 1 -o $O/${TAG}_full_$kn -f python tools/bench_heev.py ${3:-512} 296 > $O/${TAG}_ncu_$kn.log 2>&1
+ncu -i $O/${TAG}_full_$kn.ncu-rep --page source --csv > $O/${TAG}_src_$kn.csv 2>/dev/null
+ncu -i $O/${TAG}_full_$kn.ncu-rep --page raw --csv > $O/${TAG}_raw_$kn.csv 2>/dev/null
+rm -f $O/${TAG}_full_$kn.ncu-rep

@@ -67,3 +67,32 @@ if os.environ.get("TS_TIME"):
         fl = 16.0 / 3 * N ** 3 * nmt
         print(f"N={N} nm={nmt}: stage1 {t1:.2f} ms ({nmt/t1*1e3:.3e}/s, {fl/t1/1e9:.2f} TF conv)  stage2 {t12-t1:.2f} ms ({nmt/(t12-t1)*1e3:.3e}/s)  "
               f"sktb_heev {tall:.2f} ms ({nmt/tall*1e3:.3e}/s, {fl/tall/1e9:.2f} TF conv) [{ham.last_kernel_info()[:40]}]", flush=True)
+
+# adversarial inputs through sktb_heev (two-stage path forced): zero / diagonal / decoupled blocks / exact degeneracies / scales
+if os.environ.get("TS_ADV"):
+    rng = np.random.default_rng(7)
+    for N in [int(x) for x in os.environ["TS_ADV"].split(",")]:
+        cases = {}
+        cases["zero"] = np.zeros((N, N), complex)
+        cases["diag_repeated"] = np.diag(np.repeat(np.array([-1.5, 0.0, 0.0, 2.0]), N // 4 + 1)[:N]).astype(complex)
+        A = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N)); A = A + A.conj().T
+        B = A.copy(); h = N // 2; B[h:, :h] = 0; B[:h, h:] = 0
+        cases["two_blocks"] = B
+        C = np.zeros((N, N), complex)                                  # bipartite hopping, zero diagonal: spectrum symmetric about 0, zero modes
+        for i in range(N - 1): C[i + 1, i] = C[i, i + 1] = 1.0 if i % 2 == 0 else 0.3
+        cases["ssh_chain"] = C
+        cases["tiny_scale"] = A * 1e-7
+        cases["big_scale"] = A * 1e3
+        Q, _ = np.linalg.qr(A)
+        lam = np.repeat(np.arange(N // 8 + 1, dtype=float), 8)[:N]       # 8-fold exact degeneracies
+        cases["degenerate8"] = (Q * lam) @ Q.conj().T
+        M = torch.tensor(np.stack(list(cases.values())), device="cuda")
+        nmc = M.shape[0]
+        ev = torch.empty((N, nmc), dtype=torch.float64, device="cuda")
+        _lib.check(lib.sktb_heev(ham._plan, M.data_ptr(), N, nmc, ev.data_ptr(), None, None, None))
+        torch.cuda.synchronize()
+        got = ev.cpu().numpy()
+        for i, (name, mat) in enumerate(cases.items()):
+            ref = np.linalg.eigvalsh(mat, UPLO="L")
+            sc = max(1e-300, np.abs(ref).max())
+            print(f"N={N} {name:14s} max err {np.abs(got[:, i] - ref).max():.2e} (rel {np.abs(got[:, i] - ref).max() / sc:.1e})  [{ham.last_kernel_info()[-45:]}]", flush=True)
