@@ -35,15 +35,31 @@ struct Stage1Args {
     cplx* Wg;                       // [nm][NR][SB]: X = A22 V T, then W
     cplx* Gg;                       // [nm][S1_WARPS][SB*SB]: per-warp partial sums of G = V^H X
     int NR, mp;                     // NR = N rounded up to 8; mp: column stride of the panel in shared memory (odd)
+    cplx* Tstore;                   // NULL, or [nm][npanels][SB*SB]: keep the block reflectors (V goes into the dead panel of H, T here)
+    int npanels;
 };
 struct Stage2Args {
     cplx* AB; int N; long long nm;
     double* de;                     // [nm][2][N]: d, then e (N - 1 entries)
+    cplx* Rstore; long long rstride;   // NULL, or [nm][rstride]: reflector k = off(s) + h of (sweep s, hop h) as 16 entries of v + tau
+};
+// number of bulge-chase reflectors of an N x N band: sum over sweeps of ceil((N - 1 - s) / SB)
+SKTB_HD long long chase_reflectors(int N) { long long k = 0; for (int s = 0; s < N - 1; ++s) k += (N - 1 - s + SB - 1) / SB; return k; }
+SKTB_HD int stage1_panels(int N) { return N > SB ? (N - SB + SB - 1) / SB : 0; }
+// selected rows of the eigenvector matrix U = Q1 Q2 Z (Q1: block reflectors of stage 1, Q2: chase reflectors, Z: tridiagonal eigenvectors)
+struct RowsArgs {
+    int N; long long nm;
+    const cplx* H;                  // [nm][N][N] after stage 1 with Tstore: V panels below the band
+    const cplx* Tstore; int npanels;
+    const cplx* Rstore; long long rstride;
+    const double* Zf; long long zstride;      // Zf[mat * zstride + k * N + n]: component k of tridiagonal eigenvector n
+    cplx* vec_out; long long vs_band, vs_k, vcol0;   // vec_out[n * vs_band + (vcol0 + mat) * vs_k + r] = U[rows[r], n]
+    int n_rows; const int* rows;
 };
 
 SKTB_HD int stage1_mp(int N) { return (((N - SB + 7) / 8) * 8) | 1; }
-SKTB_HD size_t stage1_smem_bytes(int N) {
-    return ((size_t)(SB + 2) * stage1_mp(N) + 4 * SB * SB + 3 * SB) * sizeof(cplx) + 64;
+SKTB_HD size_t stage1_smem_bytes(int N, int ring_depth) {
+    return ((size_t)(SB + 2) * stage1_mp(N) + 4 * SB * SB + 5 * SB + (size_t)S1_WARPS * ring_depth * 64) * sizeof(cplx) + 64;
 }
 SKTB_HD size_t scratch_bytes_per_matrix(int N) {
     const size_t NR = (size_t)(N + 7) / 8 * 8;
@@ -58,6 +74,9 @@ inline cplx* band_of(void* scratch) { return reinterpret_cast<cplx*>(scratch); }
 bool supported(int N);
 // eigenvalues of the tridiagonal matrices de[mat][2][N] by bisection (product-form Sturm sequence), ascending: evals[n*ld + col0 + mat]
 int launch_bisect(const double* de, int N, long long nm, double* evals, long long ld, long long col0, cudaStream_t st);
+// keep variant: Tstore / Rstore (see Stage1Args / Stage2Args) are filled for launch_rows
+int launch_tridiag_keep(cplx* H, int N, long long nm, void* scratch, double* de, cplx* Tstore, cplx* Rstore, long long rstride, cudaStream_t st, char* info, size_t info_len);
+int launch_rows(const RowsArgs& a, cudaStream_t st);
 
 #if defined(__CUDACC__) && defined(SKTB_TWOSTAGE_KERNELS)      // the kernels live in heev_twostage.cu only
 // D(8x8) += A(8x4) B(4x8) in FP64; lane = 4 g + q: a = A[g][q], b = B[q][g], c0/c1 = C[g][2q], C[g][2q+1]
@@ -106,6 +125,16 @@ SKTB_D void s1_xtile(double (&Xr)[2][2], double (&Xi)[2][2], double (&Zr)[2][2],
     dmma(Zr[1][0], Zr[1][1], a1i, b11.y);  dmma(Zi[1][0], Zi[1][1], a1j, b11.x);
 }
 
+// asynchronous 16-byte copy global -> shared (LDGSTS), zero-filled when !ok; per-thread commit groups
+SKTB_D void cp_async16(cplx* smem_dst, const cplx* gsrc, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+SKTB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+SKTB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
 // rank-2k tile update helpers: P = V_I W_J^H + W_I V_J^H accumulated as Pr (real part), Pp - Pm (imaginary part)
 SKTB_D void s1_r2k(double (&Pr)[2], double (&Pp)[2], double (&Pm)[2], double (&Qr)[2], double (&Qp)[2], double (&Qm)[2], cplx vI, cplx wI,
                    cplx v2, cplx w2) {
@@ -133,6 +162,7 @@ __device__ unsigned long long g_s1_prof[32];
 #define S1_WMARK(i)
 #define S1_WSTART()
 #endif
+template <int RD>      // depth of the per-warp ring of asynchronously prefetched 8 x 8 tiles (shared memory, 1 KB per tile)
 __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
 #ifdef SKTB_TS_PROFILE
     long long tmark_ = clock64(), wmark_ = 0;
@@ -146,9 +176,11 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
     cplx* Rs = Ts + SB * SB;                                 // [SB][SB] R, Rs[r*SB+c]
     cplx* Ss = Rs + SB * SB;                                 // [SB][SB] G, then 1/2 S = 1/2 T^H G
     cplx* Zs = Ss + SB * SB;                                 // [SB][SB] Zs[w*SB+c] = V_w^H v_c (w < c), for T
-    cplx* dots = Zs + SB * SB;                               // [2][SB] raw dots with the pivot column (double-buffered)
-    cplx* taus = dots + 2 * SB;                              // [SB]
+    cplx* part = Zs + SB * SB;                               // [2][SB] raw dots with the pivot column, one per row half
+    cplx* rowc = part + 2 * SB;                              // [2][SB] entries of the current pivot row of every column (double-buffered)
+    cplx* taus = rowc + 2 * SB;                              // [SB]
     cplx* shadow = taus + SB;                                // [2][mp] the current pivot column, updated and unscaled
+    cplx* ring = shadow + (size_t)2 * mp + (size_t)warp * RD * 64 + lane;   // this lane's slots: ring[(stage * 2 + e) * 32]
 
     for (long long mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
         cplx* A = a.H + (size_t)mat * N * N;
@@ -163,97 +195,126 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
             const int mr = (m + 7) / 8 * 8;
             const int nt = mr / 8;
             cplx* A22 = A + (size_t)(c0 + SB) * N + (c0 + SB);
-            // ---- 1. panel -> shared memory (column-major), rows m .. mr-1 zero ----
+            // ---- 1 + 2. Householder QR of the panel with the panel in REGISTERS.  Warp (k2 = warp >> 1, h = warp & 1) owns columns 2 k2,
+            //         2 k2 + 1 on the rows r = 64 i + 32 h + lane (i < 8): 16 complex per lane.  Per column c: the pivot column (shared
+            //         memory, written by its owners in the previous step) is read ONCE into registers, the two dots of the own columns
+            //         with it go through part[h][w]; after the barrier every warp forms the reflector, updates its columns from the cached
+            //         pivot and publishes the entries of row c+1 (rowc) and, if it owns it, the next pivot column.  (With the panel in shared
+            //         memory every column step streams the whole panel through the 128 B/clk pipe: 5 kclk per column, 17 % of the kernel.) ----
             __syncthreads();
             S1_MARK(0)
-            for (int idx = tid; idx < mr * SB; idx += S1_THREADS) {
-                const int r = idx >> 4, c = idx & 15;
-                Ps[(size_t)c * mp + r] = r < m ? ldcg(A + (size_t)(c0 + SB + r) * N + c0 + c) : cmake(0.0, 0.0);
+            const int k2 = warp >> 1, hq = warp & 1, w0 = 2 * k2;
+            cplx col0[8], col1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 64 * i + 32 * hq + lane;
+                col0[i] = col1[i] = cmake(0.0, 0.0);
+                if (r < m) { const cplx* ap = A + (size_t)(c0 + SB + r) * N + c0 + w0; col0[i] = ldcg(ap); col1[i] = ldcg(ap + 1); }
             }
             for (int idx = tid; idx < 4 * SB * SB; idx += S1_THREADS) Ts[idx] = cmake(0.0, 0.0);   // T, R, S, Z
+            if (k2 == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int r = 64 * i + 32 * hq + lane; if (r < m) shadow[r] = col0[i]; }
+            }
+            if (hq == 0 && lane == 0) { rowc[w0] = col0[0]; rowc[w0 + 1] = col1[0]; }
             __syncthreads();
             S1_MARK(1)
-            // ---- 2. Householder QR of the panel, one warp per column, ONE barrier per column: after the barrier every warp knows
-            //         the reflector of column c (alpha, norm from the dots), updates its own column and - with the updated pivot
-            //         column c+1 recomputed on the fly from the not-yet-overwritten data - accumulates the dot it needs for step c+1.
-            //         The pivot column lives in a shadow buffer (warp c+1 writes it there), R entries go straight to Rs. ----
-            cplx* myc = Ps + (size_t)warp * mp;
             const int ncol = m < SB ? m : SB;                 // columns that have a diagonal row
-            {
-                if (warp == 0) for (int r = lane; r < m; r += 32) shadow[r] = Ps[r];
-                cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
-                int r = 1 + lane;
-                for (; r + 32 < m; r += 64) { cfmac(acc, Ps[r], myc[r]); cfmac(acc2, Ps[r + 32], myc[r + 32]); }
-                if (r < m) cfmac(acc, Ps[r], myc[r]);
-                acc = cwarp_sum(cadd(acc, acc2));
-                if (lane == 0) dots[warp] = acc;
-            }
-            __syncthreads();
+            const int ns = (m + 63) >> 6;                     // live 64-row slots
             for (int c = 0; c < ncol; ++c) {
                 const cplx* pc = shadow + (size_t)(c & 1) * mp;
-                cplx* nxt = shadow + (size_t)((c + 1) & 1) * mp;
-                const cplx* D = dots + (c & 1) * SB;
-                cplx* Dn = dots + ((c + 1) & 1) * SB;
-                const bool has_next = c + 1 < ncol;
-                double beta; cplx tau, scale;
-                fast_householder(pc[c], D[c].x, beta, tau, scale);
-                const cplx ctau = cconj(tau);
-                const cplx* pn = Ps + (size_t)(c + 1) * mp;                           // column c+1 before this step's update
-                cplx csn = cmake(0.0, 0.0);
-                if (has_next) csn = cmul(cmul(ctau, cadd(pn[c], cmulc(scale, D[c + 1]))), scale);
-                cplx acc = cmake(0.0, 0.0);
-                if (warp > c) {
-                    const cplx coef = cmul(ctau, cadd(myc[c], cmulc(scale, D[warp])));   // conj(tau) v^H a_w
-                    const cplx cs2 = cmul(coef, scale);
-                    if (lane == 0) Rs[c * SB + warp] = csub(myc[c], coef);
-                    if (warp == c + 1) {
-                        for (int r = c + 1 + lane; r < m; r += 32) {
-                            cplx an = myc[r]; cfms(an, cs2, pc[r]);
-                            nxt[r] = an;
-                            if (r > c + 1) acc.x += an.x * an.x + an.y * an.y;
-                        }
-                    } else {
-                        for (int r = c + 1 + lane; r < m; r += 32) {
-                            const cplx pr = pc[r];
-                            cplx aw = myc[r]; cfms(aw, cs2, pr);
-                            myc[r] = aw;
-                            if (has_next && r > c + 1) { cplx an = pn[r]; cfms(an, csn, pr); cfmac(acc, an, aw); }
-                        }
+                cplx pcr[8];
+                cplx d0 = cmake(0.0, 0.0), d1 = cmake(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 64 * i + 32 * hq + lane;
+                    pcr[i] = cmake(0.0, 0.0);
+                    if (i < ns) {                                               // (uniform) slots beyond the panel carry no work
+                        if (r > c && r < m) pcr[i] = pc[r];
+                        cfmac(d0, pcr[i], col0[i]); cfmac(d1, pcr[i], col1[i]);
                     }
-                } else if (warp == c) {
-                    for (int r = c + 1 + lane; r < m; r += 32) {
-                        const cplx pr = pc[r];
-                        const cplx vr = cmul(pr, scale);
-                        myc[r] = vr;
-                        if (has_next && r > c + 1) { cplx an = pn[r]; cfms(an, csn, pr); cfmac(acc, an, vr); }
-                    }
-                    if (lane < c) myc[lane] = cmake(0.0, 0.0);
-                    if (lane == 0) { myc[c] = cmake(1.0, 0.0); taus[c] = tau; Rs[c * SB + c] = cmake(beta, 0.0); }
-                } else {
-                    if (lane == 0) Zs[warp * SB + c] = cadd(cconj(myc[c]), cmul(scale, cconj(D[warp])));   // V_w^H v_c
-                    if (has_next)
-                        for (int r = c + 2 + lane; r < m; r += 32) { cplx an = pn[r]; cfms(an, csn, pc[r]); cfmac(acc, an, myc[r]); }
                 }
-                if (has_next) {
-                    acc = cwarp_sum(acc);
-                    if (lane == 0) Dn[warp] = acc;
-                }
+                d0 = cwarp_sum(d0); d1 = cwarp_sum(d1);
+                if (lane == 0) { part[hq * SB + w0] = d0; part[hq * SB + w0 + 1] = d1; }
+                S1_MARK(15)
                 __syncthreads();
-            }
-            // columns without a diagonal row (m < SB) are R only: their V column is zero
-            if (warp >= ncol) for (int r = lane; r < m; r += 32) myc[r] = cmake(0.0, 0.0);
-            if (ncol < SB) __syncthreads();                   // (uniform) the zeroed columns are operands of step 4
-            // T[:c][c] = -tau_c T[:c][:c] z_c, T[c][c] = tau_c (warp 0; the band output below overlaps with it)
-            if (warp == 0) {
-                for (int c = 0; c < ncol; ++c) {
-                    const cplx tau = taus[c];
-                    if (lane < c) {
-                        cplx t = cmake(0.0, 0.0);
-                        for (int k = lane; k < c; ++k) cfma(t, Ts[lane * SB + k], Zs[k * SB + c]);
-                        Ts[lane * SB + c] = cmul(cmake(-tau.x, -tau.y), t);
-                    } else if (lane == c) Ts[c * SB + c] = tau;
-                    __syncwarp();
+                S1_MARK(12)
+                double beta; cplx tau, scale;
+                fast_householder(pc[c], part[c].x + part[SB + c].x, beta, tau, scale);
+                const cplx ctau = cconj(tau);
+                const cplx* rc = rowc + (c & 1) * SB;         // entries of row c of every column (before this step)
+                cplx* rn = rowc + ((c + 1) & 1) * SB;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int w = w0 + j;
+                    cplx* col = j ? col1 : col0;
+                    const cplx raw = cadd(part[w], part[SB + w]);
+                    const cplx ac = rc[w];
+                    if (w > c) {
+                        const cplx coef = cmul(ctau, cadd(ac, cmulc(scale, raw)));     // conj(tau) v^H a_w
+                        const cplx cs2 = cmul(coef, scale);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (i < ns) cfms(col[i], cs2, pcr[i]);
+                        if (hq == 0 && lane == 0) Rs[c * SB + w] = csub(ac, coef);
+                    } else if (w == c) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 64 * i + 32 * hq + lane;
+                            col[i] = r == c ? cmake(1.0, 0.0) : cmul(pcr[i], scale);   // rows < c: pcr = 0
+                        }
+                        if (hq == 0 && lane == 0) { taus[c] = tau; Rs[c * SB + c] = cmake(beta, 0.0); }
+                    } else {
+                        if (hq == 0 && lane == 0) Zs[w * SB + c] = cadd(cconj(ac), cmul(scale, cconj(raw)));   // V_w^H v_c
+                    }
                 }
+                // publish row c+1 of the own columns and, for its owners, the next pivot column
+                if (c + 1 < ncol) {
+                    const int rr = c + 1;
+                    if (((rr >> 5) & 1) == hq && (rr & 31) == lane) {
+                        const int ii = rr >> 6;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (i == ii) { rn[w0] = col0[i]; rn[w0 + 1] = col1[i]; }
+                    }
+                    if ((rr >> 1) == k2) {
+                        cplx* nx = shadow + (size_t)(rr & 1) * mp;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 64 * i + 32 * hq + lane;
+                            if (r > c && r < m) nx[r] = (rr & 1) ? col1[i] : col0[i];
+                        }
+                    }
+                }
+                S1_MARK(16)
+                __syncthreads();
+                S1_MARK(13)
+            }
+            // V -> shared memory (column-major) for the GEMM operands; columns without a diagonal row (m < SB) and rows m .. mr-1 are zero
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 64 * i + 32 * hq + lane;
+                if (r < mr) {
+                    const bool live = r < m;
+                    const cplx v0 = (live && w0 < ncol) ? col0[i] : cmake(0.0, 0.0), v1 = (live && w0 + 1 < ncol) ? col1[i] : cmake(0.0, 0.0);
+                    Ps[(size_t)w0 * mp + r] = v0;
+                    Ps[(size_t)(w0 + 1) * mp + r] = v1;
+                    if (a.Tstore && live) { cplx* vp = A + (size_t)(c0 + SB + r) * N + c0 + w0; vp[0] = v0; vp[1] = v1; }   // V into the dead panel of H
+                }
+            }
+            __syncthreads();
+            // T[t][c] = -tau_c sum_{k=t}^{c-1} T[t][k] z[k][c], T[t][t] = tau_t: the rows of T are independent - one half-warp per row
+            // (lane k holds T[t][k]), 15 uniform column steps with a 16-lane reduction each
+            if (warp < SB / 2) {
+                const int t = 2 * warp + (lane >> 4), k = lane & 15;
+                cplx Tk = (k == t && t < ncol) ? taus[t] : cmake(0.0, 0.0);
+                for (int c = 1; c < ncol; ++c) {
+                    cplx pr = cmake(0.0, 0.0);
+                    if (k >= t && k < c) pr = cmul(Tk, Zs[k * SB + c]);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) { pr.x += __shfl_xor_sync(0xffffffffu, pr.x, o); pr.y += __shfl_xor_sync(0xffffffffu, pr.y, o); }
+                    if (k == c && c > t) { const cplx tc = taus[c]; Tk = cmul(cmake(-tc.x, -tc.y), pr); }
+                }
+                Ts[t * SB + k] = Tk;
+                if (a.Tstore) a.Tstore[((size_t)mat * a.npanels + c0 / SB) * SB * SB + t * SB + k] = Tk;
             }
             S1_MARK(2)
             // ---- 3. band output of the 16 columns of this panel: diagonal block (lower) + R; the rest of the column is zero ----
@@ -283,83 +344,72 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                     if (idle < best) { best = idle; P = pp; }
                 }
             }
-            for (int u = warp; u < nt * P; u += S1_WARPS) {
-                const int I = u / P, p = u - I * P;
-                const int J0 = (int)((long long)p * nt / P), J1 = (int)((long long)(p + 1) * nt / P);
-                double Xr[2][2] = {{0, 0}, {0, 0}}, Xi[2][2] = {{0, 0}, {0, 0}}, Zr[2][2] = {{0, 0}, {0, 0}}, Zi[2][2] = {{0, 0}, {0, 0}};
-                const int row = 8 * I + g;
-                const bool rok = row < m;
-                // row orientation, J < I (columns < 8I <= m - 1: no column guard)
-                {
-                    const int Ja = J0, Jb = J1 < I ? J1 : I;
-                    const cplx* ap = A22 + (size_t)row * N + 2 * q;
-                    const cplx z = cmake(0.0, 0.0);
-                    // three tiles in flight, each buffer re-loaded right after its use (no register rotation: a move out of a
-                    // register with a pending load would wait for that load)
-                    cplx n0 = z, n1 = z, f0 = z, f1 = z, h0 = z, h1 = z;
-                    if (Ja < Jb && rok) { n0 = ldcg(ap + 8 * Ja); n1 = ldcg(ap + 8 * Ja + 1); }
-                    if (Ja + 1 < Jb && rok) { f0 = ldcg(ap + 8 * Ja + 8); f1 = ldcg(ap + 8 * Ja + 9); }
-                    if (Ja + 2 < Jb && rok) { h0 = ldcg(ap + 8 * Ja + 16); h1 = ldcg(ap + 8 * Ja + 17); }
-                    for (int J = Ja; J < Jb; J += 3) {
-                        s1_xtile<false>(Xr, Xi, Zr, Zi, n0, n1, Ps, mp, 8 * J + 2 * q, g);
-                        if (J + 3 < Jb && rok) { n0 = ldcg(ap + 8 * J + 24); n1 = ldcg(ap + 8 * J + 25); }
-                        if (J + 1 < Jb) {
-                            s1_xtile<false>(Xr, Xi, Zr, Zi, f0, f1, Ps, mp, 8 * J + 8 + 2 * q, g);
-                            if (J + 4 < Jb && rok) { f0 = ldcg(ap + 8 * J + 32); f1 = ldcg(ap + 8 * J + 33); }
-                        }
-                        if (J + 2 < Jb) {
-                            s1_xtile<false>(Xr, Xi, Zr, Zi, h0, h1, Ps, mp, 8 * J + 16 + 2 * q, g);
-                            if (J + 5 < Jb && rok) { h0 = ldcg(ap + 8 * J + 40); h1 = ldcg(ap + 8 * J + 41); }
-                        }
-                    }
-                }
-                // diagonal tile
-                if (J0 <= I && I < J1) {
-                    cplx av[2];
+            {
+                // one stream of tiles per warp across its units; the tiles are copied to the warp's ring RD - 1 tiles ahead (cp.async)
+                const int nunits = nt * P;
+                int uI = warp, iI = 0, pI = 0, jI = 0, j1I = 0;                 // issue cursor
+                int uC = warp, iC = 0, pC = 0, jC = 0, j1C = 0;                 // compute cursor
+                auto unit_of = [&](int u, int& I, int& p, int& J, int& J1) {
+                    I = u / P; p = u - I * P;
+                    J = (int)((long long)p * nt / P); J1 = (int)((long long)(p + 1) * nt / P);
+                };
+                if (uI < nunits) { unit_of(uI, iI, pI, jI, j1I); unit_of(uC, iC, pC, jC, j1C); }
+                auto issue = [&](int stage) {
+                    if (uI < nunits) {
+                        const int I = iI, J = jI;
+                        const int row = 8 * I + g;
+                        cplx* dst = ring + stage * 64;
+                        if (J < I) {                                            // A22[row][8J + 2q + e]
+                            const cplx* ap = A22 + (size_t)row * N + 8 * J + 2 * q;
+                            const bool ok = row < m;
+                            cp_async16(dst, ok ? ap : A22, ok); cp_async16(dst + 32, ok ? ap + 1 : A22, ok);
+                        } else if (J > I) {                                     // A22[8J + 2q + e][8I + g] (conjugated at use)
+                            const int r0 = 8 * J + 2 * q;
+                            const cplx* ap = A22 + (size_t)r0 * N + row;
+                            const bool ok0 = r0 < m, ok1 = r0 + 1 < m;
+                            cp_async16(dst, ok0 ? ap : A22, ok0); cp_async16(dst + 32, ok1 ? ap + N : A22, ok1);
+                        } else {                                                // diagonal tile: the stored (lower) one of (row, col), (col, row)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int col = 8 * I + 2 * q + e;
-                        cplx x = cmake(0.0, 0.0);
-                        if (row < m && col < m) {
-                            if (row > col) x = ldcg(A22 + (size_t)row * N + col);
-                            else if (row < col) x = cconj(ldcg(A22 + (size_t)col * N + row));
-                            else x = cmake(ldcg(A22 + (size_t)row * N + row).x, 0.0);
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = 8 * I + 2 * q + e;
+                                const bool ok = row < m && col < m;
+                                const cplx* ap = row >= col ? A22 + (size_t)row * N + col : A22 + (size_t)col * N + row;
+                                cp_async16(dst + 32 * e, ok ? ap : A22, ok);
+                            }
                         }
-                        av[e] = x;
+                        if (++jI >= j1I) { uI += S1_WARPS; if (uI < nunits) unit_of(uI, iI, pI, jI, j1I); }
                     }
-                    s1_xtile<false>(Xr, Xi, Zr, Zi, av[0], av[1], Ps, mp, 8 * I + 2 * q, g);
-                }
-                // column orientation, J > I: A-operand [g][k = 2q+e] = conj(A22[8J+2q+e][8I+g])
-                {
-                    const int Ja = J0 > I + 1 ? J0 : I + 1, Jb = J1;
-                    const cplx* ap = A22 + (size_t)(2 * q) * N + 8 * I + g;      // column 8I+g < m always (I < nt - 1 here)
-                    const cplx z = cmake(0.0, 0.0);
-                    auto ld2 = [&](int J, cplx& x0, cplx& x1) {
-                        const int r0 = 8 * J + 2 * q;
-                        x0 = r0 < m ? ldcg(ap + (size_t)8 * J * N) : z;
-                        x1 = r0 + 1 < m ? ldcg(ap + (size_t)(8 * J + 1) * N) : z;
-                    };
-                    cplx n0 = z, n1 = z, f0 = z, f1 = z, h0 = z, h1 = z;
-                    if (Ja < Jb) ld2(Ja, n0, n1);
-                    if (Ja + 1 < Jb) ld2(Ja + 1, f0, f1);
-                    if (Ja + 2 < Jb) ld2(Ja + 2, h0, h1);
-                    for (int J = Ja; J < Jb; J += 3) {
-                        s1_xtile<true>(Xr, Xi, Zr, Zi, n0, n1, Ps, mp, 8 * J + 2 * q, g);
-                        if (J + 3 < Jb) ld2(J + 3, n0, n1);
-                        if (J + 1 < Jb) {
-                            s1_xtile<true>(Xr, Xi, Zr, Zi, f0, f1, Ps, mp, 8 * J + 8 + 2 * q, g);
-                            if (J + 4 < Jb) ld2(J + 4, f0, f1);
-                        }
-                        if (J + 2 < Jb) {
-                            s1_xtile<true>(Xr, Xi, Zr, Zi, h0, h1, Ps, mp, 8 * J + 16 + 2 * q, g);
-                            if (J + 5 < Jb) ld2(J + 5, h0, h1);
-                        }
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int k = 0; k < RD - 1; ++k) issue(k);
+                double Xr[2][2] = {{0, 0}, {0, 0}}, Xi[2][2] = {{0, 0}, {0, 0}}, Zr[2][2] = {{0, 0}, {0, 0}}, Zi[2][2] = {{0, 0}, {0, 0}};
+                int stage = 0;
+                while (uC < nunits) {
+                    issue(stage == 0 ? RD - 1 : stage - 1);
+                    cp_async_wait<RD - 1>();
+                    cplx a0 = ring[stage * 64], a1 = ring[stage * 64 + 32];
+                    const int I = iC, J = jC;
+                    if (J > I) { a0.y = dneg(a0.y); a1.y = dneg(a1.y); }
+                    else if (J == I) {
+                        const int row = 8 * I + g, col = 8 * I + 2 * q;
+                        if (row < col) a0.y = dneg(a0.y); else if (row == col) a0.y = 0.0;
+                        if (row < col + 1) a1.y = dneg(a1.y); else if (row == col + 1) a1.y = 0.0;
                     }
+                    s1_xtile<false>(Xr, Xi, Zr, Zi, a0, a1, Ps, mp, 8 * J + 2 * q, g);
+                    if (++jC >= j1C) {
+                        // partial Y tile -> Yp[p] (C layout: row g, columns 8t + 2q, 8t + 2q + 1)
+                        cplx* xp = Yp + ((size_t)pC * NR + 8 * I + g) * SB + 2 * q;
+                        xp[0] = cmake(Xr[0][0] + Zr[0][0], Xi[0][0] + Zi[0][0]); xp[1] = cmake(Xr[0][1] + Zr[0][1], Xi[0][1] + Zi[0][1]);
+                        xp[8] = cmake(Xr[1][0] + Zr[1][0], Xi[1][0] + Zi[1][0]); xp[9] = cmake(Xr[1][1] + Zr[1][1], Xi[1][1] + Zi[1][1]);
+#pragma unroll
+                        for (int t2 = 0; t2 < 2; ++t2) { Xr[t2][0] = Xr[t2][1] = Xi[t2][0] = Xi[t2][1] = Zr[t2][0] = Zr[t2][1] = Zi[t2][0] = Zi[t2][1] = 0.0; }
+                        uC += S1_WARPS;
+                        if (uC < nunits) unit_of(uC, iC, pC, jC, j1C);
+                    }
+                    stage = stage + 1 == RD ? 0 : stage + 1;
                 }
-                // partial Y tile -> Yp[p] (C layout: row g, columns 8t + 2q, 8t + 2q + 1)
-                cplx* xp = Yp + ((size_t)p * NR + row) * SB + 2 * q;
-                xp[0] = cmake(Xr[0][0] + Zr[0][0], Xi[0][0] + Zi[0][0]); xp[1] = cmake(Xr[0][1] + Zr[0][1], Xi[0][1] + Zi[0][1]);
-                xp[8] = cmake(Xr[1][0] + Zr[1][0], Xi[1][0] + Zi[1][0]); xp[9] = cmake(Xr[1][1] + Zr[1][1], Xi[1][1] + Zi[1][1]);
+                cp_async_wait<0>();
             }
             S1_WMARK(10)
             __syncthreads();
@@ -476,18 +526,35 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                 while ((I + 1) * (I + 2) / 2 <= t) ++I;
                 while (I * (I + 1) / 2 > t) --I;
                 int J = t - I * (I + 1) / 2;
-                int In = I, Jn = J;                                      // position of the tile to prefetch next
-                cplx cA0, cA1, wA0, wA1, wA2, wA3;                       // buffer A: C entries and the W_J operands of a tile
-                cplx cB0, cB1, wB0, wB1, wB2, wB3;                       // buffer B
-                cA0 = cA1 = wA0 = wA1 = wA2 = wA3 = cB0 = cB1 = wB0 = wB1 = wB2 = wB3 = cmake(0.0, 0.0);
-                if (t < t1) s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cA0, cA1, wA0, wA1, wA2, wA3);
-                if (++Jn > In) { ++In; Jn = 0; }
-                if (t + 1 < t1) s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cB0, cB1, wB0, wB1, wB2, wB3);
+                // C tiles: cp.async ring, RD - 1 tiles ahead; W_J operands: registers, one tile ahead (two buffers, no register rotation)
+                int Ic = I, Jc = J, tc = t;                              // issue cursor of the C ring
+                auto issue_c = [&](int stage) {
+                    if (tc < t1) {
+                        const int row = 8 * Ic + g, col = 8 * Jc + 2 * q;
+                        const cplx* cp = A22 + (size_t)row * N + col;
+                        const bool ok0 = row < m && col < m, ok1 = row < m && col + 1 < m;
+                        cplx* dst = ring + stage * 64;
+                        cp_async16(dst, ok0 ? cp : A22, ok0); cp_async16(dst + 32, ok1 ? cp + 1 : A22, ok1);
+                        ++tc; if (++Jc > Ic) { ++Ic; Jc = 0; }
+                    }
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int k = 0; k < RD - 1; ++k) issue_c(k);
+                int stage = 0;
+                int In = I, Jn = J;                                      // position of the W operands to prefetch next
+                cplx wA0, wA1, wA2, wA3, wB0, wB1, wB2, wB3;
+                wA0 = wA1 = wA2 = wA3 = wB0 = wB1 = wB2 = wB3 = cmake(0.0, 0.0);
+                auto load_w = [&](int Jj, cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
+                    const cplx* wj = Wg + (size_t)(8 * Jj + g) * SB + 2 * q;      // k index of (q, s) = 2q + (s & 1) + 8 (s >> 1)
+                    x0 = wj[0]; x1 = wj[1]; x2 = wj[8]; x3 = wj[9];
+                };
+                if (t < t1) load_w(Jn, wA0, wA1, wA2, wA3);
                 if (++Jn > In) { ++In; Jn = 0; }
                 int Irow = -1;
                 cplx vI0, vI1, vI2, vI3, wI0, wI1, wI2, wI3;
                 vI0 = vI1 = vI2 = vI3 = wI0 = wI1 = wI2 = wI3 = cmake(0.0, 0.0);
-#define SKTB_S1_TILE(C0, C1, W0, W1, W2, W3)                                                                              \
+#define SKTB_S1_TILE(W0, W1, W2, W3)                                                                                       \
                     {                                                                                                      \
                         if (I != Irow) {                                                                                   \
                             const int rw = 8 * I + g;                                                                      \
@@ -497,26 +564,31 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                             wI0 = wp[0]; wI1 = wp[1]; wI2 = wp[8]; wI3 = wp[9];                                            \
                             Irow = I;                                                                                      \
                         }                                                                                                  \
+                        issue_c(stage == 0 ? RD - 1 : stage - 1);                                                          \
+                        cp_async_wait<RD - 1>();                                                                           \
+                        const cplx C0 = ring[stage * 64], C1 = ring[stage * 64 + 32];                                      \
+                        stage = stage + 1 == RD ? 0 : stage + 1;                                                           \
                         const int row = 8 * I + g, col = 8 * J + 2 * q;                                                    \
                         double Pr[2] = {0, 0}, Pp[2] = {0, 0}, Pm[2] = {0, 0}, Qr[2] = {0, 0}, Qp[2] = {0, 0}, Qm[2] = {0, 0};      \
                         const cplx* vp = Ps + (size_t)(2 * q) * mp + 8 * J + g;                                            \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI0, wI0, vp[0], W0);                                                           \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI1, wI1, vp[mp], W1);                                                          \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI2, wI2, vp[(size_t)8 * mp], W2);                                              \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI3, wI3, vp[(size_t)9 * mp], W3);                                              \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI0, wI0, vp[0], W0);                                               \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI1, wI1, vp[mp], W1);                                              \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI2, wI2, vp[(size_t)8 * mp], W2);                                  \
+                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI3, wI3, vp[(size_t)9 * mp], W3);                                  \
                         cplx* cp = A22 + (size_t)row * N + col;                                                            \
                         if (row < m && col < m) cp[0] = cmake(C0.x - (Pr[0] + Qr[0]), C0.y - ((Pp[0] + Qp[0]) - (Pm[0] + Qm[0])));  \
                         if (row < m && col + 1 < m) cp[1] = cmake(C1.x - (Pr[1] + Qr[1]), C1.y - ((Pp[1] + Qp[1]) - (Pm[1] + Qm[1])));  \
                         if (++J > I) { ++I; J = 0; }                                                                       \
                     }
                 for (; t < t1; t += 2) {
-                    SKTB_S1_TILE(cA0, cA1, wA0, wA1, wA2, wA3)
-                    if (t + 2 < t1) { s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cA0, cA1, wA0, wA1, wA2, wA3); if (++Jn > In) { ++In; Jn = 0; } }
+                    if (t + 1 < t1) { load_w(Jn, wB0, wB1, wB2, wB3); if (++Jn > In) { ++In; Jn = 0; } }
+                    SKTB_S1_TILE(wA0, wA1, wA2, wA3)
                     if (t + 1 < t1) {
-                        SKTB_S1_TILE(cB0, cB1, wB0, wB1, wB2, wB3)
-                        if (t + 3 < t1) { s1_prefetch(A22, Wg, N, m, In, Jn, g, q, cB0, cB1, wB0, wB1, wB2, wB3); if (++Jn > In) { ++In; Jn = 0; } }
+                        if (t + 2 < t1) { load_w(Jn, wA0, wA1, wA2, wA3); if (++Jn > In) { ++In; Jn = 0; } }
+                        SKTB_S1_TILE(wB0, wB1, wB2, wB3)
                     }
                 }
+                cp_async_wait<0>();
 #undef SKTB_S1_TILE
                 S1_WMARK(11)
             }
@@ -549,7 +621,7 @@ constexpr int S2_WARPS = 8;
 constexpr int S2_DONE = 1 << 30;
 constexpr int S2_DS = SB + 1;                       // row stride of the D slab (conflict-free rows and columns)
 constexpr int S2_SLAB = SB * S2_DS + 3 * SB;        // per warp: D block, v_a, v_b, w
-SKTB_HD size_t stage2_smem_bytes(int N) { return (size_t)S2_WARPS * S2_SLAB * sizeof(cplx) + (size_t)N * sizeof(int); }
+SKTB_HD size_t stage2_smem_bytes(int N) { return (size_t)S2_WARPS * S2_SLAB * sizeof(cplx) + (size_t)2 * N * sizeof(int); }
 
 // lower triangle of the diagonal block rows/cols r1 .. r1+L-1 -> slab Ds[r][c] (c <= r), zero padded to 16 x 16
 template <bool FULL>
@@ -676,9 +748,15 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) 
     cplx* Ds = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * S2_SLAB;
     cplx* vecs = Ds + SB * S2_DS;                              // v_a, v_b, w
     volatile int* prog = reinterpret_cast<volatile int*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)S2_WARPS * S2_SLAB);
+    int* roff = const_cast<int*>(prog) + N;                    // first reflector index of every sweep (recording only)
+    if (a.Rstore) {
+        if (tid == 0) { int k = 0; for (int s = 0; s < N - 1; ++s) { roff[s] = k; k += (N - 1 - s + SB - 1) / SB; } }
+        __syncthreads();
+    }
 
     for (long long mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
         cplx* AB = a.AB + (size_t)mat * N * ABW;
+        cplx* Rst = a.Rstore ? a.Rstore + (size_t)mat * a.rstride : nullptr;
         __syncthreads();
         for (int s = tid; s < N; s += S2_WARPS * 32) prog[s] = 0;
         __syncthreads();
@@ -704,6 +782,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) 
             cplx v = s2_reflector(x, r, L, beta, tau);
             if (hh == 0 && r < L) __stcg(AB + s * ABW + 1 + r, r == 0 ? cmake(beta, 0.0) : cmake(0.0, 0.0));
             if (hh == 0) vS[r] = v;
+            if (Rst && hh == 0) { cplx* rp = Rst + (size_t)roff[s] * (SB + 1); rp[r] = v; if (r == 0) rp[SB] = tau; }
             __syncwarp();
             int r0 = s + 1;
             s2_two_sided<false>(AB, r0, L, vS, wS, Ds, tau, r, hh);
@@ -717,6 +796,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) 
                 cplx tau2;
                 if (L == SB && L2 == SB) s2_hop<true>(AB, r0, L, r1, L2, vS, v2S, wS, Ds, tau, tau2, r, hh);
                 else s2_hop<false>(AB, r0, L, r1, L2, vS, v2S, wS, Ds, tau, tau2, r, hh);
+                if (Rst && hh == 0) { cplx* rp = Rst + (size_t)(roff[s] + h) * (SB + 1); rp[r] = v2S[r]; if (r == 0) rp[SB] = tau2; }
                 publish(++h);
                 cplx* tmp = vS; vS = v2S; v2S = tmp;
                 tau = tau2; L = L2; r0 = r1;
@@ -736,14 +816,13 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) 
 // p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (3 FP64 operations per row; the quotient form q_i = d_i - x - e^2 / q_{i-1} of dstebz costs a
 // division, ~10 FP64 operations with a Newton reciprocal - at N = 512 the bisection was as expensive as the band reduction).  The matrix is
 // scaled by an exact power of two so that |d|, |e| <= 1, (p_{i-1}, p_i) are renormalised by a power of two whenever the exponent leaves
-// +-300 (integer test per row), an exact zero is replaced by -2^-100 p_{i-1} (counted as a sign change, dstebz's pivmin rule).
+// +-300 (integer test every 8 rows), an exact zero is replaced by -2^-100 p_{i-1} (counted as a sign change, dstebz's pivmin rule).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) bisect_prod_kernel(const double* __restrict__ de, int N, long long nm, double* __restrict__ evals,
                                                            long long ld, long long col0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* d = reinterpret_cast<double*>(smem_raw);
-    double* e2 = d + N;
-    double* red = e2 + N;                                                 // [3][32]
+    double2* de2 = reinterpret_cast<double2*>(smem_raw);                  // [N] (d_r, e_{r-1}^2), scaled
+    double* red = reinterpret_cast<double*>(de2 + N);                     // [3][32]
     const int tid = threadIdx.x, T = blockDim.x;
     for (long long mat = blockIdx.x; mat < nm; mat += gridDim.x) {
         const double* hd = de + (size_t)mat * 2 * N;
@@ -767,7 +846,8 @@ __global__ void __launch_bounds__(1024) bisect_prod_kernel(const double* __restr
         const double sc = scalbn(1.0, -ex), isc = scalbn(1.0, ex);
         di *= sc; el *= sc; er *= sc;
         double lo_b = 1e300, hi_b = -1e300;
-        if (tid < N) { d[tid] = di; e2[tid] = er * er; lo_b = di - el - er; hi_b = di + el + er; }
+        // rows interleaved: de2[r] = (d_r, e_{r-1}^2): one 16-byte broadcast load per Sturm step
+        if (tid < N) { de2[tid] = make_double2(di, el * el); lo_b = di - el - er; hi_b = di + el + er; }
         for (int o = 16; o > 0; o >>= 1) {
             lo_b = fmin(lo_b, __shfl_xor_sync(0xffffffffu, lo_b, o));
             hi_b = fmax(hi_b, __shfl_xor_sync(0xffffffffu, hi_b, o));
@@ -782,28 +862,148 @@ __global__ void __launch_bounds__(1024) bisect_prod_kernel(const double* __restr
         gl -= 2.0 * eps * N + 2.0 * pivmin; gu += 2.0 * eps * N + 2.0 * pivmin;
         if (tid < N) {
             double lo = gl, hi = gu;
+            const double tiny = -7.888609052210118e-31;                   // -2^-100
             for (int it = 0; it < 128; ++it) {
                 const double x = 0.5 * (lo + hi);
                 if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
-                double p0 = 1.0, p1 = d[0] - x;
-                if (p1 == 0.0) p1 = -7.888609052210118e-31;               // -2^-100 p0
+                double p0 = 1.0, p1 = de2[0].x - x;
+                if (p1 == 0.0) p1 = tiny;
                 int cnt = p1 < 0.0;
-                for (int r = 1; r < N; ++r) {
-                    double pn = fma(d[r] - x, p1, -(e2[r - 1] * p0));
-                    if (pn == 0.0) pn = -7.888609052210118e-31 * p1;
-                    const int hn = __double2hiint(pn);
-                    cnt += (unsigned)(hn ^ __double2hiint(p1)) >> 31;
-                    p0 = p1; p1 = pn;
-                    const int exq = ((hn >> 20) & 0x7ff) - 1023;
-                    if (exq > 300 || exq < -300) {                        // renormalise the pair by 2^-exq (exact)
-                        const double rs = __hiloint2double((1023 - exq) << 20, 0);
+                int r = 1;
+                // careful step: an exact zero becomes -2^-100 p_{i-1} (a sign change, dstebz's pivmin rule)
+#define SKTB_STURM_STEP(RR)                                                                         \
+                {                                                                                   \
+                    const double2 v = de2[RR];                                                      \
+                    double pn = fma(v.x - x, p1, -(v.y * p0));                                      \
+                    if (pn == 0.0) pn = tiny * p1;                                                  \
+                    cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p1)) >> 31;               \
+                    p0 = p1; p1 = pn;                                                               \
+                }
+                // fast step: no zero test on the FP64 pipe; `nz` collects min over the block of (bits of |p| != 0) with integer operations
+#define SKTB_STURM_FAST(RR)                                                                         \
+                {                                                                                   \
+                    const double2 v = de2[RR];                                                      \
+                    const double pn = fma(v.x - x, p1, -(v.y * p0));                                \
+                    const int hn = __double2hiint(pn);                                              \
+                    cnt += (unsigned)(hn ^ __double2hiint(p1)) >> 31;                               \
+                    nz = min(nz, (unsigned)(hn << 1) | (unsigned)__double2loint(pn));               \
+                    p0 = p1; p1 = pn;                                                               \
+                }
+                for (; r + 8 <= N; r += 8) {
+                    const double s0 = p0, s1 = p1; const int sc0 = cnt;
+                    unsigned nz = 0xffffffffu;
+                    SKTB_STURM_FAST(r) SKTB_STURM_FAST(r + 1) SKTB_STURM_FAST(r + 2) SKTB_STURM_FAST(r + 3)
+                    SKTB_STURM_FAST(r + 4) SKTB_STURM_FAST(r + 5) SKTB_STURM_FAST(r + 6) SKTB_STURM_FAST(r + 7)
+                    if (nz == 0u) {                                       // some p was exactly zero (rare): redo the block carefully
+                        p0 = s0; p1 = s1; cnt = sc0;
+                        for (int q = 0; q < 8; ++q) SKTB_STURM_STEP(r + q)
+                    }
+                    // per step |p| grows by < 2^2.2 (|d - x| <= 4, e^2 <= 1): renormalise the pair by an exact power of two every 8 rows
+                    const int exq = ((__double2hiint(p1) >> 20) & 0x7ff) - 1023;
+                    if (exq > 300 || exq < -300) {
+                        const double rs = __hiloint2double((1023 - max(exq, -1000)) << 20, 0);
                         p0 *= rs; p1 *= rs;
                     }
                 }
+                for (; r < N; ++r) SKTB_STURM_STEP(r)
+#undef SKTB_STURM_STEP
+#undef SKTB_STURM_FAST
                 if (cnt > tid) hi = x; else lo = x;
             }
             evals[(long long)tid * ld + col0 + mat] = 0.5 * (lo + hi) * isc;
         }
+    }
+}
+// ---------------------------------------------------------------------------------------------------------------------
+// Selected rows of U = Q1 Q2 Z after the two-stage reduction (LDOS / spectral projections need a few rows only): p = Q2^H Q1^H e_i by
+// applying the block reflectors of stage 1 (V in the panels of H, T in Tstore) and then the chase reflectors in sweep / hop order,
+// then U[i, n] = sum_k conj(p_k) Z[k, n].  One (matrix, row) per warp, p in shared memory.  O(N^2) per row.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ROWS_WARPS = 8;
+__global__ void __launch_bounds__(ROWS_WARPS * 32) rows_kernel(RowsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cplx* us = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * N;
+    const long long total = a.nm * a.n_rows;
+    for (long long work = (long long)blockIdx.x * ROWS_WARPS + warp; work < total; work += (long long)gridDim.x * ROWS_WARPS) {
+        const long long mat = work / a.n_rows;
+        const int r = (int)(work - mat * a.n_rows);
+        const int irow = a.rows[r];
+        const cplx* H = a.H + (size_t)mat * N * N;
+        for (int i = lane; i < N; i += 32) us[i] = cmake(i == irow ? 1.0 : 0.0, 0.0);
+        __syncwarp();
+        // ---- Q1^H: u <- u - V T^H (V^H u), panel by panel ----
+        for (int p = 0; p < a.npanels; ++p) {
+            const int c0 = SB * p, R = c0 + SB, m = N - R;
+            cplx y[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) y[c] = cmake(0.0, 0.0);
+            for (int rr = lane; rr < m; rr += 32) {
+                const cplx ur = us[R + rr];
+                const cplx* vp = H + (size_t)(R + rr) * N + c0;
+#pragma unroll
+                for (int c = 0; c < SB; ++c) cfmac(y[c], vp[c], ur);
+            }
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { y[c].x += __shfl_xor_sync(0xffffffffu, y[c].x, o); y[c].y += __shfl_xor_sync(0xffffffffu, y[c].y, o); }
+            }
+            // z = T^H y (lane i < 16 computes z_i), then every lane gets all of z
+            const cplx* Tp = a.Tstore + ((size_t)mat * a.npanels + p) * SB * SB;
+            cplx zi = cmake(0.0, 0.0);
+            if (lane < SB) {
+#pragma unroll
+                for (int k = 0; k < SB; ++k) if (k <= lane) cfmac(zi, Tp[k * SB + lane], y[k]);
+            }
+            cplx z[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) { z[c].x = __shfl_sync(0xffffffffu, zi.x, c); z[c].y = __shfl_sync(0xffffffffu, zi.y, c); }
+            for (int rr = lane; rr < m; rr += 32) {
+                cplx ur = us[R + rr];
+                const cplx* vp = H + (size_t)(R + rr) * N + c0;
+#pragma unroll
+                for (int c = 0; c < SB; ++c) cfms(ur, vp[c], z[c]);
+                us[R + rr] = ur;
+            }
+            __syncwarp();
+        }
+        // ---- Q2^H: the chase reflectors in sweep / hop order, 16 lanes each (lanes >= 16 mirror) ----
+        {
+            const cplx* rp = a.Rstore + (size_t)mat * a.rstride;
+            const int l = lane & 15;
+            cplx vn = rp[l], tn = rp[SB];                                 // reflector 0
+            for (int s = 0; s < N - 1; ++s) {
+                for (int R0 = s + 1; R0 < N; R0 += SB) {
+                    const cplx v = vn, tau = tn;
+                    rp += SB + 1;
+                    vn = rp[l]; tn = rp[SB];                              // next reflector (one slot of slack behind the last one)
+                    const int L = min(SB, N - R0);
+                    const cplx x = l < L ? us[R0 + l] : cmake(0.0, 0.0);
+                    cplx dot = cmulc(v, x);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) { dot.x += __shfl_xor_sync(0xffffffffu, dot.x, o); dot.y += __shfl_xor_sync(0xffffffffu, dot.y, o); }
+                    const cplx wv = cmul(cconj(tau), dot);
+                    cplx xn = x; cfms(xn, wv, v);
+                    if (lane < L) us[R0 + lane] = xn;
+                    __syncwarp();
+                }
+            }
+        }
+        // ---- rows of U ----
+        const double* Zm = a.Zf + (size_t)mat * a.zstride;
+        for (int n = lane; n < N; n += 32) {
+            double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+            int k = 0;
+            for (; k + 1 < N; k += 2) {
+                const double z0 = Zm[(size_t)k * N + n], z1 = Zm[(size_t)(k + 1) * N + n];
+                const cplx p0 = us[k], p1 = us[k + 1];
+                ax = fma(p0.x, z0, ax); ay = fma(-p0.y, z0, ay); bx = fma(p1.x, z1, bx); by = fma(-p1.y, z1, by);
+            }
+            if (k < N) { const double z0 = Zm[(size_t)k * N + n]; const cplx p0 = us[k]; ax = fma(p0.x, z0, ax); ay = fma(-p0.y, z0, ay); }
+            a.vec_out[(long long)n * a.vs_band + (a.vcol0 + mat) * a.vs_k + r] = cmake(ax + bx, ay + by);
+        }
+        __syncwarp();
     }
 }
 #endif  // __CUDACC__

@@ -428,6 +428,17 @@ static int launch_heev_generic_phase(sktb_plan* p, HeevArgs a, cudaStream_t st, 
 // bisection kernel takes the merged (d, e).
 static const int PEEL_MAX = getenv("SKTB_PEEL_MAX") ? atoi(getenv("SKTB_PEEL_MAX")) : 320;
 static size_t peel_bytes_per_k(int N) { return (size_t)2 * (N - 56) * 8 + small::cta64_bytes_per_k(); }   // P <= N - 57
+// Two-stage tridiagonalisation (heev_twostage.cuh: dense -> band 16 on DMMA, band -> tridiagonal by bulge chasing) + bisection:
+// eigenvalues only, N >= SKTB_TWOSTAGE_MIN.  The one-stage kernels read the trailing matrix once per reflector and are HBM-bound
+// from N ~ 300 up; here the matrix is read twice and written once per 16 reflectors.
+static int twostage_min() { static const int v = getenv("SKTB_TWOSTAGE_MIN") ? atoi(getenv("SKTB_TWOSTAGE_MIN")) : 224; return v; }   // measured, 296 matrices: N = 192 old 8.8e4 / new 7.6e4 per s, N = 256 3.7e4 / 4.9e4
+static bool use_twostage(int N) { return N >= twostage_min() && twostage::supported(N); }
+// scratch per matrix of the eigenvalues-only paths above N = 64 (HeevArgs::peel_ws): peeled run or two-stage
+static size_t evals_ws_bytes_per_k(int N) {
+    if (N <= 64) return 0;
+    if (use_twostage(N)) return twostage::scratch_bytes_per_matrix(N);
+    return N <= PEEL_MAX ? peel_bytes_per_k(N) : 0;
+}
 static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     const int N = a.N;
     const int nb = N >= 160 ? 8 : 4;
@@ -465,16 +476,12 @@ static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     return 0;
 }
 
-// Two-stage tridiagonalisation (heev_twostage.cuh: dense -> band 16 on DMMA, band -> tridiagonal by bulge chasing) + bisection:
-// eigenvalues only, N >= SKTB_TWOSTAGE_MIN.  The one-stage kernels read the trailing matrix once per reflector and are HBM-bound
-// from N ~ 300 up; here the matrix is read twice and written once per 16 reflectors.
-static int twostage_min() { static const int v = getenv("SKTB_TWOSTAGE_MIN") ? atoi(getenv("SKTB_TWOSTAGE_MIN")) : 352; return v; }
-static bool use_twostage(int N) { return N >= twostage_min() && twostage::supported(N); }
-// scratch per matrix of the eigenvalues-only paths above N = 64 (HeevArgs::peel_ws): peeled run or two-stage
-static size_t evals_ws_bytes_per_k(int N) {
-    if (N <= 64) return 0;
-    if (use_twostage(N)) return twostage::scratch_bytes_per_matrix(N);
-    return N <= PEEL_MAX ? peel_bytes_per_k(N) : 0;
+// chunk size of the two-stage path: whole waves of both persistent grids (148 CTAs of stage 1, 3 x 148 of the bulge chase)
+static long long twostage_chunk(int N, long long n, size_t bytes_per_k) {
+    long long c = std::max<long long>(1, std::min<long long>(n, (long long)(((size_t)4 << 30) / bytes_per_k)));
+    if (c >= n) return n;
+    if (c >= 444) c = c / 444 * 444; else if (c >= 148) c = c / 148 * 148;
+    return c;
 }
 static int launch_heev_twostage(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     const int N = a.N;
@@ -536,8 +543,16 @@ static int launch_vecbt_big(const BigVecArgs& b, cudaStream_t st, int sms) {
     LAUNCHED();
     return 0;
 }
+// Selected rows (LDOS / spectral projections) on top of the two-stage reduction: scratch holds the bigvec layout (the reflector region
+// takes the chase reflectors and the T factors), ts_scratch the two-stage workspace.  N >= SKTB_TWOSTAGE_MIN only.
+static bool bigvec_twostage(int N, int n_rows) {
+    static const bool off = getenv("SKTB_TWOSTAGE_ROWS") && getenv("SKTB_TWOSTAGE_ROWS")[0] == '0';
+    return !off && n_rows > 0 && use_twostage(N) &&
+           ((size_t)(twostage::chase_reflectors(N) + 1) * (twostage::SB + 1) + (size_t)twostage::stage1_panels(N) * twostage::SB * twostage::SB) <= (size_t)N * N;
+}
 static int launch_bigvec(sktb_plan* p, cplx* H, int N, long long nm, double* evals_d, long long ld, long long col0, cplx* vec_out,
-                         long long vs_band, long long vs_k, long long vcol0, int n_rows, const int* rows_d, void* scratch, cudaStream_t st) {
+                         long long vs_band, long long vs_k, long long vcol0, int n_rows, const int* rows_d, void* scratch, cudaStream_t st,
+                         void* ts_scratch = nullptr) {
     const size_t nn = (size_t)N * N;
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);      // 16-byte types first: every segment stays aligned for odd N
     cplx* vstore = reinterpret_cast<cplx*>(base);                      base += (size_t)nm * nn * 16;
@@ -546,6 +561,35 @@ static int launch_bigvec(sktb_plan* p, cplx* H, int N, long long nm, double* eva
     double* lu = reinterpret_cast<double*>(base);                      base += (size_t)nm * 4 * nn * 8;
     double* de = reinterpret_cast<double*>(base);                      base += (size_t)nm * 2 * N * 8;
     unsigned char* pin = base;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ts_scratch && bigvec_twostage(N, n_rows)) {
+        const long long rstride = (twostage::chase_reflectors(N) + 1) * (twostage::SB + 1);
+        cplx* Rstore = vstore;                                            // [nm][nn] region: chase reflectors, then the T factors
+        cplx* Tstore = vstore + (size_t)nm * rstride;
+        if ((size_t)nm * rstride + (size_t)nm * twostage::stage1_panels(N) * twostage::SB * twostage::SB > (size_t)nm * nn) return fail("two-stage rows: reflector store too small");
+        char info[320];
+        const int rl = twostage::launch_tridiag_keep(H, N, nm, ts_scratch, de, Tstore, Rstore, rstride, st, info, sizeof info);
+        if (rl < 0) return fail("two-stage tridiagonalisation does not support N = %d", N);
+        g_launches += rl;
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail("two-stage launch: %s", cudaGetErrorString(e_)); }
+        BigVecArgs b{};
+        b.N = N; b.nm = nm; b.de = de; b.evals = evals_d; b.ld = ld; b.col0 = col0;
+        b.Z = Z; b.lu = lu; b.pin = pin; b.vstore = vstore; b.taustore = taus;
+        b.vec_out = vec_out; b.vs_band = vs_band; b.vs_k = vs_k; b.vcol0 = vcol0; b.n_rows = n_rows; b.rows = rows_d;
+        const int T = (N + 31) / 32 * 32;
+        stein_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, (size_t)4 * N * 8, st>>>(b);
+        LAUNCHED();
+        twostage::RowsArgs ra{};
+        ra.N = N; ra.nm = nm; ra.H = H; ra.Tstore = Tstore; ra.npanels = twostage::stage1_panels(N); ra.Rstore = Rstore; ra.rstride = rstride;
+        ra.Zf = lu; ra.zstride = (long long)4 * N * N;
+        ra.vec_out = vec_out; ra.vs_band = vs_band; ra.vs_k = vs_k; ra.vcol0 = vcol0; ra.n_rows = n_rows; ra.rows = rows_d;
+        if (twostage::launch_rows(ra, st) < 0) return fail("two-stage rows kernel launch failed");
+        LAUNCHED();
+        g_kinfo = std::string(info) + " (reflectors kept) + stein (bisection + inverse iteration, 1 eigenpair/thread) + rows_kernel (selected rows of Q1 Q2, then of U)";
+        return 0;
+    }
     HeevArgs a{};
     a.H = H; a.N = N; a.nm = (int)nm;
     a.evals = evals_d; a.ld = ld; a.col0 = col0;
@@ -553,9 +597,6 @@ static int launch_bigvec(sktb_plan* p, cplx* H, int N, long long nm, double* eva
     int rc = launch_heev_generic_phase(p, a, st, 1);                  // tridiagonalisation only: (d, e) and the reflectors are kept
     if (rc) return rc;
     const std::string first = g_kinfo;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     BigVecArgs b{};
     b.N = N; b.nm = nm; b.de = de; b.evals = evals_d; b.ld = ld; b.col0 = col0;
     b.Z = Z; b.lu = lu; b.pin = pin; b.vstore = vstore; b.taustore = taus;
@@ -706,6 +747,10 @@ static int solve_impl(sktb_plan* p, const double* k_d, const int32_t* nk_mesh, l
         if (W.H.ensure(perH * chunk)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
         if (want_vecs && W.RT.ensure(bigvec ? bigvec_bytes_per_matrix(N) * chunk : perH * chunk)) return fail("out of device memory (RT workspace)");
         const bool peel = !want_vecs && evals_ws_bytes_per_k(N) > 0;
+        if (peel && use_twostage(N)) {
+            chunk = twostage_chunk(N, nk, perH);
+            if (W.H.ensure(perH * chunk)) return fail("out of device memory (H workspace %zu B)", perH * chunk);
+        }
         if (peel && W.S.ensure(evals_ws_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
         if (!k_d && W.K.ensure((size_t)chunk * 3 * 8)) return fail("out of device memory (k workspace)");
         for (long long c0 = 0; c0 < nk; c0 += chunk) {
@@ -843,6 +888,10 @@ extern "C" int sktb_heev(sktb_plan* p, const double* H_d, int32_t N, int64_t nm,
     if (p->ws[2].H.ensure(perH * chunk) || (evecs_d && p->ws[2].RT.ensure(bigvec ? bigvec_bytes_per_matrix(N) * chunk : perH * chunk)))
         return fail("out of device memory (heev workspace)");
     const bool peel = !evecs_d && evals_ws_bytes_per_k(N) > 0 && !heev_generic_only;
+    if (peel && use_twostage(N)) {
+        chunk = twostage_chunk(N, nm, perH);
+        if (p->ws[2].H.ensure(perH * chunk)) return fail("out of device memory (heev workspace)");
+    }
     if (peel && p->ws[2].S.ensure(evals_ws_bytes_per_k(N) * chunk)) return fail("out of device memory (peel workspace)");
     for (long long c0 = 0; c0 < nm; c0 += chunk) {
         long long cnt = std::min(chunk, (long long)nm - c0);
@@ -1063,8 +1112,13 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
                 a.vec_out = (cplx*)p->wsVec.p; a.vs_band = cnt * n_rows; a.vs_k = n_rows; a.vcol0 = 0;
             }
             if (dos_bigvec) {
+                void* ts_ws = nullptr;
+                if (bigvec_twostage(N, n_rows)) {
+                    if (p->ws[2].S.ensure((size_t)cnt * twostage::scratch_bytes_per_matrix(N))) return fail("out of device memory (two-stage workspace)");
+                    ts_ws = p->ws[2].S.p;
+                }
                 rc = launch_bigvec(p, (cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, cnt, 0, (cplx*)p->wsVec.p, cnt * n_rows, n_rows, 0, n_rows, d_rows,
-                                   p->ws[2].RT.p, st);
+                                   p->ws[2].RT.p, st, ts_ws);
                 if (rc) return rc;
             } else if (use_vec64) {
                 int rl = small::launch_vec64((const cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, (cplx*)p->wsVec.p, cnt, 0, p->d_fail, p->ws[2].RT.p, st, &g_kinfo);
@@ -1185,7 +1239,12 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
                 a.H = (cplx*)p->ws[2].H.p; a.N = N; a.nm = (int)cnt;
                 a.evals = (double*)p->wsE.p; a.ld = cnt; a.col0 = 0;
                 if (sp_bigvec) {
-                    rc = launch_bigvec(p, (cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, cnt, 0, (cplx*)p->wsVec.p, cnt * nr, nr, 0, nr, d_rows, p->ws[2].RT.p, st);
+                    void* ts_ws = nullptr;
+                    if (bigvec_twostage(N, nr)) {
+                        if (p->ws[2].S.ensure((size_t)cnt * twostage::scratch_bytes_per_matrix(N))) return fail("out of device memory (two-stage workspace)");
+                        ts_ws = p->ws[2].S.p;
+                    }
+                    rc = launch_bigvec(p, (cplx*)p->ws[2].H.p, N, cnt, (double*)p->wsE.p, cnt, 0, (cplx*)p->wsVec.p, cnt * nr, nr, 0, nr, d_rows, p->ws[2].RT.p, st, ts_ws);
                     if (rc) return rc;
                 } else {
                 if (nr) {

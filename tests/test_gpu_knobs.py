@@ -62,6 +62,9 @@ CASES = {
     "SKTB_VEC32_SPLIT=0": [(32, 200, True), (20, 100, True), (32, 300, False), (9, 50, False)],
     "SKTB_NO_PAIR=1": [(32, 300, False), (26, 300, False)],
     "SKTB_HEEV_GENERIC=1": [(8, 50, False), (32, 50, True), (64, 30, False)],
+    "SKTB_TWOSTAGE_MIN=65": [(65, 40, False), (100, 30, False), (200, 20, False), (333, 7, False), (130, 10, True)],   # two-stage from N = 65 (vectors: unaffected)
+    "SKTB_TWOSTAGE_MIN=100000": [(352, 8, False), (512, 5, False)],                                                    # one-stage path for every N
+    "SKTB_TWOSTAGE_BISECT=0": [(352, 8, False), (400, 6, False)],                                                      # quotient-form Sturm count
 }
 
 

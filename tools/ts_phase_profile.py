@@ -16,6 +16,7 @@ for rep in range(2):
     raw.sktb_ts_profile(buf)
 v = np.array(list(buf), dtype=float)
 names = ["top barrier (update imbalance)", "panel load", "QR", "band out", "Y = A V (+barrier)", "X = Y T", "G, S", "W", "update (warp 0)"]
-tot = v[:9].sum()
+tot = v[:9].sum() + v[12:17].sum()
 for i, n in enumerate(names): print(f"{n:32s} {v[i]/nm/1e6:8.3f} Mclk/matrix  {100*v[i]/tot:5.1f}%")
+print(f"  inside QR: dots {v[15]/nm/1e6:.3f} + barrier {v[12]/nm/1e6:.3f}, update {v[16]/nm/1e6:.3f} + barrier {v[13]/nm/1e6:.3f} Mclk/matrix (thread 0)")
 print(f"total {tot/nm/1e6:.3f} Mclk/matrix; warp-busy Y = A V: {v[10]/16/nm/1e6:.3f}, update: {v[11]/16/nm/1e6:.3f} Mclk/matrix (mean over warps)")
