@@ -155,6 +155,59 @@ SKTB_D cplx block_sum(cplx v, double* scratch) {
     return cmake(warp_sum(tx), warp_sum(ty));
 }
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------
+// Sturm count (number of eigenvalues < x) of the symmetric tridiagonal block rows i0..i1 in PRODUCT form:
+// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, 3 FP64 operations per row (the quotient form of dstebz costs a division).
+// de2[i] = (d_i, e_{i-1}^2), scaled so that |d|, |e| <= 1 (then |p| grows by < 2^2.2 per row): the pair (p_{i-1}, p_i) is renormalised
+// by an exact power of two every 8 rows when its exponent leaves +-300; an exact zero becomes -2^-100 p_{i-1} (a sign change, dstebz's
+// pivmin rule) - blocks of 8 rows run without the zero test on the FP64 pipe and are redone carefully when an integer test saw a zero.
+// ---------------------------------------------------------------------------------------------------------
+SKTB_D int sturm_count_prod(const double2* __restrict__ de2, int i0, int i1, double x) {
+    const double tiny = -7.888609052210118e-31;                   // -2^-100
+    double p0 = 1.0, p1 = de2[i0].x - x;
+    if (p1 == 0.0) p1 = tiny;
+    int cnt = p1 < 0.0;
+    int r = i0 + 1;
+#define SKTB_STURM_STEP(RR)                                                                         \
+    {                                                                                               \
+        const double2 v = de2[RR];                                                                  \
+        double pn = fma(v.x - x, p1, -(v.y * p0));                                                  \
+        if (pn == 0.0) pn = tiny * p1;                                                              \
+        cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p1)) >> 31;                           \
+        p0 = p1; p1 = pn;                                                                           \
+    }
+#define SKTB_STURM_FAST(RR)                                                                         \
+    {                                                                                               \
+        const double2 v = de2[RR];                                                                  \
+        const double pn = fma(v.x - x, p1, -(v.y * p0));                                            \
+        const int hn = __double2hiint(pn);                                                          \
+        cnt += (unsigned)(hn ^ __double2hiint(p1)) >> 31;                                           \
+        nz = min(nz, (unsigned)(hn << 1) | (unsigned)__double2loint(pn));                           \
+        p0 = p1; p1 = pn;                                                                           \
+    }
+    for (; r + 8 <= i1 + 1; r += 8) {
+        const double s0 = p0, s1 = p1; const int sc0 = cnt;
+        unsigned nz = 0xffffffffu;
+        SKTB_STURM_FAST(r) SKTB_STURM_FAST(r + 1) SKTB_STURM_FAST(r + 2) SKTB_STURM_FAST(r + 3)
+        SKTB_STURM_FAST(r + 4) SKTB_STURM_FAST(r + 5) SKTB_STURM_FAST(r + 6) SKTB_STURM_FAST(r + 7)
+        if (nz == 0u) {
+            p0 = s0; p1 = s1; cnt = sc0;
+            for (int q = 0; q < 8; ++q) SKTB_STURM_STEP(r + q)
+        }
+        const int exq = ((__double2hiint(p1) >> 20) & 0x7ff) - 1023;
+        if (exq > 300 || exq < -300) {
+            const double rs = __hiloint2double((1023 - max(exq, -1000)) << 20, 0);
+            p0 *= rs; p1 *= rs;
+        }
+    }
+    for (; r <= i1; ++r) SKTB_STURM_STEP(r)
+#undef SKTB_STURM_STEP
+#undef SKTB_STURM_FAST
+    return cnt;
+}
+#endif
+
 // k-mesh point of flat index idx (greens.py:104-109): true IEEE divisions, no reciprocal multiply.
 SKTB_HD void kmesh_point(long long idx, int n0, int n1, int n2, double& kx, double& ky, double& kz) {
     long long l, j, i;

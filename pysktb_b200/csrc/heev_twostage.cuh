@@ -862,52 +862,10 @@ __global__ void __launch_bounds__(1024) bisect_prod_kernel(const double* __restr
         gl -= 2.0 * eps * N + 2.0 * pivmin; gu += 2.0 * eps * N + 2.0 * pivmin;
         if (tid < N) {
             double lo = gl, hi = gu;
-            const double tiny = -7.888609052210118e-31;                   // -2^-100
             for (int it = 0; it < 128; ++it) {
                 const double x = 0.5 * (lo + hi);
                 if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
-                double p0 = 1.0, p1 = de2[0].x - x;
-                if (p1 == 0.0) p1 = tiny;
-                int cnt = p1 < 0.0;
-                int r = 1;
-                // careful step: an exact zero becomes -2^-100 p_{i-1} (a sign change, dstebz's pivmin rule)
-#define SKTB_STURM_STEP(RR)                                                                         \
-                {                                                                                   \
-                    const double2 v = de2[RR];                                                      \
-                    double pn = fma(v.x - x, p1, -(v.y * p0));                                      \
-                    if (pn == 0.0) pn = tiny * p1;                                                  \
-                    cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p1)) >> 31;               \
-                    p0 = p1; p1 = pn;                                                               \
-                }
-                // fast step: no zero test on the FP64 pipe; `nz` collects min over the block of (bits of |p| != 0) with integer operations
-#define SKTB_STURM_FAST(RR)                                                                         \
-                {                                                                                   \
-                    const double2 v = de2[RR];                                                      \
-                    const double pn = fma(v.x - x, p1, -(v.y * p0));                                \
-                    const int hn = __double2hiint(pn);                                              \
-                    cnt += (unsigned)(hn ^ __double2hiint(p1)) >> 31;                               \
-                    nz = min(nz, (unsigned)(hn << 1) | (unsigned)__double2loint(pn));               \
-                    p0 = p1; p1 = pn;                                                               \
-                }
-                for (; r + 8 <= N; r += 8) {
-                    const double s0 = p0, s1 = p1; const int sc0 = cnt;
-                    unsigned nz = 0xffffffffu;
-                    SKTB_STURM_FAST(r) SKTB_STURM_FAST(r + 1) SKTB_STURM_FAST(r + 2) SKTB_STURM_FAST(r + 3)
-                    SKTB_STURM_FAST(r + 4) SKTB_STURM_FAST(r + 5) SKTB_STURM_FAST(r + 6) SKTB_STURM_FAST(r + 7)
-                    if (nz == 0u) {                                       // some p was exactly zero (rare): redo the block carefully
-                        p0 = s0; p1 = s1; cnt = sc0;
-                        for (int q = 0; q < 8; ++q) SKTB_STURM_STEP(r + q)
-                    }
-                    // per step |p| grows by < 2^2.2 (|d - x| <= 4, e^2 <= 1): renormalise the pair by an exact power of two every 8 rows
-                    const int exq = ((__double2hiint(p1) >> 20) & 0x7ff) - 1023;
-                    if (exq > 300 || exq < -300) {
-                        const double rs = __hiloint2double((1023 - max(exq, -1000)) << 20, 0);
-                        p0 *= rs; p1 *= rs;
-                    }
-                }
-                for (; r < N; ++r) SKTB_STURM_STEP(r)
-#undef SKTB_STURM_STEP
-#undef SKTB_STURM_FAST
+                const int cnt = sturm_count_prod(de2, 0, N - 1, x);
                 if (cnt > tid) hi = x; else lo = x;
             }
             evals[(long long)tid * ld + col0 + mat] = 0.5 * (lo + hi) * isc;

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
     double* w = e + N;                 // eigenvalue of thread n (n-th position of its block, ascending inside the block)
     int* blo = reinterpret_cast<int*>(w + N);   // first / last index of the unreduced block that contains index n
     int* bhi = blo + N;
+    double2* de2 = reinterpret_cast<double2*>(bhi + N);      // [N] (d_i, e_{i-1}^2) scaled by an exact power of two: product-form Sturm counts
     const double eps = 2.220446049250313e-16;
     for (long long mat = blockIdx.x; mat < a.nm; mat += gridDim.x) {
         __syncthreads();
@@ -61,6 +62,11 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
         // ---- split into unreduced blocks (dstebz / dstein work block by block: eigenvectors of different blocks are
         //      orthogonal by support, so exact degeneracies ACROSS blocks - diagonal, zero, decoupled matrices - cost nothing)
         for (int i = tid; i < N - 1; i += T) if (fabs(e[i]) <= eps * onenrm) e[i] = 0.0;
+        __syncthreads();
+        int sex = 0;
+        if (onenrm > 0.0) frexp(onenrm, &sex);
+        const double ssc = scalbn(1.0, -sex), issc = scalbn(1.0, sex);
+        for (int i = tid; i < N; i += T) { const double el = i > 0 ? e[i - 1] * ssc : 0.0; de2[i] = make_double2(d[i] * ssc, el * el); }
         __syncthreads();
         double* Zm = a.Z + (size_t)mat * N * N;
         double* La = a.lu + (size_t)mat * 4 * N * N;
@@ -86,23 +92,15 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
                     tn = fmax(tn, fmax(fabs(d[i]), fmax(el, er)));
                 }
                 const int nbk = b1 - b0 + 1;
-                const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, tn * tn), 1e-290);
-                gl -= 2.0 * eps * tn * nbk + 2.0 * pivmin; gu += 2.0 * eps * tn * nbk + 2.0 * pivmin;
-                double lo = gl, hi = gu;
+                // bisection in the scaled units of de2 (|T| <= 1): product-form Sturm count, see sturm_count_prod
+                const double pivmin = 1e-290;
+                double lo = gl * ssc - (2.0 * eps * (tn * ssc) * nbk + 2.0 * pivmin), hi = gu * ssc + (2.0 * eps * (tn * ssc) * nbk + 2.0 * pivmin);
                 for (int it = 0; it < 128; ++it) {
                     const double x = 0.5 * (lo + hi);
                     if (!(hi - lo > 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) || x <= lo || x >= hi) break;
-                    int cnt = 0;
-                    double q = d[b0] - x;
-                    if (fabs(q) < pivmin) q = -pivmin;
-                    cnt += q < 0.0;
-                    for (int i = b0 + 1; i <= b1; ++i) {
-                        q = fma(-e[i - 1] * e[i - 1], fast_rcp(q), d[i] - x);
-                        if (fabs(q) < pivmin) q = -pivmin;
-                        cnt += q < 0.0;
-                    }
-                    if (cnt > r) hi = x; else lo = x;
+                    if (sturm_count_prod(de2, b0, b1, x) > r) hi = x; else lo = x;
                 }
+                lo *= issc; hi *= issc;
                 lam = 0.5 * (lo + hi);
             }
             w[tid] = lam;

@@ -579,7 +579,7 @@ static int launch_bigvec(sktb_plan* p, cplx* H, int N, long long nm, double* eva
         b.Z = Z; b.lu = lu; b.pin = pin; b.vstore = vstore; b.taustore = taus;
         b.vec_out = vec_out; b.vs_band = vs_band; b.vs_k = vs_k; b.vcol0 = vcol0; b.n_rows = n_rows; b.rows = rows_d;
         const int T = (N + 31) / 32 * 32;
-        stein_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, (size_t)4 * N * 8, st>>>(b);
+        stein_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, (size_t)6 * N * 8, st>>>(b);
         LAUNCHED();
         twostage::RowsArgs ra{};
         ra.N = N; ra.nm = nm; ra.H = H; ra.Tstore = Tstore; ra.npanels = twostage::stage1_panels(N); ra.Rstore = Rstore; ra.rstride = rstride;
@@ -602,7 +602,7 @@ static int launch_bigvec(sktb_plan* p, cplx* H, int N, long long nm, double* eva
     b.Z = Z; b.lu = lu; b.pin = pin; b.vstore = vstore; b.taustore = taus;
     b.vec_out = vec_out; b.vs_band = vs_band; b.vs_k = vs_k; b.vcol0 = vcol0; b.n_rows = n_rows; b.rows = rows_d;
     const int T = (N + 31) / 32 * 32;
-    stein_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, (size_t)4 * N * 8, st>>>(b);
+    stein_kernel<<<(unsigned)std::min<long long>(nm, (long long)sms * 8), T, (size_t)6 * N * 8, st>>>(b);
     LAUNCHED();
     if (N <= 128) rc = launch_vecbt_big<4>(b, st, sms);
     else if (N <= 256) rc = launch_vecbt_big<8>(b, st, sms);
@@ -1064,6 +1064,7 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     size_t per_k = (size_t)N * 8 + ((use_small || use_vec32 || dos_fused) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? small::cta64_bytes_per_k() : 0) +
                    (use_vec32 ? small::vec32_bytes_per_k() : 0) + (use_vec64 ? small::vec64_bytes_per_k() : 0) + (dos_bigvec ? bigvec_bytes_per_matrix(N) : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)((dos_bigvec ? BIGVEC_BUDGET : WS_BUDGET) / per_k)));
+    if (dos_bigvec && bigvec_twostage(N, n_rows) && chunk >= 444 && chunk < k_count) chunk = chunk / 444 * 444;   // whole waves of stage 1 (148) and of the bulge chase (3 x 148)
     const int LOR_GRID = 148 * 4;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && !dos_fused && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k()
@@ -1190,6 +1191,7 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
     size_t per_k = (size_t)N * 8 + ((small_path) ? 0 : (size_t)N * N * 16) + (size_t)N * vstride * 32 + 4 +
                    (small_path ? (nr ? small::vec32_bytes_per_k() : 1024) : 0) + (mid_path ? small::vec64_bytes_per_k() : 0) + (sp_bigvec ? bigvec_bytes_per_matrix(N) : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)((sp_bigvec ? BIGVEC_BUDGET : WS_BUDGET) / per_k)));
+    if (sp_bigvec && bigvec_twostage(N, nr) && chunk >= 444 && chunk < nk) chunk = chunk / 444 * 444;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!small_path && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (nr && p->wsVec.ensure((size_t)chunk * N * vstride * 16)) ||
         (nr && p->ws[2].RT.ensure(small_path ? (size_t)chunk * small::vec32_bytes_per_k()
