@@ -619,6 +619,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int S2_WARPS = 8;
 constexpr int S2_DONE = 1 << 30;
+#ifndef S2_SPIN_NS
+#define S2_SPIN_NS 100
+#endif
 constexpr int S2_DS = SB + 1;                       // row stride of the D slab (conflict-free rows and columns)
 constexpr int S2_SLAB = SB * S2_DS + 3 * SB;        // per warp: D block, v_a, v_b, w
 SKTB_HD size_t stage2_smem_bytes(int N) { return (size_t)S2_WARPS * S2_SLAB * sizeof(cplx) + (size_t)2 * N * sizeof(int); }
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) 
             cplx* vS = vecs; cplx* v2S = vecs + SB; cplx* wS = vecs + 2 * SB;
             int h = 0;
             auto wait_for = [&](int need) {
-                if (s > 0) { while (prog[s - 1] < need) { } }
+                if (s > 0) { while (prog[s - 1] < need) { __nanosleep(S2_SPIN_NS); } }      // sleeping leaves the issue slots to the warps that chase
                 __syncwarp();
                 __threadfence_block();
             };

@@ -1,0 +1,37 @@
+"""Copy the evidence of tools/collect_round2b.sh (two-stage path) from gpurun_out/ (scratch) into profiles/ (tracked): ncu summary of the new
+kernels, launch lists, bench lines, size scan, and the traffic record bench.py reads for the C5 roofline block."""
+import csv, io, json, os, shutil, subprocess, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+O, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
+order = ["stage1", "stage2", "bisect_prod", "stein_ts", "rows_ts"]
+reps = [os.path.join("gpurun_out", f"r2b_full_{k}.raw.csv") for k in order
+        if os.path.exists(os.path.join(O, f"r2b_full_{k}.raw.csv")) and os.path.getsize(os.path.join(O, f"r2b_full_{k}.raw.csv")) > 1000]
+subprocess.run([sys.executable, os.path.join(R, "tools", "make_profile_summary.py"), os.path.join(P, "r02b_ncu_summary.md"),
+                "ncu --set full summaries, round 2, two-stage path (N = 512: stage1 / stage2 / bisect_prod on 296 random matrices through sktb_heev; stein / rows_kernel on the "
+                "C5 ribbon, 444 k-points, LDOS of one atom)"] + reps, cwd=R, check=True)
+copies = [("r2b_launches_C5.csv", "r02b_launches_C5_values.csv"), ("r2b_launches_C5ldos.csv", "r02b_launches_C5_edge_ldos.csv"),
+          ("r2b_bench_T.json", "r02_bench_T_1gpu.json"), ("r2b_bench_C5.json", "r02_bench_C5_1gpu.json"), ("r2b_secondary.log", "r02b_secondary_throughput.log"),
+          ("r2b_nscan.log", "r02b_heev_size_scan.log"), ("r2b_pytest.log", "r02_pytest_gpu.log"), ("r2b_smoke.log", "r02_smoke.log"),
+          ("dmma_probe.log", "r02b_dmma_probe.log"), ("lat_probe.log", "r02b_latency_probe.log"), ("ts_phase5.log", "r02b_stage1_phase_clocks.log")]
+for src, dst in copies:
+    if os.path.exists(os.path.join(O, src)) and os.path.getsize(os.path.join(O, src)) > 0:
+        shutil.copy(os.path.join(O, src), os.path.join(P, dst))
+
+
+def dram(rep):
+    rows = list(csv.reader(io.StringIO(open(rep).read()))); hdr, units, vals = rows[0], rows[1], rows[2]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    g = lambda k: float(vals[hdr.index(k)]) * scale[units[hdr.index(k)]]
+    return g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
+
+
+tfile = os.path.join(P, "r02_traffic.json")
+tj = json.load(open(tfile)) if os.path.exists(tfile) else {}
+f = os.path.join(O, "r2b_full_stage1.raw.csv")
+if os.path.exists(f) and os.path.getsize(f) > 1000:
+    r, w = dram(f)
+    tj["stage1_kernel"] = {"matrix_size": 512, "k_points_per_launch": 296, "dram_bytes_per_launch": r + w, "dram_bytes_read": r, "dram_bytes_write": w,
+                           "source": "profiles/r02b_ncu_summary.md (ncu --set full, one launch of 296 matrices; algorithmic: two reads + one write of the lower triangle per "
+                                     "16-column panel = N^3/(3*16)*32 B = 89.5 MB per 512-orbital matrix = 2.65e10 B per launch)"}
+    json.dump(tj, open(tfile, "w"), indent=1)
+print("published", sorted(x for x in os.listdir(P) if x.startswith("r02b") or x in ("r02_traffic.json",)))
