@@ -1,20 +1,22 @@
-// Two-stage tridiagonalisation for large matrices (128 <= N <= ~600, eigenvalues only).
+// Two-stage tridiagonalisation for large matrices (224 <= N <= 528: eigenvalues, and selected eigenvector rows for LDOS / spectral maps).
 //
 // The one-stage Householder reduction (kernels_generic.cuh) reads the trailing matrix once per reflector: 16 N^3 / 3 bytes
-// per matrix (0.9 GB at N = 512 against 4 MB of matrix) - it is HBM-bound at 11 % of the FP64 peak.  Here:
+// per matrix (0.8-0.9 GB at N = 512 against 4 MB of matrix) - it is HBM-bound at 11 % of the FP64 peak.  Here:
 //   stage 1  dense -> band of width SB = 16 (LAPACK zhetrd_he2hb idea): QR of a 16-column panel below the band (panel in
-//            shared memory, one warp per column), compact-WY block reflector Q = I - V T V^H, two-sided update of the trailing
-//            matrix A <- Q^H A Q = A - V W^H - W V^H with X = A (V T), W = X - 1/2 V (T^H V^H X).  Both matrix-sized
-//            operations (X = A V~ and the rank-32 update) are complex GEMMs on the FP64 tensor instruction
+//            registers, a warp per column pair and row half), compact-WY block reflector Q = I - V T V^H, two-sided update of the
+//            trailing matrix A <- Q^H A Q = A - V W^H - W V^H with X = (A V) T, W = X - 1/2 V (T^H V^H X).  Both matrix-sized
+//            operations (Y = A V and the rank-32 update) and the small products are complex GEMMs on the FP64 tensor instruction
 //            (mma.sync.m8n8k4.f64 -> DMMA.8x8x4): measured on B200 it shares the DFMA pipe but reaches the full 37 TFLOP/s
 //            with 8x fewer issue slots and no register-operand limit (tools/probe/dmma_probe.cu).  The trailing matrix is
 //            read twice and written once per PANEL (32 m^2 bytes, lower triangle only): N^3/(3*16)*32 B = 90 MB at N = 512.
 //   stage 2  band -> tridiagonal by bulge chasing (zhbtrd / sb2st idea): sweep s annihilates column s of the band and chases
-//            the 16x16 bulge down the band; one warp per sweep, sweeps pipelined three hops apart inside a CTA (progress
+//            the 16x16 bulge down the band; one warp per sweep, sweeps pipelined two hops apart inside a CTA (progress
 //            counters in shared memory), the band (2*SB diagonals with the fill, 262 KB at N = 512) stays in L2.
+//   then     bisection on the tridiagonal matrix with the product-form Sturm count (bisect_prod_kernel), or - for projections -
+//            inverse iteration (stein_kernel) and rows_kernel: rows of U = Q1 Q2 Z from the reflectors both stages keep.
 // Every reflector follows zlarfg (H^H x = beta e1, H = I - tau v v^H, beta real), the band layout is AB[j][d] = A[j+d][j].
 // tools/proto_twostage.py is the numpy model of both stages (same blocking, conventions and index arithmetic).
-// Replaces, for eigenvalues of large matrices, the LAPACK call behind numpy.linalg.eigh at pysktb/hamiltonian.py:119.
+// Replaces, for large matrices, the LAPACK call behind numpy.linalg.eigh at pysktb/hamiltonian.py:119.
 #pragma once
 #include "common.cuh"
 
@@ -142,16 +144,6 @@ SKTB_D void s1_r2k(double (&Pr)[2], double (&Pp)[2], double (&Pm)[2], double (&Q
     dmma(Qr[0], Qr[1], wI.x, v2.x); dmma(Qp[0], Qp[1], wI.y, v2.x); dmma(Qm[0], Qm[1], wI.x, v2.y);
     dmma(Pr[0], Pr[1], vI.y, w2.y); dmma(Qr[0], Qr[1], wI.y, v2.y);
 }
-SKTB_D void s1_prefetch(const cplx* A22, const cplx* Wg, int N, int m, int I, int J, int g, int q, cplx& c0, cplx& c1, cplx& w0, cplx& w1,
-                        cplx& w2, cplx& w3) {
-    const int row = 8 * I + g, col = 8 * J + 2 * q;
-    const cplx* cp = A22 + (size_t)row * N + col;
-    c0 = (row < m && col < m) ? ldcg(cp) : cmake(0.0, 0.0);
-    c1 = (row < m && col + 1 < m) ? ldcg(cp + 1) : cmake(0.0, 0.0);
-    const cplx* wj = Wg + (size_t)(8 * J + g) * SB + 2 * q;      // k index of (q, s) = 2q + (s & 1) + 8 (s >> 1)
-    w0 = wj[0]; w1 = wj[1]; w2 = wj[8]; w3 = wj[9];
-}
-
 #ifdef SKTB_TS_PROFILE
 __device__ unsigned long long g_s1_prof[32];
 #define S1_MARK(i) { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_s1_prof[i], (unsigned long long)(now_ - tmark_)); tmark_ = now_; } }
