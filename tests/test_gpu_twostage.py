@@ -145,3 +145,41 @@ def test_ldos_rows_after_two_stage_against_lapack(ctx, n_chains):
     np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-12)
     edge = tb.SurfaceGreensFunction(ham, [0, 1, N - 2, N - 1]).edge_dos(E, k_points=k, eta=eta, soc=False)
     np.testing.assert_allclose(edge, ref[[0, 1, 3, 4]].sum(axis=0), rtol=1e-8, atol=1e-12)
+
+
+def test_ldos_rows_multi_chunk_sums_to_dos(ctx):
+    """More k-points than one workspace chunk of the projection path (chunks are whole waves of the two-stage grids): the LDOS of ALL atoms
+    (240 selected rows per k through rows_kernel) must add up to the eigenvalue-only DOS (two-stage + bisection), chunk boundaries included."""
+    import pysktb_b200 as tb
+    from pysktb_b200 import workloads as W
+    _, ham = W.instantiate(W.zigzag_ribbon(120), tb, tb.scaling)
+    gf = tb.GreensFunction(ham)
+    E = np.linspace(-3.0, 3.0, 9)
+    nk = [3001, 1, 1]
+    ld = gf.ldos(E, atom_indices=list(range(240)), nk=nk, eta=0.07, soc=False)
+    assert "rows_kernel" in ham.last_kernel_info()
+    dos = gf.dos(E, nk=nk, eta=0.07, soc=False)
+    assert "two-stage" in ham.last_kernel_info()
+    np.testing.assert_allclose(ld.sum(axis=0), dos, rtol=1e-9)
+
+
+def test_spectral_maps_after_two_stage_against_lapack(ctx):
+    """A(k,E) maps with projections (edge_spectral_kpath: sktb_spectral with an index list) on the 256-orbital ribbon against LAPACK."""
+    import pysktb_b200 as tb
+    from pysktb_b200 import workloads as W
+    _, ham = W.instantiate(W.zigzag_ribbon(128), tb, tb.scaling)
+    N = 256
+    kv = np.array([0.0, 0.21, 0.5, 0.77])
+    k = np.stack([kv, np.zeros(4), np.zeros(4)], axis=1)
+    H = ham.get_ham_batch(k, l_soc=False)
+    E = np.linspace(-3.0, 3.0, 31)
+    eta = 0.05
+    atoms = [0, 1, N - 2, N - 1]
+    got = tb.SurfaceGreensFunction(ham, atoms).edge_spectral_kpath(kv, E, eta=eta, soc=False)
+    assert "rows_kernel" in ham.last_kernel_info(), ham.last_kernel_info()
+    ref = np.zeros((4, len(E)))
+    for q in range(4):
+        w, U = np.linalg.eigh(H[q])
+        lor = (eta / np.pi) / ((E[None, :] - w[:, None]) ** 2 + eta ** 2)
+        ref[q] = (np.abs(U[atoms, :]) ** 2).sum(axis=0) @ lor
+    np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-12)
