@@ -170,34 +170,63 @@ __global__ void __launch_bounds__(1024) stein_kernel(BigVecArgs a) {
                     for (int i = b0; i <= b1; ++i) s1 += fabs(Zm[(size_t)i * N + j]);
                     const double scl = (double)nbk * fmax(onenrm, 1e-300) * fmax(eps, fabs(a_last)) / fmax(s1, 1e-300);
                     // forward: y <- L^-1 P y (with the scaling of the start vector folded in)
+                    // (the loads of four steps are issued together: the recurrence is latency-bound on its global-memory operands)
                     double yprev = Zm[(size_t)b0 * N + j] * scl;
-                    for (int k = b0 + 1; k <= b1; ++k) {
-                        const size_t lk = (size_t)(k - 1) * N + j;
-                        double yk = Zm[(size_t)k * N + j] * scl;
-                        const double c = Lc[lk];
-                        if (Pn[lk]) { const double t = yprev; yprev = yk; yk = t - c * yk; }
-                        else yk -= c * yprev;
-                        Zm[(size_t)(k - 1) * N + j] = yprev;
-                        yprev = yk;
+                    int k = b0 + 1;
+#define SKTB_FWD(YK, CV, PV, ROW)                                                                   \
+                    {                                                                               \
+                        double yk = (YK) * scl;                                                     \
+                        if (PV) { const double t = yprev; yprev = yk; yk = t - (CV) * yk; }         \
+                        else yk -= (CV) * yprev;                                                    \
+                        Zm[(size_t)(ROW) * N + j] = yprev;                                          \
+                        yprev = yk;                                                                 \
                     }
+                    for (; k + 3 <= b1; k += 4) {
+                        const size_t lk = (size_t)(k - 1) * N + j;
+                        const double y0 = Zm[lk + N], y1 = Zm[lk + 2 * (size_t)N], y2 = Zm[lk + 3 * (size_t)N], y3 = Zm[lk + 4 * (size_t)N];
+                        const double c0 = Lc[lk], c1 = Lc[lk + N], c2 = Lc[lk + 2 * (size_t)N], c3 = Lc[lk + 3 * (size_t)N];
+                        const unsigned char p0 = Pn[lk], p1 = Pn[lk + N], p2 = Pn[lk + 2 * (size_t)N], p3 = Pn[lk + 3 * (size_t)N];
+                        SKTB_FWD(y0, c0, p0, k - 1) SKTB_FWD(y1, c1, p1, k) SKTB_FWD(y2, c2, p2, k + 1) SKTB_FWD(y3, c3, p3, k + 2)
+                    }
+                    for (; k <= b1; ++k) {
+                        const size_t lk = (size_t)(k - 1) * N + j;
+                        SKTB_FWD(Zm[(size_t)k * N + j], Lc[lk], Pn[lk], k - 1)
+                    }
+#undef SKTB_FWD
                     Zm[(size_t)b1 * N + j] = yprev;
                     // backward: x <- U^-1 y, tiny pivots perturbed to +-tol
                     double x1 = 0.0, x2 = 0.0;
-                    for (int k = b1; k >= b0; --k) {
-                        const size_t at = (size_t)k * N + j;
-                        double t = Zm[at];
-                        if (k <= b1 - 1) t -= Lb[at] * x1;
-                        if (k <= b1 - 2) t -= Ld[at] * x2;
-                        double akk = La[at];
-                        if (fabs(akk) < tol) akk = akk >= 0.0 ? tol : -tol;
-                        t /= akk;
-                        if (fabs(t) > 1.0e150) {       // exponentially localised vectors (edge states) span hundreds of decades: rescale
-                            for (int kk = b0; kk <= b1; ++kk) Zm[(size_t)kk * N + j] *= 1.0e-150;      // (solution so far and the right-hand side still ahead)
-                            t *= 1.0e-150; x1 *= 1.0e-150; x2 *= 1.0e-150;
-                        }
-                        Zm[at] = t;
-                        x2 = x1; x1 = t;
+                    int kb = b1;
+#define SKTB_BWD(KK, TV, LBV, LDV, LAV)                                                             \
+                    {                                                                               \
+                        double t = (TV) * rs;                                                       \
+                        if ((KK) <= b1 - 1) t -= (LBV) * x1;                                        \
+                        if ((KK) <= b1 - 2) t -= (LDV) * x2;                                        \
+                        double akk = (LAV);                                                         \
+                        if (fabs(akk) < tol) akk = akk >= 0.0 ? tol : -tol;                         \
+                        t /= akk;                                                                   \
+                        if (fabs(t) > 1.0e150) {       /* exponentially localised vectors (edge states) span hundreds of decades: rescale */ \
+                            for (int kk = b0; kk <= b1; ++kk) Zm[(size_t)kk * N + j] *= 1.0e-150;   /* (solution so far and the right-hand side still ahead) */ \
+                            t *= 1.0e-150; x1 *= 1.0e-150; x2 *= 1.0e-150; rs *= 1.0e-150;          /* rs: right-hand sides of this block already in registers */ \
+                        }                                                                           \
+                        Zm[(size_t)(KK) * N + j] = t;                                               \
+                        x2 = x1; x1 = t;                                                            \
                     }
+                    for (; kb - 3 >= b0; kb -= 4) {
+                        const size_t at = (size_t)kb * N + j;
+                        const double t0 = Zm[at], t1 = Zm[at - N], t2 = Zm[at - 2 * (size_t)N], t3 = Zm[at - 3 * (size_t)N];
+                        const double lb0 = Lb[at], lb1 = Lb[at - N], lb2 = Lb[at - 2 * (size_t)N], lb3 = Lb[at - 3 * (size_t)N];
+                        const double ld0 = Ld[at], ld1 = Ld[at - N], ld2 = Ld[at - 2 * (size_t)N], ld3 = Ld[at - 3 * (size_t)N];
+                        const double la0 = La[at], la1 = La[at - N], la2 = La[at - 2 * (size_t)N], la3 = La[at - 3 * (size_t)N];
+                        double rs = 1.0;
+                        SKTB_BWD(kb, t0, lb0, ld0, la0) SKTB_BWD(kb - 1, t1, lb1, ld1, la1) SKTB_BWD(kb - 2, t2, lb2, ld2, la2) SKTB_BWD(kb - 3, t3, lb3, ld3, la3)
+                    }
+                    for (; kb >= b0; --kb) {
+                        const size_t at = (size_t)kb * N + j;
+                        double rs = 1.0;
+                        SKTB_BWD(kb, Zm[at], Lb[at], Ld[at], La[at])
+                    }
+#undef SKTB_BWD
                     // modified Gram-Schmidt against the earlier vectors of the tight cluster
                     for (int q = tid; q < j; ++q) {
                         double dot = 0.0;
