@@ -607,9 +607,17 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
 // sweep s-1 starts at row s+16h+32: sweep s may run hop h once sweep s-1 has completed hop h + 1 (all synchronisation is inside one
 // CTA: block-scope fences).  Per hop a warp loads the off-diagonal block B (registers) and the lower triangle of the diagonal
 // block D (into its shared-memory slab, mirrored from there) in one go, applies the previous reflector from the right, builds the
-// new one from B's first column, applies it from the left and to D from both sides.  Latency-bound by design: 3 CTAs x 8 warps/SM.
+// new one from B's first column, applies it from the left and to D from both sides.  Latency-bound by design: 4 CTAs x 4 warps per SM (a
+// warp that has to wait for its predecessor sweep idles; fewer warps per matrix and more matrices per SM keep the warps busy).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int S2_WARPS = 8;
+#ifndef S2_MIN_CTAS
+#define S2_MIN_CTAS 4      // measured, matrices/s at N = 512 / 256 (no spills up to 128 registers): 4 CTAs x 4 warps 4.9e4 / 1.8e5, 2 x 8 4.8e4 / 1.3e5, 1 x 16 3.3e4 / 7.3e4,
+                           // 8 x 2 3.0e4 / 1.8e5; with 8 warps: 3 CTAs at 80 registers 4.5e4, 4 CTAs at 64 registers (spills) 3.3e4
+#endif
+#ifndef S2_NWARPS
+#define S2_NWARPS 4
+#endif
+constexpr int S2_WARPS = S2_NWARPS;
 constexpr int S2_DONE = 1 << 30;
 #ifndef S2_SPIN_NS
 #define S2_SPIN_NS 100
@@ -735,7 +743,7 @@ SKTB_D void s2_hop(cplx* __restrict__ AB, int r0, int L, int r1, int L2, const c
     s2_two_sided<FULL>(AB, r1, L2, v2S, wS, Ds, tau2, r, hh);
 }
 
-__global__ void __launch_bounds__(S2_WARPS * 32, 3) stage2_kernel(Stage2Args a) {
+__global__ void __launch_bounds__(S2_WARPS * 32, S2_MIN_CTAS) stage2_kernel(Stage2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

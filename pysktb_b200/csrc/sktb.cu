@@ -476,11 +476,11 @@ static int launch_heev_peel(sktb_plan* p, HeevArgs a, cudaStream_t st) {
     return 0;
 }
 
-// chunk size of the two-stage path: whole waves of both persistent grids (148 CTAs of stage 1, 3 x 148 of the bulge chase)
+// chunk size of the two-stage path: whole waves of both persistent grids (148 CTAs of stage 1, 4 x 148 of the bulge chase)
 static long long twostage_chunk(int N, long long n, size_t bytes_per_k) {
-    long long c = std::max<long long>(1, std::min<long long>(n, (long long)(((size_t)4 << 30) / bytes_per_k)));
+    long long c = std::max<long long>(1, std::min<long long>(n, (long long)(((size_t)5 << 30) / bytes_per_k)));
     if (c >= n) return n;
-    if (c >= 444) c = c / 444 * 444; else if (c >= 148) c = c / 148 * 148;
+    if (c >= 592) c = c / 592 * 592; else if (c >= 148) c = c / 148 * 148;
     return c;
 }
 static int launch_heev_twostage(sktb_plan* p, HeevArgs a, cudaStream_t st) {
@@ -1064,7 +1064,7 @@ extern "C" int sktb_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3
     size_t per_k = (size_t)N * 8 + ((use_small || use_vec32 || dos_fused) ? 0 : (size_t)N * N * 16) + (size_t)N * n_rows * 32 + 24 + 4 + (use_cta64 ? small::cta64_bytes_per_k() : 0) +
                    (use_vec32 ? small::vec32_bytes_per_k() : 0) + (use_vec64 ? small::vec64_bytes_per_k() : 0) + (dos_bigvec ? bigvec_bytes_per_matrix(N) : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)((dos_bigvec ? BIGVEC_BUDGET : WS_BUDGET) / per_k)));
-    if (dos_bigvec && bigvec_twostage(N, n_rows) && chunk >= 444 && chunk < k_count) chunk = chunk / 444 * 444;   // whole waves of stage 1 (148) and of the bulge chase (3 x 148)
+    if (dos_bigvec && bigvec_twostage(N, n_rows) && chunk >= 592 && chunk < k_count) chunk = chunk / 592 * 592;   // whole waves of stage 1 (148) and of the bulge chase (4 x 148)
     const int LOR_GRID = 148 * 4;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!use_small && !use_vec32 && !dos_fused && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (n_rows && (p->ws[2].RT.ensure(use_vec32 ? (size_t)chunk * small::vec32_bytes_per_k()
@@ -1191,7 +1191,7 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
     size_t per_k = (size_t)N * 8 + ((small_path) ? 0 : (size_t)N * N * 16) + (size_t)N * vstride * 32 + 4 +
                    (small_path ? (nr ? small::vec32_bytes_per_k() : 1024) : 0) + (mid_path ? small::vec64_bytes_per_k() : 0) + (sp_bigvec ? bigvec_bytes_per_matrix(N) : 0);
     long long chunk = std::max<long long>(1, std::min<long long>(nk, (long long)((sp_bigvec ? BIGVEC_BUDGET : WS_BUDGET) / per_k)));
-    if (sp_bigvec && bigvec_twostage(N, nr) && chunk >= 444 && chunk < nk) chunk = chunk / 444 * 444;
+    if (sp_bigvec && bigvec_twostage(N, nr) && chunk >= 592 && chunk < nk) chunk = chunk / 592 * 592;
     if (p->wsE.ensure((size_t)chunk * N * 8) || (!small_path && p->ws[2].H.ensure((size_t)chunk * N * N * 16)) ||
         (nr && p->wsVec.ensure((size_t)chunk * N * vstride * 16)) ||
         (nr && p->ws[2].RT.ensure(small_path ? (size_t)chunk * small::vec32_bytes_per_k()
