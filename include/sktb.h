@@ -103,7 +103,7 @@ int sktb_heev(sktb_plan* plan, const double* H_d, int32_t N, int64_t nm, double*
               int32_t* nonherm_d, void* stream);
 
 /* Diagnostic entry of the two-stage tridiagonalisation that sktb_heev / sktb_solve* use for eigenvalues of large matrices
- * (N >= 352 by default; csrc/heev_twostage.cuh): stage 1 reduces H to a Hermitian band of width 16 (blocked Householder,
+ * (N >= 208 by default; csrc/heev_twostage.cuh): stage 1 reduces H to a Hermitian band of width 16 (blocked Householder,
  * GEMMs on the FP64 tensor instruction), stage 2 chases the band to tridiagonal form.  Same input convention as sktb_heev.
  * band_d NULL or [nm][N][32] complex: band after stage 1, band[j][d] = A[j+d][j] (d <= 16, rest zero);
  * de_d NULL or [nm][2][N]: diagonal and sub-diagonal of the tridiagonal matrix.  Used by the parity tests to check each

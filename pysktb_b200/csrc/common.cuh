@@ -1,5 +1,5 @@
 // Shared device helpers for libsktb (sm_100a).  FP64 arithmetic throughout.  The batched Hermitian eigenproblem of tight binding is not
-// GEMM-shaped for N <= ~200 (register-resident DFMA kernels); from N = 224 the two-stage reduction (heev_twostage.cuh) puts its BLAS-3
+// GEMM-shaped for N <= ~200 (register-resident DFMA kernels); from N = 208 the two-stage reduction (heev_twostage.cuh) puts its BLAS-3
 // part on the FP64 tensor instruction (DMMA), which on B200 shares the DFMA pipe but reaches its full rate.
 #pragma once
 #include <cuda_runtime.h>

@@ -1,4 +1,4 @@
-// Two-stage tridiagonalisation for large matrices (224 <= N <= 528: eigenvalues, and selected eigenvector rows for LDOS / spectral maps).
+// Two-stage tridiagonalisation for large matrices (208 <= N <= 528: eigenvalues, and selected eigenvector rows for LDOS / spectral maps).
 //
 // The one-stage Householder reduction (kernels_generic.cuh) reads the trailing matrix once per reflector: 16 N^3 / 3 bytes
 // per matrix (0.8-0.9 GB at N = 512 against 4 MB of matrix) - it is HBM-bound at 11 % of the FP64 peak.  Here:

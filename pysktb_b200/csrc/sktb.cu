@@ -431,7 +431,7 @@ static size_t peel_bytes_per_k(int N) { return (size_t)2 * (N - 56) * 8 + small:
 // Two-stage tridiagonalisation (heev_twostage.cuh: dense -> band 16 on DMMA, band -> tridiagonal by bulge chasing) + bisection:
 // eigenvalues only, N >= SKTB_TWOSTAGE_MIN.  The one-stage kernels read the trailing matrix once per reflector and are HBM-bound
 // from N ~ 300 up; here the matrix is read twice and written once per 16 reflectors.
-static int twostage_min() { static const int v = getenv("SKTB_TWOSTAGE_MIN") ? atoi(getenv("SKTB_TWOSTAGE_MIN")) : 224; return v; }   // measured, 296 matrices: N = 192 old 8.8e4 / new 7.6e4 per s, N = 256 3.7e4 / 4.9e4
+static int twostage_min() { static const int v = getenv("SKTB_TWOSTAGE_MIN") ? atoi(getenv("SKTB_TWOSTAGE_MIN")) : 208; return v; }   // measured, matrices/s one-stage / two-stage: N = 192 9.5e4 / 1.01e5 at 592 matrices but 1.17e5 / 1.01e5 at 8192; N = 208 7.0e4 / 8.8e4; N = 256 4.0e4 / 6.1e4
 static bool use_twostage(int N) { return N >= twostage_min() && twostage::supported(N); }
 // scratch per matrix of the eigenvalues-only paths above N = 64 (HeevArgs::peel_ws): peeled run or two-stage
 static size_t evals_ws_bytes_per_k(int N) {

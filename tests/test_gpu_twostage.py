@@ -119,7 +119,7 @@ def test_heev_large_batch_matches_small_batch(ctx):
 
 @pytest.mark.parametrize("n_chains", [120, 256])
 def test_ldos_rows_after_two_stage_against_lapack(ctx, n_chains):
-    """Projections for N >= 224 take selected rows of U = Q1 Q2 Z from the two-stage reduction (block reflectors of stage 1, chase
+    """Projections for N >= 208 take selected rows of U = Q1 Q2 Z from the two-stage reduction (block reflectors of stage 1, chase
     reflectors of stage 2, inverse iteration on the tridiagonal): LDOS of edge and bulk atoms of zigzag ribbons (240 / 512 pz orbitals,
     nearly degenerate edge states) against a Lorentzian sum over LAPACK eigenpairs of the device-built H(k); 1e-8 relative
     (north-star tolerance for eigenvector-derived projections)."""

@@ -8,7 +8,7 @@ reps = [os.path.join("gpurun_out", f"r2b_full_{k}.raw.csv") for k in order
         if os.path.exists(os.path.join(O, f"r2b_full_{k}.raw.csv")) and os.path.getsize(os.path.join(O, f"r2b_full_{k}.raw.csv")) > 1000]
 subprocess.run([sys.executable, os.path.join(R, "tools", "make_profile_summary.py"), os.path.join(P, "r02b_ncu_summary.md"),
                 "ncu --set full summaries, round 2, two-stage path (N = 512: stage1 / stage2 / bisect_prod on 296 random matrices through sktb_heev; stein / rows_kernel on the "
-                "C5 ribbon, 444 k-points, LDOS of one atom)"] + reps, cwd=R, check=True)
+                "C5 ribbon, 592 k-points, LDOS of one atom)"] + reps, cwd=R, check=True)
 copies = [("r2b_launches_C5.csv", "r02b_launches_C5_values.csv"), ("r2b_launches_C5ldos.csv", "r02b_launches_C5_edge_ldos.csv"),
           ("r2b_bench_T.json", "r02_bench_T_1gpu.json"), ("r2b_bench_C5.json", "r02_bench_C5_1gpu.json"), ("r2b_secondary.log", "r02b_secondary_throughput.log"),
           ("r2b_nscan.log", "r02b_heev_size_scan.log"), ("r2b_pytest.log", "r02_pytest_gpu.log"), ("r2b_smoke.log", "r02_smoke.log"),
