@@ -137,12 +137,16 @@ SKTB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 template <int N_>
 SKTB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-// rank-2k tile update helpers: P = V_I W_J^H + W_I V_J^H accumulated as Pr (real part), Pp - Pm (imaginary part)
-SKTB_D void s1_r2k(double (&Pr)[2], double (&Pp)[2], double (&Pm)[2], double (&Qr)[2], double (&Qp)[2], double (&Qm)[2], cplx vI, cplx wI,
-                   cplx v2, cplx w2) {
-    dmma(Pr[0], Pr[1], vI.x, w2.x); dmma(Pp[0], Pp[1], vI.y, w2.x); dmma(Pm[0], Pm[1], vI.x, w2.y);
-    dmma(Qr[0], Qr[1], wI.x, v2.x); dmma(Qp[0], Qp[1], wI.y, v2.x); dmma(Qm[0], Qm[1], wI.x, v2.y);
-    dmma(Pr[0], Pr[1], vI.y, w2.y); dmma(Qr[0], Qr[1], wI.y, v2.y);
+// rank-2k tile update: C -= V_I W_J^H + W_I V_J^H accumulated straight into the C fragment (Cr, Ci) - the signs go into the B operands (sign-bit
+// flips on the integer pipe), so the tile has no FP64 epilogue: with the pipe full of DMMAs every DADD of an epilogue waits in line behind them
+// (ncu: a quarter of the update phase was 'math pipe throttle' on 12 DADD per tile).
+//   Re: Cr += Vr (-Wr) + Vi (-Wi) + Wr (-Vr) + Wi (-Vi)      Im: Ci += Vi (-Wr) + Vr Wi + Wi (-Vr) + Wr Vi
+SKTB_D void s1_r2k(double (&Cr)[2], double (&Ci)[2], cplx vI, cplx wI, cplx v2, cplx w2) {
+    const double nwx = dneg(w2.x), nwy = dneg(w2.y), nvx = dneg(v2.x), nvy = dneg(v2.y);
+    dmma(Cr[0], Cr[1], vI.x, nwx); dmma(Ci[0], Ci[1], vI.y, nwx);
+    dmma(Cr[0], Cr[1], vI.y, nwy); dmma(Ci[0], Ci[1], vI.x, w2.y);
+    dmma(Cr[0], Cr[1], wI.x, nvx); dmma(Ci[0], Ci[1], wI.y, nvx);
+    dmma(Cr[0], Cr[1], wI.y, nvy); dmma(Ci[0], Ci[1], wI.x, v2.y);
 }
 #ifdef SKTB_TS_PROFILE
 __device__ unsigned long long g_s1_prof[32];
@@ -535,14 +539,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                 for (int k = 0; k < RD - 1; ++k) issue_c(k);
                 int stage = 0;
                 int In = I, Jn = J;                                      // position of the W operands to prefetch next
-                cplx wA0, wA1, wA2, wA3, wB0, wB1, wB2, wB3;
-                wA0 = wA1 = wA2 = wA3 = wB0 = wB1 = wB2 = wB3 = cmake(0.0, 0.0);
+                cplx wA0, wA1, wA2, wA3, wB0, wB1, wB2, wB3, wC0, wC1, wC2, wC3;      // three buffers: the W operands are loaded two tiles ahead
+                wA0 = wA1 = wA2 = wA3 = wB0 = wB1 = wB2 = wB3 = wC0 = wC1 = wC2 = wC3 = cmake(0.0, 0.0);
                 auto load_w = [&](int Jj, cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
                     const cplx* wj = Wg + (size_t)(8 * Jj + g) * SB + 2 * q;      // k index of (q, s) = 2q + (s & 1) + 8 (s >> 1)
                     x0 = wj[0]; x1 = wj[1]; x2 = wj[8]; x3 = wj[9];
                 };
-                if (t < t1) load_w(Jn, wA0, wA1, wA2, wA3);
-                if (++Jn > In) { ++In; Jn = 0; }
+                if (t < t1) { load_w(Jn, wA0, wA1, wA2, wA3); if (++Jn > In) { ++In; Jn = 0; } }
+                if (t + 1 < t1) { load_w(Jn, wB0, wB1, wB2, wB3); if (++Jn > In) { ++In; Jn = 0; } }
                 int Irow = -1;
                 cplx vI0, vI1, vI2, vI3, wI0, wI1, wI2, wI3;
                 vI0 = vI1 = vI2 = vI3 = wI0 = wI1 = wI2 = wI3 = cmake(0.0, 0.0);
@@ -561,23 +565,27 @@ __global__ void __launch_bounds__(S1_THREADS, 1) stage1_kernel(Stage1Args a) {
                         const cplx C0 = ring[stage * 64], C1 = ring[stage * 64 + 32];                                      \
                         stage = stage + 1 == RD ? 0 : stage + 1;                                                           \
                         const int row = 8 * I + g, col = 8 * J + 2 * q;                                                    \
-                        double Pr[2] = {0, 0}, Pp[2] = {0, 0}, Pm[2] = {0, 0}, Qr[2] = {0, 0}, Qp[2] = {0, 0}, Qm[2] = {0, 0};      \
+                        double Cr[2] = {C0.x, C1.x}, Ci[2] = {C0.y, C1.y};                                                 \
                         const cplx* vp = Ps + (size_t)(2 * q) * mp + 8 * J + g;                                            \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI0, wI0, vp[0], W0);                                               \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI1, wI1, vp[mp], W1);                                              \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI2, wI2, vp[(size_t)8 * mp], W2);                                  \
-                        s1_r2k(Pr, Pp, Pm, Qr, Qp, Qm, vI3, wI3, vp[(size_t)9 * mp], W3);                                  \
+                        s1_r2k(Cr, Ci, vI0, wI0, vp[0], W0);                                                               \
+                        s1_r2k(Cr, Ci, vI1, wI1, vp[mp], W1);                                                              \
+                        s1_r2k(Cr, Ci, vI2, wI2, vp[(size_t)8 * mp], W2);                                                  \
+                        s1_r2k(Cr, Ci, vI3, wI3, vp[(size_t)9 * mp], W3);                                                  \
                         cplx* cp = A22 + (size_t)row * N + col;                                                            \
-                        if (row < m && col < m) cp[0] = cmake(C0.x - (Pr[0] + Qr[0]), C0.y - ((Pp[0] + Qp[0]) - (Pm[0] + Qm[0])));  \
-                        if (row < m && col + 1 < m) cp[1] = cmake(C1.x - (Pr[1] + Qr[1]), C1.y - ((Pp[1] + Qp[1]) - (Pm[1] + Qm[1])));  \
+                        if (row < m && col < m) cp[0] = cmake(Cr[0], Ci[0]);                                               \
+                        if (row < m && col + 1 < m) cp[1] = cmake(Cr[1], Ci[1]);                                           \
                         if (++J > I) { ++I; J = 0; }                                                                       \
                     }
-                for (; t < t1; t += 2) {
-                    if (t + 1 < t1) { load_w(Jn, wB0, wB1, wB2, wB3); if (++Jn > In) { ++In; Jn = 0; } }
+                for (; t < t1; t += 3) {
+                    if (t + 2 < t1) { load_w(Jn, wC0, wC1, wC2, wC3); if (++Jn > In) { ++In; Jn = 0; } }
                     SKTB_S1_TILE(wA0, wA1, wA2, wA3)
                     if (t + 1 < t1) {
-                        if (t + 2 < t1) { load_w(Jn, wA0, wA1, wA2, wA3); if (++Jn > In) { ++In; Jn = 0; } }
+                        if (t + 3 < t1) { load_w(Jn, wA0, wA1, wA2, wA3); if (++Jn > In) { ++In; Jn = 0; } }
                         SKTB_S1_TILE(wB0, wB1, wB2, wB3)
+                    }
+                    if (t + 2 < t1) {
+                        if (t + 4 < t1) { load_w(Jn, wB0, wB1, wB2, wB3); if (++Jn > In) { ++In; Jn = 0; } }
+                        SKTB_S1_TILE(wC0, wC1, wC2, wC3)
                     }
                 }
                 cp_async_wait<0>();
