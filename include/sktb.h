@@ -133,6 +133,32 @@ int sktb_spectral(sktb_plan* plan, const double* k_d, int64_t nk, int32_t soc, c
                   double eta, int32_t n_idx, const int32_t* idx, double* out_d, int32_t* nonherm_any_h,
                   void* stream);
 
+/* max over bonds of |T_b[mu,nu] - T_rev(b)[nu,mu]| and over soc_mat of |S - S^dagger|: 0 (to rounding) <=> H(k) is Hermitian
+ * for every k.  Unlike sktb_plan_asym_bound (the real-part test of hamiltonian.py:112) this sees the purely imaginary
+ * asymmetry of the f-orbital blocks; the Python layer uses it to choose between sktb_dos / sktb_spectral
+ * (eigenpairs, exact for Hermitian H) and sktb_gf_dos (dense inverse, what the reference computes in every case).      */
+int sktb_plan_herm_defect(const sktb_plan* plan, double* defect);
+
+/* K1+K5: GreensFunction.dos / ldos / ldos_by_orbital / spectral_kpath, SurfaceGreensFunction.* (greens.py:113-376, 431-557)
+ * exactly as the reference computes them: G = inv((E + i eta) I - H(k)) of the FULL matrix get_ham returns (greens.py:70,
+ * :455), one complex inverse per (k, E) (csrc/gf_inverse.cuh).  8 N^3 flops per (k, E) instead of one eigensolve per k: meant
+ * for models whose H(k) is not Hermitian, where the eigenpair route is not what the reference returns.
+ * k-points, groups and energies as in sktb_dos (n_groups == 0 -> trace; indices count with multiplicity).
+ * per_k == 0: out_d [max(n_groups,1)][nE] = sum over the k-points of -(1/pi) sum_{i in group} Im G_ii, UN-normalised;
+ * per_k == 1: out_d [k_count][max(n_groups,1)][nE], one map per k-point (spectral_kpath / edge_spectral_kpath).        */
+int sktb_gf_dos(sktb_plan* plan, const double* k_d, const int32_t nk_mesh[3], int64_t k_first, int64_t k_count, int32_t soc,
+                const double* energies_d, int32_t nE, double eta, int32_t n_groups, const int32_t* grp_ptr,
+                const int32_t* grp_idx, int32_t per_k, double* out_d, void* stream);
+
+/* Batched dense inverse of caller-supplied matrices (the counterpart of sktb_heev for the Green's function, greens.py:70):
+ * H_d [nm][N][N] row-major complex (every entry is read - no triangle reading), energies_d [nE] device;
+ * G_d [nm][nE][N][N] = inv((E_e + i eta) I - H_m), Gauss-Jordan with partial (row) pivoting on LAPACK izamax's measure.   */
+int sktb_gf_inverse(sktb_plan* plan, const double* H_d, int32_t N, int64_t nm, const double* energies_d, int32_t nE, double eta,
+                    double* G_d, void* stream);
+
+/* GreensFunction.retarded (greens.py:46-71): G_d [N][N] row-major complex = inv((E + i eta) I - H(k)), k_h HOST [3].   */
+int sktb_gf_retarded(sktb_plan* plan, const double k_h[3], double E, double eta, int32_t soc, double* G_d, void* stream);
+
 /* Hamiltonian.get_dos (hamiltonian.py:233-253): Gaussian-broadened DOS of a set of eigenvalues,
  *   out[e] = sum_i exp(-(E_e - eps_i)^2 / (2 w^2)) / (pi w sqrt(2))      (the reference's own prefactor),
  * evals_d [n] device (any layout, flat), energies_d [nE], out_d [nE] overwritten.  Deterministic (fixed-order sums). */

@@ -242,6 +242,48 @@ def nonherm_dos_fixture(ref):
     np.savez_compressed(os.path.join(OUT, "nonherm_dos.npz"), **out)
 
 
+NONHERM_GF = {"ce_spf_example": ("ce_spf_example", {}), "T": ("ce_spdf_1atom", {}), "C4": ("ce_spdf_2atom", {}),
+              "d_soc": ("d_soc_nonhermitian", {})}
+
+
+def nonherm_gf_fixture(ref):
+    """Every Green's-function entry point of the reference (greens.py:46-376, 431-557) on models whose H(k) is not Hermitian
+    (f shells: imaginary asymmetry; d-shell SOC: the model solve_kpath refuses): the dense-inverse numbers the CUDA path's
+    `method="inverse"` (csrc/gf_inverse.cuh) has to reproduce.  tests/golden/nonherm_gf.npz"""
+    out = {}
+    E = np.linspace(-3.0, 3.0, 9)
+    kpt = np.array([0.1, 0.2, 0.3])
+    path = [[0.0, 0.0, 0.0], [0.5, 0.0, 0.0], [0.5, 0.5, 0.0]]
+    kvals = np.array([0.0, 0.13, 0.5, 0.77])
+    for tag, (fn, kw) in NONHERM_GF.items():
+        spec = W.ALL[fn](**kw)
+        st, ham = quiet(W.instantiate, spec, ref, ref.scaling, numba=0)
+        soc = spec["soc"]
+        gf = ref.GreensFunction(ham)
+        n_at = len(st.atoms)
+        nk = [2, 2, 2] if tag != "C4" else [2, 1, 2]
+        out[tag + "_E"], out[tag + "_nk"], out[tag + "_eta"] = E, np.array(nk), np.array(0.07)
+        out[tag + "_dos"] = quiet(gf.dos, E, nk=nk, eta=0.07, soc=soc, parallel=False)
+        out[tag + "_ldos"] = quiet(gf.ldos, E, atom_indices=list(range(n_at))[::-1], nk=nk, eta=0.07, soc=soc, parallel=False)
+        out[tag + "_ldos_orb"] = quiet(gf.ldos, E, atom_indices=[0], orbital_indices=[0, 2, 5], nk=nk, eta=0.07, soc=soc, parallel=False)
+        byorb = quiet(gf.ldos_by_orbital, E, atom_index=n_at - 1, nk=nk, eta=0.07, soc=soc, parallel=False)
+        out[tag + "_by_orbital"] = np.array([byorb[o] for o in st.atoms[n_at - 1].orbitals])
+        out[tag + "_retarded"] = gf.retarded(0.3, kpt, eta=0.05, soc=soc)
+        out[tag + "_spectral"] = gf.spectral(-0.4, kpt, eta=0.05, soc=soc)
+        kd, amap, spl = quiet(gf.spectral_kpath, path, E, nk=3, eta=0.07, soc=soc)
+        out[tag + "_kpath_map"], out[tag + "_kpath_dist"] = amap, kd
+        sg = ref.SurfaceGreensFunction(ham, surface_atoms=[n_at - 1])
+        kp = np.array([[k, 0.0, 0.0] for k in kvals])
+        out[tag + "_edge_dos"] = quiet(sg.edge_dos, E, k_points=kp, eta=0.07, soc=soc, parallel=False)
+        out[tag + "_edge_map"] = quiet(sg.edge_spectral_kpath, kvals, E, eta=0.07, soc=soc)
+        out[tag + "_surface_spectral"] = np.array(sg.surface_spectral(0.2, kpt, eta=0.05, soc=soc))
+        Hk = ham.get_ham(kpt, l_soc=soc)
+        out[tag + "_asym"] = np.array(np.abs(Hk - Hk.conj().T).max())
+        print(tag, "N =", Hk.shape[0], "max |H - H^dagger| =", float(out[tag + "_asym"]))
+    out["kpt"], out["kvals"], out["path"] = kpt, kvals, np.array(path)
+    np.savez_compressed(os.path.join(OUT, "nonherm_gf.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
@@ -251,6 +293,9 @@ def main():
         model_fixture(ref, W.lowsym_spd(laws="misc"), nk_test=12, dos=(np.linspace(-3, 3, 13), [2, 2, 2], 0.1),
                       ldos=(np.linspace(-3, 3, 7), [2, 2, 1], 0.1, [2, 1], None))
         fuzz_fixture(ref)
+        return
+    if "--nonherm-gf-only" in sys.argv:
+        nonherm_gf_fixture(ref)
         return
     if "--next-rows-only" in sys.argv:
         next_rows_fixture(ref)
@@ -284,6 +329,7 @@ def main():
                   ldos=(E(-3, 3, 7), [2, 2, 1], 0.1, [2, 1], None))
     laws_fixture(ref)
     nonherm_dos_fixture(ref)
+    nonherm_gf_fixture(ref)
     model_fixture(ref, W.d_soc_nonhermitian(), nk_test=8)
 
 

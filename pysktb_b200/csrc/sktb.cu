@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "sk_table.cuh"
 #include "kernels_generic.cuh"
+#include "gf_inverse.cuh"
 #include "heev_twostage.cuh"
 #include "kernels_big_vec.cuh"
 #include "heev_small.cuh"
@@ -93,6 +94,7 @@ struct sktb_plan {
     std::vector<double> T_host_creation_order;  // hopping blocks in the caller's bond order
     std::vector<int> bond_ni, bond_nj;
     double asym_bound = 0.0;
+    double herm_defect = 0.0;                 // max |T_b[mu,nu] - T_rev(b)[nu,mu]|, |S - S^dagger|: 0 <=> H(k) = H(k)^dagger for every k
     const cplx* soc_dense = nullptr;          // [2n][2n] dense soc_mat (32 < 2n <= 64: fused build of tridiag_cta64)
     small::SmallTables small_tab{};           // dense tables for the register-resident path
     bool small_ok = false;
@@ -291,6 +293,23 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
             sb = std::max(sb, fabs(kv.second - other));
         }
         p->asym_bound = bound + sb;
+        // full (complex) Hermiticity defect: H(k) = H(k)^dagger for every k iff every hopping block equals the transpose of its
+        // reverse bond's block and soc_mat is Hermitian.  Decides which Green's-function path reproduces the reference's dense
+        // inverse: eigenpairs + Lorentzians (exact when the defect is 0) or one inverse per (k, E) (gf_inverse.cuh).
+        double defect = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            const int rb = find(D->bond_j[b], D->bond_i[b], D->bond_vec + 3 * b, -1.0);
+            for (int r = 0; r < p->bond_ni[b]; ++r)
+                for (int c = 0; c < p->bond_nj[b]; ++c) defect = std::max(defect, fabs(Tb(b, r, c) - Tb(rb, c, r)));
+        }
+        std::map<std::pair<int, int>, std::pair<double, double>> sc;
+        for (int t = 0; t < D->soc_nnz; ++t) sc[{D->soc_row[t], D->soc_col[t]}] = {D->soc_val[2 * t], D->soc_val[2 * t + 1]};
+        for (auto& kv : sc) {
+            auto it = sc.find({kv.first.second, kv.first.first});
+            const double ore = it == sc.end() ? 0.0 : it->second.first, oim = it == sc.end() ? 0.0 : it->second.second;
+            defect = std::max(defect, std::max(fabs(kv.second.first - ore), fabs(kv.second.second + oim)));
+        }
+        p->herm_defect = defect;
     }
 
     // ---- upload ---------------------------------------------------------------------------------------
@@ -365,6 +384,12 @@ extern "C" int sktb_plan_hoppings(const sktb_plan* p, double* out_host, int64_t 
 extern "C" int sktb_plan_asym_bound(const sktb_plan* p, double* bound) {
     if (!p || !bound) return fail("null argument");
     *bound = p->asym_bound;
+    return 0;
+}
+
+extern "C" int sktb_plan_herm_defect(const sktb_plan* p, double* defect) {
+    if (!p || !defect) return fail("null argument");
+    *defect = p->herm_defect;
     return 0;
 }
 
@@ -1271,6 +1296,111 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
     CK(cudaStreamSynchronize(st));
     if (nonherm_any_h) *nonherm_any_h = p->h_pinned[0];
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1+K5: the reference's dense-inverse Green's function for models whose H(k) is not Hermitian (gf_inverse.cuh)
+// ------------------------------------------------------------------------------------------------------
+static int launch_gf(sktb_plan* p, GfArgs a, cudaStream_t st) {
+    const int N = a.N;
+    if (N > 2048) return fail("dense-inverse Green's function: N = %d > 2048", N);
+    const bool in_smem = gf_smem_bytes(N, true) <= 227 * 1024;
+    const size_t smem = gf_smem_bytes(N, in_smem);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        CK(cudaFuncSetAttribute(gf_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_inverse_kernel, GF_THREADS, smem));
+    per_sm = std::max(per_sm, 1);
+    const long long items = a.nk * a.nE;
+    const unsigned grid = (unsigned)std::min<long long>(items, 148LL * per_sm);
+    if (!in_smem) {
+        if (p->ws[2].RT.ensure((size_t)grid * N * (N + 1) * sizeof(cplx))) return fail("out of device memory (inverse workspace)");
+        a.ws = (cplx*)p->ws[2].RT.p;
+    }
+    gf_inverse_kernel<<<grid, GF_THREADS, smem, st>>>(a);
+    LAUNCHED();
+    char info[200];
+    snprintf(info, sizeof info, "gf_inverse (dense inverse per (k,E), N=%d, %s) grid=%u x %d thr smem=%zuB %d CTA/SM", N,
+             in_smem ? "matrix in shared memory" : "matrix in a global workspace", grid, GF_THREADS, smem, per_sm);
+    g_kinfo = info;
+    return 0;
+}
+
+extern "C" int sktb_gf_dos(sktb_plan* p, const double* k_d, const int32_t nk_mesh[3], int64_t k_first, int64_t k_count, int32_t soc,
+                           const double* energies_d, int32_t nE, double eta, int32_t n_groups, const int32_t* grp_ptr,
+                           const int32_t* grp_idx, int32_t per_k, double* out_d, void* stream) {
+    if (!p || !energies_d || !out_d) return fail("null argument");
+    if (!k_d && !nk_mesh) return fail("need k points or a mesh");
+    if (nE <= 0) return 0;
+    ON_DEVICE(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = soc ? 2 * p->n_orb : p->n_orb;
+    const int ng = n_groups > 0 ? n_groups : 1;
+    const int total = n_groups > 0 ? grp_ptr[n_groups] : 0;
+    for (int q = 0; q < total; ++q)
+        if (grp_idx[q] < 0 || grp_idx[q] >= N) return fail("group index %d outside the %d x %d Hamiltonian", grp_idx[q], N, N);
+    if (!per_k) CK(cudaMemsetAsync(out_d, 0, (size_t)ng * nE * 8, st));
+    if (k_count <= 0) return 0;
+    int *d_gptr = nullptr, *d_grows = nullptr;
+    if (n_groups > 0) {
+        if (p->wsMisc.ensure(((size_t)n_groups + 1 + std::max(total, 1)) * sizeof(int))) return fail("out of device memory");
+        d_gptr = (int*)p->wsMisc.p; d_grows = d_gptr + n_groups + 1;
+        CK(cudaMemcpyAsync(d_gptr, grp_ptr, ((size_t)n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (total) CK(cudaMemcpyAsync(d_grows, grp_idx, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    const size_t per_kpt = (size_t)N * N * 16 + 24 + (per_k ? 0 : (size_t)ng * nE * 8);
+    const long long chunk = std::max<long long>(1, std::min<long long>(k_count, (long long)(((size_t)1 << 30) / per_kpt)));
+    if (p->ws[2].H.ensure((size_t)chunk * N * N * 16) || (!k_d && p->ws[2].K.ensure((size_t)chunk * 24)) ||
+        (!per_k && p->wsPart.ensure((size_t)chunk * ng * nE * 8)))
+        return fail("out of device memory (Green's function workspaces)");
+    for (long long c0 = 0; c0 < k_count; c0 += chunk) {
+        const long long cnt = std::min(chunk, (long long)k_count - c0);
+        const double* kk = k_d ? k_d + 3 * c0 : (const double*)p->ws[2].K.p;
+        if (!k_d) { int rc = sktb_kmesh(nk_mesh, k_first + c0, cnt, (double*)p->ws[2].K.p, st); if (rc) return rc; }
+        int rc = launch_hk(p, kk, cnt, soc, (cplx*)p->ws[2].H.p, nullptr, 0, st);
+        if (rc) return rc;
+        GfArgs a{};
+        a.H = (const cplx*)p->ws[2].H.p; a.N = N; a.nk = cnt; a.E = energies_d; a.nE = nE; a.eta = eta;
+        a.n_groups = n_groups > 0 ? n_groups : 0; a.gptr = d_gptr; a.grows = d_grows;
+        a.part = per_k ? out_d + (size_t)c0 * ng * nE : (double*)p->wsPart.p;
+        rc = launch_gf(p, a, st);
+        if (rc) return rc;
+        if (!per_k) {
+            lorentz_reduce_kernel<<<(ng * nE + 127) / 128, 128, 0, st>>>((const double*)p->wsPart.p, (int)cnt, ng * nE, out_d, 1);
+            LAUNCHED();
+        }
+    }
+    return 0;
+}
+
+extern "C" int sktb_gf_inverse(sktb_plan* p, const double* H_d, int32_t N, int64_t nm, const double* energies_d, int32_t nE, double eta,
+                               double* G_d, void* stream) {
+    if (!p || !H_d || !energies_d || !G_d) return fail("null argument");
+    if (N <= 0 || nm <= 0 || nE <= 0) return 0;
+    ON_DEVICE(p->device);
+    GfArgs a{};
+    a.H = reinterpret_cast<const cplx*>(H_d); a.N = N; a.nk = nm; a.E = energies_d; a.nE = nE; a.eta = eta;
+    a.Gout = reinterpret_cast<cplx*>(G_d);
+    return launch_gf(p, a, (cudaStream_t)stream);
+}
+
+extern "C" int sktb_gf_retarded(sktb_plan* p, const double k_h[3], double E, double eta, int32_t soc, double* G_d, void* stream) {
+    if (!p || !k_h || !G_d) return fail("null argument");
+    ON_DEVICE(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = soc ? 2 * p->n_orb : p->n_orb;
+    if (p->ws[2].H.ensure((size_t)N * N * 16) || p->ws[2].K.ensure(64)) return fail("out of device memory");
+    double* kE = (double*)p->ws[2].K.p;                     // k (3 doubles) | E
+    const double host[4] = {k_h[0], k_h[1], k_h[2], E};
+    CK(cudaMemcpyAsync(kE, host, sizeof host, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                          // `host` leaves scope at return
+    int rc = launch_hk(p, kE, 1, soc, (cplx*)p->ws[2].H.p, nullptr, 0, st);
+    if (rc) return rc;
+    return sktb_gf_inverse(p, (const double*)p->ws[2].H.p, N, 1, kE + 3, 1, eta, G_d, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -134,6 +134,9 @@ class Hamiltonian(object):
         bound = _lib.C.c_double()
         _lib.check(_lib.lib().sktb_plan_asym_bound(self._plan, _lib.C.byref(bound)))
         self.asym_bound = bound.value
+        defect = _lib.C.c_double(0.0)
+        _lib.check(_lib.lib().sktb_plan_herm_defect(self._plan, _lib.C.byref(defect)))
+        self.herm_defect = defect.value            # 0 (to rounding) <=> H(k) is Hermitian for every k (greens.py picks its path by it)
 
     def __del__(self):
         try:
@@ -222,6 +225,18 @@ class Hamiltonian(object):
             out = H.cpu().numpy()
             flags = fl.cpu().numpy()
         return (out, flags) if return_flags else out
+
+    def _gf_inverse_raw(self, H, e_real, eta):
+        """inv((e_real + i eta) I - H) of one caller-supplied matrix on the device (sktb_gf_inverse; diagnostics / tests)."""
+        torch = _torch()
+        H = np.ascontiguousarray(np.asarray(H, dtype=complex))
+        n = H.shape[0]
+        with torch.cuda.device(self._device):
+            Hd = torch.from_numpy(H).cuda()
+            Ed = torch.tensor([float(e_real)], dtype=torch.float64, device="cuda")
+            G = torch.empty((n, n), dtype=torch.complex128, device="cuda")
+            _lib.check(_lib.lib().sktb_gf_inverse(self._plan, Hd.data_ptr(), n, 1, Ed.data_ptr(), 1, float(eta), G.data_ptr(), self._stream()))
+            return G.cpu().numpy()
 
     def calc_g(self, kpt):
         """Phase tensor g[image, i, j] of the reference (hamiltonian.py:275-317).  Diagnostic only: the

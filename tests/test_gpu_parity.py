@@ -595,9 +595,10 @@ def test_zz_no_ql_failures(tb):
 @pytest.mark.parametrize("tag", ["ce_spf_example", "T", "C4"])
 def test_nonhermitian_dos_follows_lower_triangle_and_deviation_is_recorded(tb, tag):
     """f-orbital models (the headline models T and C4 among them): H(k) is not Hermitian, the reference's dense inverse
-    (greens.py:70) is then not an eigenvalue sum.  The CUDA path returns the DOS of the lower-triangle spectrum - equal to
+    (greens.py:70) is then not an eigenvalue sum.  `method="eigh"` returns the DOS of the lower-triangle spectrum - equal to
     1e-8 to the Lorentzian sum over the REFERENCE's own solve_kpath eigenvalues - and its deviation from the reference's
-    inverse-based numbers is the recorded one, not a silent difference."""
+    inverse-based numbers is the recorded one; the default method returns the reference's inverse-based
+    numbers themselves (tests/test_gpu_gf_inverse.py)."""
     from pysktb_b200 import workloads as W
     from test_oracle_golden import NONHERM, NONHERM_DEVIATION
     g = golden("nonherm_dos")
@@ -605,7 +606,7 @@ def test_nonhermitian_dos_follows_lower_triangle_and_deviation_is_recorded(tb, t
     spec = W.ALL[fn](**kw)
     _, ham = W.instantiate(spec, tb, tb.scaling)
     E, nk, eta = g[tag + "_E"], [int(x) for x in g[tag + "_nk"]], float(g[tag + "_eta"])
-    dos = tb.GreensFunction(ham).dos(E, nk=nk, eta=eta, soc=spec["soc"])
+    dos = tb.GreensFunction(ham, method="eigh").dos(E, nk=nk, eta=eta, soc=spec["soc"])     # the fast, lower-triangle reading (opt-in)
     np.testing.assert_allclose(dos, g[tag + "_dos_lower"], rtol=1e-8)
     dev = float(np.abs(dos / g[tag + "_dos_inv"] - 1).max())
     assert abs(dev - NONHERM_DEVIATION[tag]) < 1e-6, dev

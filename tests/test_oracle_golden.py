@@ -182,6 +182,41 @@ def test_nonhermitian_dos_deviation_recorded(tag):
     assert abs(dev - NONHERM_DEVIATION[tag]) < 1e-8 and float(g[tag + "_asym"]) > 1.0
 
 
+NONHERM_GF = {"ce_spf_example": ("ce_spf_example", {}), "T": ("ce_spdf_1atom", {}), "C4": ("ce_spdf_2atom", {}),
+              "d_soc": ("d_soc_nonhermitian", {})}
+
+
+@pytest.mark.parametrize("tag", ["ce_spf_example", "T", "d_soc"])
+def test_oracle_inverse_greens_function_vs_reference_on_nonhermitian_models(tag):
+    """The oracle's dense-inverse Green's function (greens.py:70 restated) against the reference's numbers on models whose
+    H(k) is not Hermitian (tests/golden/nonherm_gf.npz) - the checker of the CUDA path's `method="inverse"`."""
+    from pysktb_b200 import workloads as W
+    g = golden("nonherm_gf")
+    fn, kw = NONHERM_GF[tag]
+    spec = W.ALL[fn](**kw)
+    m = oracle_model(spec)
+    E, nk, eta, soc = g[tag + "_E"], [int(x) for x in g[tag + "_nk"]], float(g[tag + "_eta"]), spec["soc"]
+    np.testing.assert_allclose(m.dos(E, nk, eta, soc), g[tag + "_dos"], rtol=1e-10)
+    n_at = len(spec["atoms"])
+    np.testing.assert_allclose(m.ldos(E, atom_indices=list(range(n_at))[::-1], nk=nk, eta=eta, soc=soc), g[tag + "_ldos"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.spectral(-0.4, g["kpt"], eta=0.05, soc=soc), g[tag + "_spectral"], rtol=0,
+                               atol=1e-11 * np.abs(g[tag + "_spectral"]).max())
+    assert float(g[tag + "_asym"]) > 0.1
+
+
+def test_gauss_jordan_model_of_the_inverse_kernel():
+    """tools/proto_gj.py, the numpy model of csrc/gf_inverse.cuh (implicit row pivoting, A^-1[i][m] = R[p_i][q_m]), against LAPACK -
+    including matrices whose leading block is zero (no elimination order without row exchanges)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("proto_gj", os.path.join(os.path.dirname(__file__), "..", "tools", "proto_gj.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = np.random.default_rng(3)
+    for N in (1, 2, 7, 32, 65):
+        A = r.standard_normal((N, N)) + 1j * r.standard_normal((N, N))
+        A[: N // 2, : N // 2] = 0.0
+        assert np.abs(mod.inverse(A) - np.linalg.inv(A)).max() < 1e-11 * max(1.0, np.abs(np.linalg.inv(A)).max()) * N
+
+
 def cluster_projectors(ev, vec, tol=1e-7):
     """Spectral projectors of one k-point: [(mean eigenvalue, P)] with P = sum over a degenerate cluster of u u^H
     (rows of `vec` are eigenvectors, the reference's layout); gauge- and basis-independent within a cluster."""

@@ -1,4 +1,4 @@
-"""Time GreensFunction.dos (K1+K2+K3) for a workload.  usage: bench_dos.py [C2|C3|T|C4] [n0 n1 n2] [nE]"""
+"""Time GreensFunction.dos (K1+K2+K3, or K1+K5 with method=inverse) for a workload.  usage: bench_dos.py [C2|C3|T|C4] [n0 n1 n2] [nE] [dos|ldos] [eigh|inverse|auto]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,7 +13,7 @@ ldos = len(sys.argv) > 6 and sys.argv[6] == "ldos"
 builder, kw, _ = WORKLOADS[name]
 spec = W.ALL[builder](**kw)
 _, ham = W.instantiate(spec, tb, tb.scaling)
-gf = tb.GreensFunction(ham)
+gf = tb.GreensFunction(ham, method=sys.argv[7] if len(sys.argv) > 7 else "eigh")
 E = np.linspace(-8, 8, nE)
 N = len([o for _, _, orbs in spec["atoms"] for o in orbs]) * (2 if spec["soc"] else 1)
 for rep in range(3):
