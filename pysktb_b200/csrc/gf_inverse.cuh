@@ -120,6 +120,98 @@ __global__ void __launch_bounds__(GF_THREADS) gf_inverse_kernel(GfArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// N <= 32 (the north-star model T among them): ONE MATRIX PER WARP, lane r owns row r in registers (32 complex = 128 registers;
+// smaller matrices are padded with an identity block, which the elimination never mixes with the rest).  The same Gauss-Jordan sweep
+// with implicit row pivoting, arranged so that one code body serves every step without dynamic register indices:
+//   * the register window ROTATES: step c reads its column from register 0, every update writes its result one register down
+//     (a DFMA's destination is free), and the finished column of the inverse enters at register 31 - after 32 steps register j
+//     holds column j of R;
+//   * the pivot row is not scaled before it is broadcast: lane p stores its raw row (predicated STS.128), every lane folds 1/piv
+//     into its own factor, g_r = f_r / piv, and the pivot lane uses g_p = 1 - 1/piv, so that the one update  B -= g * prow  also
+//     turns the pivot row into prow / piv; the new column is  r == p ? 1/piv : -g_r;
+//   * the pivot search is one REDUX: key = (float bits of |Re| + |Im|, low 5 bits replaced by 31 - lane), 0 for used rows
+//     (an FP32 measure decides between near-equal candidates differently from LAPACK's FP64 izamax; either choice is stable).
+// Per step: 124 DFMA against 31 broadcast LDS.128 + 31 single-lane STS.128; no barrier, no spill at 3 x 4 warps per SM.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int GFW_WARPS = 4;
+
+__global__ void __launch_bounds__(GFW_WARPS * 32, 3) gf_inverse_warp_kernel(GfArgs a) {
+    __shared__ __align__(16) cplx s_prow[GFW_WARPS][32];
+    __shared__ double s_diag[GFW_WARPS][32];
+    const int N = a.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ng = a.n_groups > 0 ? a.n_groups : 1;
+    const long long n_items = a.nk * a.nE;
+    cplx* prow = s_prow[warp];
+    double* diag = s_diag[warp];
+#pragma unroll 1
+    for (long long item = (long long)blockIdx.x * GFW_WARPS + warp; item < n_items; item += (long long)gridDim.x * GFW_WARPS) {
+        const long long k = item / a.nE;
+        const int e = (int)(item - k * a.nE);
+        const cplx z = cmake(a.E[e], a.eta);
+        const cplx* Hr = a.H + (size_t)k * N * N + (size_t)min(lane, N - 1) * N;
+        cplx B[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const cplx h = Hr[min(j, N - 1)];
+            cplx v = cmake(-h.x, -h.y);
+            if (j == lane) { v.x += z.x; v.y += z.y; }
+            if (j >= N || lane >= N) v = cmake(j == lane ? 1.0 : 0.0, 0.0);
+            B[j] = v;
+        }
+        bool used = false;
+        int my_step = 0;
+#pragma unroll 1
+        for (int c = 0; c < 32; ++c) {
+            const cplx f = B[0];
+            const float mag = fmaxf((float)(fabs(f.x) + fabs(f.y)), 1.17549435e-38f);
+            const unsigned key = used ? 0u : ((__float_as_uint(mag) & 0xffffffe0u) | (unsigned)(31 - lane));
+            const int p = 31 - (int)(__reduce_max_sync(0xffffffffu, key) & 31u);
+            const bool is_p = lane == p;
+            if (is_p) { used = true; my_step = c; }
+            const cplx piv = cmake(__shfl_sync(0xffffffffu, f.x, p), __shfl_sync(0xffffffffu, f.y, p));
+            const double rd = fast_rcp(fma(piv.x, piv.x, piv.y * piv.y));
+            const cplx inv = cmake(piv.x * rd, -piv.y * rd);
+            cplx g = cmul(f, inv);
+            if (is_p) g = cmake(1.0 - inv.x, -inv.y);
+            __syncwarp();                                   // the previous step's readers of prow are done
+            if (is_p) {
+#pragma unroll
+                for (int m = 1; m < 32; ++m) prow[m] = B[m];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 1; m < 32; ++m) {
+                const cplx pm = prow[m];
+                cplx v = B[m];
+                cfms(v, g, pm);
+                B[m - 1] = v;
+            }
+            B[31] = is_p ? inv : cmake(-g.x, -g.y);
+        }
+        // lane r was the pivot row of step i = my_step:  G_ii = R[p_i][q_i] = register step_of_row[i] of this lane
+        const int q = __shfl_sync(0xffffffffu, my_step, my_step);
+        double gi = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gi = j == q ? B[j].y : gi;
+        __syncwarp();
+        diag[my_step] = gi;
+        __syncwarp();
+        for (int g = 0; g < ng; ++g) {
+            double s = 0.0;
+            if (a.n_groups > 0) {
+                for (int t = a.gptr[g] + lane; t < a.gptr[g + 1]; t += 32) s += diag[a.grows[t]];
+            } else {
+                s = lane < N ? diag[lane] : 0.0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) a.part[((size_t)k * ng + g) * a.nE + e] = -s / 3.141592653589793;
+        }
+    }
+}
+
 inline size_t gf_smem_bytes(int N, bool in_smem) {
     return (in_smem ? (size_t)N * (N + 1) * sizeof(cplx) : 0) + (size_t)2 * N * sizeof(cplx) + (size_t)2 * N * sizeof(int);
 }

@@ -1304,6 +1304,18 @@ extern "C" int sktb_spectral(sktb_plan* p, const double* k_d, int64_t nk, int32_
 static int launch_gf(sktb_plan* p, GfArgs a, cudaStream_t st) {
     const int N = a.N;
     if (N > 2048) return fail("dense-inverse Green's function: N = %d > 2048", N);
+    static const bool no_warp = getenv("SKTB_GF_WARP") && atoi(getenv("SKTB_GF_WARP")) == 0;
+    if (N <= 32 && !a.Gout && a.part && !no_warp) {        // one matrix per warp, rows in registers
+        const long long items = a.nk * a.nE;
+        const unsigned grid = (unsigned)std::min<long long>((items + GFW_WARPS - 1) / GFW_WARPS, 148LL * 3);
+        gf_inverse_warp_kernel<<<grid, GFW_WARPS * 32, 0, st>>>(a);
+        LAUNCHED();
+        char info[200];
+        snprintf(info, sizeof info, "gf_inverse_warp (dense inverse per (k,E), N=%d, one matrix per warp in registers) grid=%u x %d thr 3 CTA/SM", N, grid,
+                 GFW_WARPS * 32);
+        g_kinfo = info;
+        return 0;
+    }
     const bool in_smem = gf_smem_bytes(N, true) <= 227 * 1024;
     const size_t smem = gf_smem_bytes(N, in_smem);
     static size_t attr_set = 0;
