@@ -152,9 +152,11 @@ int sktb_gf_dos(sktb_plan* plan, const double* k_d, const int32_t nk_mesh[3], in
 
 /* Batched dense inverse of caller-supplied matrices (the counterpart of sktb_heev for the Green's function, greens.py:70):
  * H_d [nm][N][N] row-major complex (every entry is read - no triangle reading), energies_d [nE] device;
- * G_d [nm][nE][N][N] = inv((E_e + i eta) I - H_m), Gauss-Jordan with partial (row) pivoting on LAPACK izamax's measure.   */
+ * G_d NULL or [nm][nE][N][N] = inv((E_e + i eta) I - H_m), Gauss-Jordan with partial (row) pivoting;
+ * trace_d NULL or [nm][nE] = -(1/pi) Im Tr G.  With G_d == NULL the register-resident kernels run (one matrix per warp for
+ * N <= 32, one per CTA with the matrix spread over its registers for N <= 96), else the shared-memory kernel.              */
 int sktb_gf_inverse(sktb_plan* plan, const double* H_d, int32_t N, int64_t nm, const double* energies_d, int32_t nE, double eta,
-                    double* G_d, void* stream);
+                    double* G_d, double* trace_d, void* stream);
 
 /* GreensFunction.retarded (greens.py:46-71): G_d [N][N] row-major complex = inv((E + i eta) I - H(k)), k_h HOST [3].   */
 int sktb_gf_retarded(sktb_plan* plan, const double k_h[3], double E, double eta, int32_t soc, double* G_d, void* stream);

@@ -1305,6 +1305,21 @@ static int launch_gf(sktb_plan* p, GfArgs a, cudaStream_t st) {
     const int N = a.N;
     if (N > 2048) return fail("dense-inverse Green's function: N = %d > 2048", N);
     static const bool no_warp = getenv("SKTB_GF_WARP") && atoi(getenv("SKTB_GF_WARP")) == 0;
+    static const bool no_tile = getenv("SKTB_GF_TILE") && atoi(getenv("SKTB_GF_TILE")) == 0;
+    static const bool tile1 = getenv("SKTB_GF_TILE1") && atoi(getenv("SKTB_GF_TILE1")) == 1;
+    if (N <= 64 && (N > 32 || tile1) && !a.Gout && a.part && !no_tile) {   // 8 x 4 register tiles per lane, four warps per matrix (one for N <= 32: knob)
+        const long long items = a.nk * a.nE;
+        const int mpc = N <= 32 ? 4 : 1;
+        const unsigned grid = (unsigned)std::min<long long>((items + mpc - 1) / mpc, 148LL * SKTB_GF_TILE_MINB);
+        if (N <= 32) gf_inverse_tile_kernel<1><<<grid, 128, 0, st>>>(a);
+        else gf_inverse_tile_kernel<4><<<grid, 128, 0, st>>>(a);
+        LAUNCHED();
+        char info[200];
+        snprintf(info, sizeof info, "gf_inverse_tile<%d> (dense inverse per (k,E), N=%d, 8x4 register tile per lane, %s) grid=%u x 128 thr 2 CTA/SM", N <= 32 ? 1 : 4,
+                 N, N <= 32 ? "one warp per matrix" : "four warps per matrix", grid);
+        g_kinfo = info;
+        return 0;
+    }
     if (N <= 32 && !a.Gout && a.part && !no_warp) {        // one matrix per warp, rows in registers
         const long long items = a.nk * a.nE;
         const unsigned grid = (unsigned)std::min<long long>((items + GFW_WARPS - 1) / GFW_WARPS, 148LL * 3);
@@ -1313,6 +1328,18 @@ static int launch_gf(sktb_plan* p, GfArgs a, cudaStream_t st) {
         char info[200];
         snprintf(info, sizeof info, "gf_inverse_warp (dense inverse per (k,E), N=%d, one matrix per warp in registers) grid=%u x %d thr 3 CTA/SM", N, grid,
                  GFW_WARPS * 32);
+        g_kinfo = info;
+        return 0;
+    }
+    if (N > 32 && N <= 96 && !a.Gout && a.part && !no_warp) {   // one matrix per CTA, distributed over its registers
+        const long long items = a.nk * a.nE;
+        const unsigned grid = (unsigned)std::min<long long>(items, 148LL * 2);
+        if (N <= 64) gf_inverse_cta_kernel<8, 2><<<grid, GF_THREADS, 0, st>>>(a);
+        else gf_inverse_cta_kernel<12, 3><<<grid, GF_THREADS, 0, st>>>(a);
+        LAUNCHED();
+        char info[200];
+        snprintf(info, sizeof info, "gf_inverse_cta<%s> (dense inverse per (k,E), N=%d, one matrix per CTA in registers) grid=%u x %d thr", N <= 64 ? "8,2" : "12,3", N,
+                 grid, GF_THREADS);
         g_kinfo = info;
         return 0;
     }
@@ -1390,13 +1417,13 @@ extern "C" int sktb_gf_dos(sktb_plan* p, const double* k_d, const int32_t nk_mes
 }
 
 extern "C" int sktb_gf_inverse(sktb_plan* p, const double* H_d, int32_t N, int64_t nm, const double* energies_d, int32_t nE, double eta,
-                               double* G_d, void* stream) {
-    if (!p || !H_d || !energies_d || !G_d) return fail("null argument");
+                               double* G_d, double* trace_d, void* stream) {
+    if (!p || !H_d || !energies_d || (!G_d && !trace_d)) return fail("null argument");
     if (N <= 0 || nm <= 0 || nE <= 0) return 0;
     ON_DEVICE(p->device);
     GfArgs a{};
     a.H = reinterpret_cast<const cplx*>(H_d); a.N = N; a.nk = nm; a.E = energies_d; a.nE = nE; a.eta = eta;
-    a.Gout = reinterpret_cast<cplx*>(G_d);
+    a.Gout = reinterpret_cast<cplx*>(G_d); a.part = trace_d;
     return launch_gf(p, a, (cudaStream_t)stream);
 }
 
@@ -1412,7 +1439,7 @@ extern "C" int sktb_gf_retarded(sktb_plan* p, const double k_h[3], double E, dou
     CK(cudaStreamSynchronize(st));                          // `host` leaves scope at return
     int rc = launch_hk(p, kE, 1, soc, (cplx*)p->ws[2].H.p, nullptr, 0, st);
     if (rc) return rc;
-    return sktb_gf_inverse(p, (const double*)p->ws[2].H.p, N, 1, kE + 3, 1, eta, G_d, stream);
+    return sktb_gf_inverse(p, (const double*)p->ws[2].H.p, N, 1, kE + 3, 1, eta, G_d, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

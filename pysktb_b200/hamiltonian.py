@@ -226,17 +226,24 @@ class Hamiltonian(object):
             flags = fl.cpu().numpy()
         return (out, flags) if return_flags else out
 
-    def _gf_inverse_raw(self, H, e_real, eta):
-        """inv((e_real + i eta) I - H) of one caller-supplied matrix on the device (sktb_gf_inverse; diagnostics / tests)."""
+    def _gf_inverse_raw(self, H, energies, eta, want="G"):
+        """Device inverse of caller-supplied matrices (sktb_gf_inverse; diagnostics / tests): H (nm, N, N) or (N, N), energies (nE,).
+        want="G": inv((E + i eta) I - H), shape (nm, nE, N, N) - shared-memory kernel; want="trace": -(1/pi) Im Tr G, shape (nm, nE) -
+        register-resident kernels."""
         torch = _torch()
         H = np.ascontiguousarray(np.asarray(H, dtype=complex))
-        n = H.shape[0]
+        H = H.reshape((-1,) + H.shape[-2:])
+        nm, n = H.shape[0], H.shape[1]
+        E = np.ascontiguousarray(np.atleast_1d(np.asarray(energies, dtype=float)))
         with torch.cuda.device(self._device):
-            Hd = torch.from_numpy(H).cuda()
-            Ed = torch.tensor([float(e_real)], dtype=torch.float64, device="cuda")
-            G = torch.empty((n, n), dtype=torch.complex128, device="cuda")
-            _lib.check(_lib.lib().sktb_gf_inverse(self._plan, Hd.data_ptr(), n, 1, Ed.data_ptr(), 1, float(eta), G.data_ptr(), self._stream()))
-            return G.cpu().numpy()
+            Hd, Ed = torch.from_numpy(H).cuda(), torch.from_numpy(E).cuda()
+            if want == "G":
+                out = torch.empty((nm, len(E), n, n), dtype=torch.complex128, device="cuda")
+                _lib.check(_lib.lib().sktb_gf_inverse(self._plan, Hd.data_ptr(), n, nm, Ed.data_ptr(), len(E), float(eta), out.data_ptr(), None, self._stream()))
+            else:
+                out = torch.empty((nm, len(E)), dtype=torch.float64, device="cuda")
+                _lib.check(_lib.lib().sktb_gf_inverse(self._plan, Hd.data_ptr(), n, nm, Ed.data_ptr(), len(E), float(eta), None, out.data_ptr(), self._stream()))
+            return out.cpu().numpy()
 
     def calc_g(self, kpt):
         """Phase tensor g[image, i, j] of the reference (hamiltonian.py:275-317).  Diagnostic only: the

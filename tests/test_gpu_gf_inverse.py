@@ -156,19 +156,24 @@ def test_fuzz_f_shell_models_vs_oracle_inverse(tb):
     assert n >= 3
 
 
-@pytest.mark.parametrize("N", [1, 3, 31, 32, 33, 64, 97, 118, 130])
-def test_dense_inverse_kernel_on_random_matrices_vs_lapack(tb, N):
-    """gf_inverse_kernel alone: G = inv(z - H) of random NON-Hermitian matrices (shared-memory sizes up to 118, the global-workspace
-    fallback above) against numpy's LAPACK inverse; also a matrix that needs pivoting (zero leading entries)."""
-    import torch
+@pytest.mark.parametrize("N", [1, 3, 31, 32, 33, 48, 64, 65, 96, 97, 118, 130])
+def test_dense_inverse_kernels_on_random_matrices_vs_lapack(tb, N):
+    """The three inverse kernels alone on random NON-Hermitian matrices against numpy's LAPACK inverse: the full G from the
+    shared-memory kernel (matrix in shared memory up to N = 118, the global-workspace fallback above), -(1/pi) Im Tr G from the
+    register-resident kernels (warp per matrix N <= 32, CTA per matrix N <= 96); half of the matrices have a zero leading block
+    (no elimination order without row exchanges)."""
     from pysktb_b200 import workloads as W
     _, ham = W.instantiate(W.graphene_pz(), tb, tb.scaling)
     r = np.random.default_rng(N)
-    for trial in range(2):
-        H = r.standard_normal((N, N)) + 1j * r.standard_normal((N, N))
-        if trial == 1:
-            H[: max(1, N // 2), : max(1, N // 2)] = 0.0                   # leading block zero: z - H has tiny pivots there without row exchanges
-        z = 0.2 + 0.05j
-        G = ham._gf_inverse_raw(H, z.real, z.imag)
-        ref = np.linalg.inv(z * np.eye(N) - H)
-        assert np.abs(G - ref).max() < 1e-11 * max(1.0, np.abs(ref).max()) * N, (N, trial)
+    nm = 5
+    H = r.standard_normal((nm, N, N)) + 1j * r.standard_normal((nm, N, N))
+    H[1::2, : max(1, N // 2), : max(1, N // 2)] = 0.0
+    E, eta = np.array([0.2, -1.3, 0.0]), 0.05
+    G = ham._gf_inverse_raw(H, E, eta, want="G")
+    tr = ham._gf_inverse_raw(H, E, eta, want="trace")
+    for m in range(nm):
+        for ie, e in enumerate(E):
+            ref = np.linalg.inv((e + 1j * eta) * np.eye(N) - H[m])
+            assert np.abs(G[m, ie] - ref).max() < 1e-11 * max(1.0, np.abs(ref).max()) * N, (N, m, ie)
+            t_ref = -np.trace(ref).imag / np.pi
+            assert abs(tr[m, ie] - t_ref) < 1e-10 * max(1.0, np.abs(ref).max()) * N, (N, m, ie, tr[m, ie], t_ref)
