@@ -482,6 +482,8 @@ def main():
         ev_multi = tbdist.solve_kpath_sharded(cham, list(kk))               # sharded + all-gathered (NCCL)
         evT_multi = tbdist.solve_kpath_sharded(ham, list(kk), soc=spec["soc"])
         dosT_multi = tb.GreensFunction(ham, method="eigh").dos(E, nk=[24, 24, 24] if N <= 64 else [64, 1, 1], eta=0.05, soc=spec["soc"])
+        inv_gf = tb.GreensFunction(ham, method="inverse") if N <= 64 else None     # dense inverse per (k, E), k-sharded + all-reduced
+        inv_multi = inv_gf.dos(E[::5], nk=[6, 5, 4], eta=0.05, soc=spec["soc"]) if inv_gf else None
         barrier()
         orig = G._dist
         G._dist = lambda: None                                             # the same calls on this rank alone
@@ -489,17 +491,20 @@ def main():
             single = cgf.dos(E, nk=[37, 29, 1], eta=0.05)
             ld_single = cgf.ldos(E, atom_indices=[1, 0], nk=[11, 13, 1], eta=0.05)
             dosT_single = tb.GreensFunction(ham, method="eigh").dos(E, nk=[24, 24, 24] if N <= 64 else [64, 1, 1], eta=0.05, soc=spec["soc"])
+            inv_single = inv_gf.dos(E[::5], nk=[6, 5, 4], eta=0.05, soc=spec["soc"]) if inv_gf else None
         finally:
             G._dist = orig
         ev_single = cham.solve_kpath(list(kk))
         evT_single = ham.solve_kpath(list(kk), soc=spec["soc"])
         rel = lambda x, y: float(np.abs(x / y - 1).max())
         loc = [rel(multi, single), rel(ld_multi, ld_single), rel(dosT_multi, dosT_single),
-               0.0 if (np.array_equal(ev_multi, ev_single) and np.array_equal(evT_multi, evT_single)) else 1.0]
+               0.0 if (np.array_equal(ev_multi, ev_single) and np.array_equal(evT_multi, evT_single)) else 1.0,
+               rel(inv_multi, inv_single) if inv_gf else 0.0]
         t = torch.tensor(loc, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                            # worst over ranks
         w = t.cpu().numpy()
         mg = {"dos_rel": float(w[0]), "ldos_rel": float(w[1]), "dos_rel_bench_model": float(w[2]), "evals_equal": bool(w[3] == 0.0),
+              "dos_inverse_rel_bench_model": float(w[4]),
               "what": "C3 model: GreensFunction.dos [37,29,1] / ldos [11,13,1] sharded + ncclAllReduce vs one rank; dist.solve_kpath_sharded "
                       "(ncclAllGather) vs solve_kpath on 1001 random k, C3 and the bench model (bit-equality); worst over ranks"}
 
