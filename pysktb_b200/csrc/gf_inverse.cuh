@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(128, SKTB_GF_TILE_MINB) gf_inverse_tile_kernel
                     if (in_col && !((used >> t) & 1u)) key = max(key, kt);
                     if (in_col) S.fcol[buf][ra + AR * t] = f;
                 }
-                key = __reduce_max_sync(0xffffffffu, key);          // (also orders the staging stores before lane 0's read)
+                key = __reduce_max_sync(0xffffffffu, key);
+                __syncwarp();                                       // the staging stores are visible to lane 0
                 if (lane == 0) {
                     const int p = 63 - (int)(key & 63u);
                     S.pivot_row[buf] = p; S.p_of_step[c] = p; S.step_of_row[p] = c;
