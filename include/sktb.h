@@ -133,11 +133,11 @@ int sktb_spectral(sktb_plan* plan, const double* k_d, int64_t nk, int32_t soc, c
                   double eta, int32_t n_idx, const int32_t* idx, double* out_d, int32_t* nonherm_any_h,
                   void* stream);
 
-/* max over bonds of |T_b[mu,nu] - T_rev(b)[nu,mu]| and over soc_mat of |S - S^dagger|: 0 (to rounding) <=> H(k) is Hermitian
- * for every k.  Unlike sktb_plan_asym_bound (the real-part test of hamiltonian.py:112) this sees the purely imaginary
+/* max over bonds of |T_b[mu,nu] - T_rev(b)[nu,mu]| and (soc != 0) over soc_mat of |S - S^dagger|: 0 (to rounding) <=> the H(k)
+ * that get_ham(k, l_soc=soc) returns is Hermitian for every k.  Unlike sktb_plan_asym_bound (the real-part test of hamiltonian.py:112) this sees the purely imaginary
  * asymmetry of the f-orbital blocks; the Python layer uses it to choose between sktb_dos / sktb_spectral
  * (eigenpairs, exact for Hermitian H) and sktb_gf_dos (dense inverse, what the reference computes in every case).      */
-int sktb_plan_herm_defect(const sktb_plan* plan, double* defect);
+int sktb_plan_herm_defect(const sktb_plan* plan, int32_t soc, double* defect);
 
 /* K1+K5: GreensFunction.dos / ldos / ldos_by_orbital / spectral_kpath, SurfaceGreensFunction.* (greens.py:113-376, 431-557)
  * exactly as the reference computes them: G = inv((E + i eta) I - H(k)) of the FULL matrix get_ham returns (greens.py:70,

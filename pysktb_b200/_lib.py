@@ -58,7 +58,7 @@ _SIGNATURES = {
                            C.c_int32, c_i32p, c_i32p, C.c_void_p, c_i32p, C.c_void_p]),
     "sktb_spectral": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_int32,
                                 c_i32p, C.c_void_p, c_i32p, C.c_void_p]),
-    "sktb_plan_herm_defect": (C.c_int, [C.c_void_p, c_f64p]),
+    "sktb_plan_herm_defect": (C.c_int, [C.c_void_p, C.c_int32, c_f64p]),
     "sktb_gf_dos": (C.c_int, [C.c_void_p, C.c_void_p, c_i32p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_double,
                               C.c_int32, c_i32p, c_i32p, C.c_int32, C.c_void_p, C.c_void_p]),
     "sktb_gf_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,

@@ -94,7 +94,7 @@ struct sktb_plan {
     std::vector<double> T_host_creation_order;  // hopping blocks in the caller's bond order
     std::vector<int> bond_ni, bond_nj;
     double asym_bound = 0.0;
-    double herm_defect = 0.0;                 // max |T_b[mu,nu] - T_rev(b)[nu,mu]|, |S - S^dagger|: 0 <=> H(k) = H(k)^dagger for every k
+    double herm_defect = 0.0, herm_defect_soc = 0.0;   // max |T_b[mu,nu] - T_rev(b)[nu,mu]| / max |S - S^dagger|: both 0 <=> H(k) = H(k)^dagger for every k
     const cplx* soc_dense = nullptr;          // [2n][2n] dense soc_mat (32 < 2n <= 64: fused build of tridiag_cta64)
     small::SmallTables small_tab{};           // dense tables for the register-resident path
     bool small_ok = false;
@@ -302,6 +302,8 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
             for (int r = 0; r < p->bond_ni[b]; ++r)
                 for (int c = 0; c < p->bond_nj[b]; ++c) defect = std::max(defect, fabs(Tb(b, r, c) - Tb(rb, c, r)));
         }
+        p->herm_defect = defect;
+        defect = 0.0;
         std::map<std::pair<int, int>, std::pair<double, double>> sc;
         for (int t = 0; t < D->soc_nnz; ++t) sc[{D->soc_row[t], D->soc_col[t]}] = {D->soc_val[2 * t], D->soc_val[2 * t + 1]};
         for (auto& kv : sc) {
@@ -309,7 +311,7 @@ extern "C" int sktb_plan_create(const sktb_model_desc* D, int device, sktb_plan*
             const double ore = it == sc.end() ? 0.0 : it->second.first, oim = it == sc.end() ? 0.0 : it->second.second;
             defect = std::max(defect, std::max(fabs(kv.second.first - ore), fabs(kv.second.second + oim)));
         }
-        p->herm_defect = defect;
+        p->herm_defect_soc = defect;
     }
 
     // ---- upload ---------------------------------------------------------------------------------------
@@ -387,9 +389,9 @@ extern "C" int sktb_plan_asym_bound(const sktb_plan* p, double* bound) {
     return 0;
 }
 
-extern "C" int sktb_plan_herm_defect(const sktb_plan* p, double* defect) {
+extern "C" int sktb_plan_herm_defect(const sktb_plan* p, int32_t soc, double* defect) {
     if (!p || !defect) return fail("null argument");
-    *defect = p->herm_defect;
+    *defect = soc ? std::max(p->herm_defect, p->herm_defect_soc) : p->herm_defect;
     return 0;
 }
 

@@ -66,16 +66,16 @@ class GreensFunction:
         self.system = hamiltonian.system
         self.method = method
 
-    def _use_inverse(self):
+    def _use_inverse(self, soc=True):
         if self.method == "auto":
-            return self.ham.herm_defect > HERM_DEFECT_TOL
+            return (self.ham.herm_defect if soc == True else self.ham.herm_defect_nosoc) > HERM_DEFECT_TOL  # noqa: E712
         return self.method == "inverse"
 
     # -- per-(E,k) matrices ------------------------------------------------------------------------
     def retarded(self, E, k, eta=0.01, soc=True):
         """G^R(E,k) = (E + i eta - H)^-1 (greens.py:46-71): assembled from the device eigenpairs of H(k) when H is
         Hermitian, else the device's dense inverse of the full matrix (sktb_gf_retarded)."""
-        if self._use_inverse():
+        if self._use_inverse(soc):
             torch = _torch()
             ham = self.ham
             n = ham.n_orbitals * (2 if soc == True else 1)  # noqa: E712
@@ -126,7 +126,7 @@ class GreensFunction:
             kd = None
             if k_points is not None:
                 kd = torch.from_numpy(np.ascontiguousarray(np.asarray(k_points, dtype=float).reshape(-1, 3)[lo:hi])).cuda()
-            if self._use_inverse():
+            if self._use_inverse(soc):
                 _lib.check(_lib.lib().sktb_gf_dos(
                     ham._plan, kd.data_ptr() if kd is not None else None, _lib.ptr_i32(nk3) if nk3 is not None else None,
                     lo, hi - lo, int(bool(soc == True)), Ed.data_ptr(), nE, float(eta), ng,  # noqa: E712
@@ -196,7 +196,7 @@ class GreensFunction:
             out = torch.empty((len(k), len(energies)), dtype=torch.float64, device="cuda")
             bad = _lib.C.c_int32(0)
             ii = _lib.as_i32(idx) if idx is not None else None
-            if self._use_inverse():
+            if self._use_inverse(soc):
                 gp = _lib.as_i32([0, len(ii)]) if ii is not None else None
                 _lib.check(_lib.lib().sktb_gf_dos(ham._plan, kd.data_ptr(), None, 0, len(k), int(bool(soc == True)), Ed.data_ptr(),  # noqa: E712
                                                   len(energies), float(eta), 1 if ii is not None else 0,

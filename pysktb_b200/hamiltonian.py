@@ -135,8 +135,10 @@ class Hamiltonian(object):
         _lib.check(_lib.lib().sktb_plan_asym_bound(self._plan, _lib.C.byref(bound)))
         self.asym_bound = bound.value
         defect = _lib.C.c_double(0.0)
-        _lib.check(_lib.lib().sktb_plan_herm_defect(self._plan, _lib.C.byref(defect)))
+        _lib.check(_lib.lib().sktb_plan_herm_defect(self._plan, 1, _lib.C.byref(defect)))
         self.herm_defect = defect.value            # 0 (to rounding) <=> H(k) is Hermitian for every k (greens.py picks its path by it)
+        _lib.check(_lib.lib().sktb_plan_herm_defect(self._plan, 0, _lib.C.byref(defect)))
+        self.herm_defect_nosoc = defect.value      # the same for get_ham(k, l_soc=False): hopping blocks only
 
     def __del__(self):
         try:

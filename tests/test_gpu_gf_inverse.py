@@ -46,6 +46,19 @@ def test_auto_method_takes_the_inverse_for_nonhermitian_models(tb, tag):
     assert not tb.GreensFunction(ham, method="eigh")._use_inverse()
 
 
+def test_d_soc_model_without_soc_is_hermitian_and_takes_the_eigenpair_route(tb):
+    """The d-SOC model's only defect is soc_mat: with soc=False its H(k) is Hermitian, `auto` takes the eigenpair route, and both
+    routes agree."""
+    spec, st, ham = model(tb, "d_soc")
+    assert ham.herm_defect > 0.5 and ham.herm_defect_nosoc <= 1e-12
+    gf = tb.GreensFunction(ham)
+    assert gf._use_inverse(True) and not gf._use_inverse(False)
+    E = np.linspace(-2, 2, 9)
+    a = gf.dos(E, nk=[3, 2, 2], eta=0.08, soc=False)
+    b = tb.GreensFunction(ham, method="inverse").dos(E, nk=[3, 2, 2], eta=0.08, soc=False)
+    np.testing.assert_allclose(a, b, rtol=1e-9)
+
+
 def test_hermitian_models_keep_the_eigenpair_route(tb):
     from pysktb_b200 import workloads as W
     for fn in ("graphene_pz", "cubic_sp3", "sb_buckled"):
@@ -177,3 +190,32 @@ def test_dense_inverse_kernels_on_random_matrices_vs_lapack(tb, N):
             assert np.abs(G[m, ie] - ref).max() < 1e-11 * max(1.0, np.abs(ref).max()) * N, (N, m, ie)
             t_ref = -np.trace(ref).imag / np.pi
             assert abs(tr[m, ie] - t_ref) < 1e-10 * max(1.0, np.abs(ref).max()) * N, (N, m, ie, tr[m, ie], t_ref)
+
+
+@pytest.mark.parametrize("tag,nk", [("T", [7, 6, 5]), ("C4", [4, 3, 3])])
+def test_inverse_path_size_independent_properties(tb, tag, nk):
+    """Larger meshes than the reference fixtures reach, through properties of the inverse itself: the atom-resolved LDOS rows
+    (all orbitals, both spins) sum to the trace DOS; the per-orbital LDOS of every atom sums to that atom's row; a mesh given as an
+    explicit k list (edge_dos route, un-normalised sum / n) equals the mesh route; splitting the k range in two and adding the
+    partial sums reproduces the whole (the multi-GPU sharding arithmetic)."""
+    import torch
+    from pysktb_b200 import _lib
+    spec, st, ham = model(tb, tag)
+    soc = spec["soc"]
+    E = np.linspace(-5, 5, 41)
+    gf = tb.GreensFunction(ham)
+    dos = gf.dos(E, nk=nk, eta=0.07, soc=soc)
+    ld = gf.ldos(E, nk=nk, eta=0.07, soc=soc)
+    np.testing.assert_allclose(ld.sum(axis=0), dos, rtol=1e-10)
+    for ai in range(len(st.atoms)):
+        by = gf.ldos_by_orbital(E, atom_index=ai, nk=nk, eta=0.07, soc=soc)
+        np.testing.assert_allclose(sum(by.values()), ld[ai], rtol=1e-10)
+    kmesh = gf._generate_kmesh(nk)
+    n = ham.n_orbitals * (2 if soc else 1)
+    res, nkp = gf._reduce(E, soc, 0.07, [list(range(n))], k_points=kmesh)
+    np.testing.assert_allclose(res[0] / nkp, dos, rtol=1e-12)
+    half = len(kmesh) // 2
+    a, _ = gf._reduce(E, soc, 0.07, None, k_points=kmesh[:half])
+    b, _ = gf._reduce(E, soc, 0.07, None, k_points=kmesh[half:])
+    np.testing.assert_allclose((a[0] + b[0]) / len(kmesh), dos, rtol=1e-12)
+    assert np.all(np.isfinite(dos))
