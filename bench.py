@@ -519,7 +519,8 @@ def main():
         mg = {"dos_rel": float(w[0]), "ldos_rel": float(w[1]), "dos_rel_bench_model": float(w[2]), "evals_equal": bool(w[3] == 0.0),
               "dos_inverse_rel_bench_model": float(w[4]),
               "what": "C3 model: GreensFunction.dos [37,29,1] / ldos [11,13,1] sharded + ncclAllReduce vs one rank; dist.solve_kpath_sharded "
-                      "(ncclAllGather) vs solve_kpath on 1001 random k, C3 and the bench model (bit-equality); worst over ranks"}
+                      "(ncclAllGather) vs solve_kpath on 1001 random k, C3 and the bench model (bit-equality); bench model: DOS by the eigenpair route and "
+                      "(N <= 64) by the dense inverse per (k,E) on a [6,5,4] mesh; worst over ranks"}
 
     if rank != 0:
         if world > 1:
