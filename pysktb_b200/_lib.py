@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsktb.so")
+LIB_PATH = os.environ.get("SKTB_LIB_PATH") or os.path.join(_HERE, "libsktb.so")     # override: A/B builds of the same ABI (tools/ab_*.sh)
 
 c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)

@@ -36,6 +36,9 @@ constexpr int PAIR_VSTORE_CPLX = 32 * 32 + 32;      // reflectors [j][i] + tau[j
 #ifndef SKTB_PAIR_S
 #define SKTB_PAIR_S 4
 #endif
+#ifndef SKTB_PAIR_EARLY
+#define SKTB_PAIR_EARLY 0      // > 0: columns of the p-half that run before the new pivot column is published (see pair_step)
+#endif
 
 // One buffer set per matrix: reflector broadcast buffers of 2 LN entries whose upper half stays zero (window
 // columns beyond the matrix read v = p = x = 0).
@@ -207,6 +210,23 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
     // rough order of independent work: with the reduction written first its DADDs - each waiting ~30 cycles for a shuffle
     // - were issued ahead of the DFMA stream and stalled the in-order warp at the top of every step) ----
     constexpr int NST = LN == 32 ? 4 : 3;     // xor 2, 4, 8 (, 16): lanes of equal column parity within the matrix
+#if SKTB_PAIR_EARLY
+    // EARLY PUBLISH: only the first K1 columns of the p-half run before the new pivot column is finished and published (the butterfly
+    // gets one stage per column), so that the STS -> LDS round trip of the publish, the norm reduction and the zlarfg chain all hide
+    // under the REST of the p-half instead of opening a bubble between the p-half and the v-half.
+    constexpr int K1 = (HALF - ME) < SKTB_PAIR_EARLY ? (HALF - ME) : SKTB_PAIR_EARLY;
+    double G = c.g;
+#pragma unroll
+    for (int m = ME; m < ME + K1; ++m) {
+        const cplx pq = Pl[2 * m];
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) pair_upd1(B[s][m], c.v[s], pq);
+        const int st = m - ME + 1;
+        if (st <= NST) G += __shfl_xor_sync(0xffffffffu, G, 1 << st);
+    }
+#pragma unroll
+    for (int st = K1 + 1; st <= NST; ++st) G += __shfl_xor_sync(0xffffffffu, G, 1 << st);
+#else
     constexpr int CH = (HALF - ME + NST) / (NST + 1) > 0 ? (HALF - ME + NST) / (NST + 1) : 1;
     double G = c.g;
 #pragma unroll
@@ -219,6 +239,7 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
     }
 #pragma unroll
     for (int st = (HALF - ME) / CH + 1; st <= NST; ++st) G += __shfl_xor_sync(0xffffffffu, G, 1 << st);   // stages the loop was too short for
+#endif
     const double coef = -c.tau2 * G;
     cplx wp[2], x[2];
     {
@@ -241,6 +262,14 @@ SKTB_D void pair_step(cplx (&B)[2][LN / 2], PairCarry& c, const int j, const Pai
     }
     const cplx alpha = S.alpha[PH];
     const double xn = pair_rsum<LN>(xnp);
+#if SKTB_PAIR_EARLY
+#pragma unroll
+    for (int m = ME + K1; m < HALF; ++m) {     // rest of the p-half
+        const cplx pq = Pl[2 * m];
+#pragma unroll
+        for (int s = 2 - NS; s < 2; ++s) pair_upd1(B[s][m], c.v[s], pq);
+    }
+#endif
     // ---- v-half on the remaining registers fused with the look-ahead mat-vec ----
     cplx z[2], acol[2];
     z[0] = z[1] = cmake(0.0, 0.0);
