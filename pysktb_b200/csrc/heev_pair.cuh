@@ -89,9 +89,12 @@ SKTB_D double pair_rcp(double a) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
     double e = fma(-a, r, 1.0);
     e = fma(e, e, e);
-    r = fma(r, e, r);
+    r = fma(r, e, r);                                     // cubic step: seed error e <= ~2^-19 -> e^3 below the last rounding
+#if !SKTB_RCP3
     e = fma(-a, r, 1.0);
-    return fma(r, e, r);
+    r = fma(r, e, r);
+#endif
+    return r;
 }
 
 // sum over the LN/2 row pairs (lanes of equal column parity within the matrix)
@@ -113,6 +116,19 @@ SKTB_D void pair_larfg(const cplx alpha, const double xn, double& beta, cplx& ta
     const double live = trivial ? 0.0 : 1.0;
     const double n2 = fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xn));
     const double inrm = pair_rsqrt(trivial ? 1.0 : n2) * live;
+#if SKTB_RCP3
+    // FP64-issue diet (the scalar chain is 20-40 % of the FP64 instructions of the tail steps): the sign of beta is applied by
+    // selecting between x and -x (a sign-bit operation, not a DMUL by +-1), and dx = alpha.x - beta reuses beta - alpha.x
+    const bool pos = alpha.x >= 0.0;
+    const double nrm = n2 * inrm;
+    beta = trivial ? alpha.x : (pos ? -nrm : nrm);
+    const double ib = pos ? -inrm : inrm;
+    const double t = beta - alpha.x, dy = alpha.y;
+    tau = cmake(t * ib, -alpha.y * ib);
+    const double den = fma(t, t, dy * dy);
+    const double id = pair_rcp(trivial ? 1.0 : den) * live;
+    scale = cmake(-t * id, -dy * id);
+#else
     const double sgn = alpha.x >= 0.0 ? -1.0 : 1.0;
     beta = trivial ? alpha.x : sgn * (n2 * inrm);
     const double ib = sgn * inrm;
@@ -121,6 +137,7 @@ SKTB_D void pair_larfg(const cplx alpha, const double xn, double& beta, cplx& ta
     const double den = fma(dx, dx, dy * dy);
     const double id = pair_rcp(trivial ? 1.0 : den) * live;
     scale = cmake(dx * id, -dy * id);
+#endif
 }
 
 // State carried from one step to the next: the reflector v (own rows), p = tau A v (own rows), the lane's share g
@@ -158,8 +175,13 @@ SKTB_D void pair_finish(PairCarry& c, const cplx (&z)[2], const cplx (&acol)[2],
     cplx y[2];
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) {
+#if SKTB_RCP3
+        cplx yp = cmake(a_here ? acol[s].x : 0.0, a_here ? acol[s].y : 0.0);     // the column where v' = 1 enters as the addend of the product
+        cfma(yp, scale, z[s]);
+#else
         cplx yp = cmul(scale, z[s]);
         yp.x += a_here ? acol[s].x : 0.0; yp.y += a_here ? acol[s].y : 0.0;
+#endif
         y[s] = yp;
     }
 #pragma unroll

@@ -72,6 +72,9 @@ struct TqlArgs {
 inline bool supports(int N) { return N >= 1 && N <= 32; }
 
 constexpr int SMALL_WARPS = 4;
+#ifndef SKTB_RCP3
+#define SKTB_RCP3 1            // 1: reciprocals of the PWK sweep / of zlarfg by one cubic step on the hardware seed (3 FP64 ops instead of 5;
+#endif                         //    measured +1.6 % on the T step, eigenvalues unchanged at the 1e-14 level); 0: two Newton steps
 #ifndef SKTB_SMALL_SYNC
 #define SKTB_SMALL_SYNC 1
 #endif
@@ -240,7 +243,11 @@ SKTB_D int tql_lane_pwk(double* d, double* e, int n) {
         for (int i = m - 1; i >= l; --i) {
             const double bb = E_(i), alpha = D_(i);
             const double r = pp + bb;
+#if SKTB_RCP3
+            const double ir = fast_rcp3(r), ipp = fast_rcp3(pp);   // independent: 1/c = r / pp
+#else
             const double ir = fast_rcp(r), ipp = fast_rcp(pp);     // independent: 1/c = r / pp
+#endif
             const double e2new = s * r;
             const double oldc = c, oldgam = gamma;
             c = pp * ir; s = bb * ir;
