@@ -107,6 +107,16 @@ SKTB_D double pair_rsum(double v) {
     return v;
 }
 
+// x with its sign bit flipped when `flip`, and x or +0.0: integer operations on the bit pattern (the FP64 pipe is the bound of these
+// kernels; a DMUL by +-1 / by a 0-1 mask or a DADD from zero would take an FP64 issue slot each)
+SKTB_D double pair_flip(double x, bool flip) {
+    return __hiloint2double(__double2hiint(x) ^ (flip ? (int)0x80000000 : 0), __double2loint(x));
+}
+SKTB_D double pair_keep(double x, bool keep) {
+    const int m = keep ? -1 : 0;
+    return __hiloint2double(__double2hiint(x) & m, __double2loint(x) & m);
+}
+
 // zlarfg, branch-free (straight-line code, so that ptxas can schedule this scalar chain under the update loop)
 SKTB_D void pair_larfg(const cplx alpha, const double xn, double& beta, cplx& tau, cplx& scale) {
     // The reciprocal square root / reciprocal run on every path (inputs replaced by 1, results multiplied by a 0/1
@@ -115,19 +125,24 @@ SKTB_D void pair_larfg(const cplx alpha, const double xn, double& beta, cplx& ta
     const bool trivial = (xn == 0.0) && (alpha.y == 0.0);
     const double live = trivial ? 0.0 : 1.0;
     const double n2 = fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xn));
+#if SKTB_RCP3
+    const double inrm = pair_keep(pair_rsqrt(trivial ? 1.0 : n2), !trivial);
+#else
     const double inrm = pair_rsqrt(trivial ? 1.0 : n2) * live;
+#endif
 #if SKTB_RCP3
     // FP64-issue diet (the scalar chain is 20-40 % of the FP64 instructions of the tail steps): the sign of beta is applied by
     // selecting between x and -x (a sign-bit operation, not a DMUL by +-1), and dx = alpha.x - beta reuses beta - alpha.x
     const bool pos = alpha.x >= 0.0;
     const double nrm = n2 * inrm;
-    beta = trivial ? alpha.x : (pos ? -nrm : nrm);
-    const double ib = pos ? -inrm : inrm;
+    beta = trivial ? alpha.x : pair_flip(nrm, pos);
+    const double ib = pair_flip(inrm, pos);
     const double t = beta - alpha.x, dy = alpha.y;
     tau = cmake(t * ib, -alpha.y * ib);
     const double den = fma(t, t, dy * dy);
-    const double id = pair_rcp(trivial ? 1.0 : den) * live;
+    const double id = pair_keep(pair_rcp(trivial ? 1.0 : den), !trivial);
     scale = cmake(-t * id, -dy * id);
+    (void)live;
 #else
     const double sgn = alpha.x >= 0.0 ? -1.0 : 1.0;
     beta = trivial ? alpha.x : sgn * (n2 * inrm);
