@@ -171,8 +171,8 @@ SKTB_D void c64_step(cplx (&B)[2][16], PairCarry& c, const int j, const C64Lane&
 #pragma unroll
     for (int s = 2 - NS; s < 2; ++s) {
         const cplx acol = ma1 ? B[s][1] : B[s][0];
-        cplx yp = cmul(scale, z[s]);
-        yp.x += a_here ? acol.x : 0.0; yp.y += a_here ? acol.y : 0.0;
+        cplx yp = cmake(a_here ? acol.x : 0.0, a_here ? acol.y : 0.0);      // the column where v' = 1 enters as the addend of the product
+        cfma(yp, scale, z[s]);
         ypart[s] = yp;
     }
     c64_finish<NS>(c, ypart, xo, beta, tau, scale, jn, L, S);
@@ -284,8 +284,8 @@ SKTB_D void c64_run(cplx (&B)[2][16], PairCarry& c, const int J0, const C64Lane&
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            cplx yp = cmul(scale, ypart[s]);
-            yp.x += (L.h == 1) ? B[s][0].x : 0.0; yp.y += (L.h == 1) ? B[s][0].y : 0.0;     // column J0+1 = class 1, register 0
+            cplx yp = cmake((L.h == 1) ? B[s][0].x : 0.0, (L.h == 1) ? B[s][0].y : 0.0);     // column J0+1 = class 1, register 0
+            cfma(yp, scale, ypart[s]);
             ypart[s] = yp;
         }
         c64_finish<2>(c, ypart, xo, beta, tau, scale, J0, L, S);

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(MAXT) heev_generic_kernel(HeevArgs a) {
                     if (fabs(q) < pivmin) q = -pivmin;
                     cnt += q < 0.0;
                     for (int r = 1; r < N; ++r) {
-                        q = fma(-e2[r - 1], fast_rcp(q), d[r] - x);      // |q| >= pivmin: the reciprocal is finite
+                        q = fma(-e2[r - 1], fast_rcp3(q), d[r] - x);      // |q| >= pivmin: the reciprocal is finite
                         if (fabs(q) < pivmin) q = -pivmin;
                         cnt += q < 0.0;
                     }
@@ -719,7 +719,7 @@ __global__ void bisect_merge_kernel(const double* __restrict__ head, int P, cons
                 if (fabs(q) < pivmin) q = -pivmin;
                 cnt += q < 0.0;
                 for (int r = 1; r < N; ++r) {
-                    q = fma(-e2[r - 1], fast_rcp(q), d[r] - x);          // |q| >= pivmin: the reciprocal is finite
+                    q = fma(-e2[r - 1], fast_rcp3(q), d[r] - x);          // |q| >= pivmin: the reciprocal is finite
                     if (fabs(q) < pivmin) q = -pivmin;
                     cnt += q < 0.0;
                 }
