@@ -1347,11 +1347,7 @@ static int launch_gf(sktb_plan* p, GfArgs a, cudaStream_t st) {
     }
     const bool in_smem = gf_smem_bytes(N, true) <= 227 * 1024;
     const size_t smem = gf_smem_bytes(N, in_smem);
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        CK(cudaFuncSetAttribute(gf_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gf_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every call
     int per_sm = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_inverse_kernel, GF_THREADS, smem));
     per_sm = std::max(per_sm, 1);
