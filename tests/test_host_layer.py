@@ -128,3 +128,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "/root/reference" not in src, f
+
+
+def test_greens_function_method_selection_without_a_device():
+    """Host logic of GreensFunction(ham, method=): "auto" takes the dense inverse exactly when the plan's Hermiticity defect of the
+    H(k) that get_ham(k, l_soc=soc) returns exceeds 1e-12 eV (soc=False ignores a non-Hermitian soc_mat); explicit methods override;
+    unknown methods raise.  No device is touched: the Hamiltonian is a stub carrying the two defects."""
+    import types
+    import pytest as _pt
+    from pysktb_b200.greens import GreensFunction, SurfaceGreensFunction, HERM_DEFECT_TOL
+
+    def stub(defect, defect_nosoc):
+        st = types.SimpleNamespace(atoms=[types.SimpleNamespace(orbitals=["s", "px"]), types.SimpleNamespace(orbitals=["s"])])
+        return types.SimpleNamespace(n_orbitals=3, structure=st, system=None, herm_defect=defect, herm_defect_nosoc=defect_nosoc)
+
+    assert HERM_DEFECT_TOL == 1e-12
+    herm, fshell, dsoc = stub(3e-17, 3e-17), stub(0.82, 0.82), stub(1.7, 0.0)
+    assert not GreensFunction(herm)._use_inverse(True) and not GreensFunction(herm)._use_inverse(False)
+    assert GreensFunction(fshell)._use_inverse(True) and GreensFunction(fshell)._use_inverse(False)
+    assert GreensFunction(dsoc)._use_inverse(True) and not GreensFunction(dsoc)._use_inverse(False)
+    assert not GreensFunction(fshell, method="eigh")._use_inverse(True)
+    assert GreensFunction(herm, method="inverse")._use_inverse(False)
+    with _pt.raises(ValueError):
+        GreensFunction(herm, method="lu")
+    sg = SurfaceGreensFunction(fshell, surface_atoms=[1], method="eigh")
+    assert sg._gf.method == "eigh" and sg.surface_orbital_indices == [2] and sg._rows(True) == [2, 5]
