@@ -215,6 +215,13 @@ def test_gauss_jordan_model_of_the_inverse_kernel():
         A = r.standard_normal((N, N)) + 1j * r.standard_normal((N, N))
         A[: N // 2, : N // 2] = 0.0
         assert np.abs(mod.inverse(A) - np.linalg.inv(A)).max() < 1e-11 * max(1.0, np.abs(np.linalg.inv(A)).max()) * N
+    # lane-level model of the row-per-lane kernel: rotating register window, unscaled pivot-row broadcast with 1/piv folded into the
+    # factors, read-out of G_ii from register my_step[my_step[r]] of lane r
+    for N in (1, 5, 22, 32):
+        A = r.standard_normal((N, N)) + 1j * r.standard_normal((N, N))
+        A[: N // 2, : N // 2] = 0.0
+        ref = np.diag(np.linalg.inv(A))
+        assert np.abs(mod.warp_kernel_model(A) - ref).max() < 1e-11 * max(1.0, np.abs(np.linalg.inv(A)).max()) * N
 
 
 def cluster_projectors(ev, vec, tol=1e-7):

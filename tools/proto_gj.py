@@ -38,3 +38,34 @@ if __name__ == "__main__":
         A = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
         G = inverse(A)
         print(N, np.abs(G - np.linalg.inv(A)).max())
+
+
+def warp_kernel_model(A):
+    """Lane-level model of gf_inverse_warp_kernel (N <= 32, identity padding): lane r owns row r in a ROTATING 32-register window
+    - step c reads its column from register 0, every update writes one register down, the finished inverse column enters at
+    register 31 -, the pivot row is broadcast UNSCALED and 1/piv is folded into the factors (g_r = f_r / piv, g_p = 1 - 1/piv),
+    and lane r (pivot row of step i = my_step[r]) finds G_ii in register my_step[i].  Returns diag(A^-1)."""
+    N = len(A)
+    B = np.eye(32, dtype=complex)
+    B[:N, :N] = A
+    used = np.zeros(32, bool)
+    my_step = np.zeros(32, int)
+    for c in range(32):
+        f = B[:, 0].copy()
+        mag = np.where(used, -1.0, np.abs(f.real) + np.abs(f.imag))
+        p = int(np.argmax(mag))
+        used[p] = True
+        my_step[p] = c
+        inv = 1.0 / f[p]
+        g = f * inv
+        g[p] = 1.0 - inv
+        prow = B[p, :].copy()                          # raw pivot row, registers 1..31 are broadcast
+        new = np.empty_like(B)
+        new[:, :31] = B[:, 1:] - np.outer(g, prow[1:])  # results land one register down
+        new[:, 31] = -g
+        new[p, 31] = inv
+        B = new
+    q = my_step[my_step]                               # lane r: i = my_step[r], needed register = my_step[i]
+    diag = np.zeros(32, complex)
+    diag[my_step] = B[np.arange(32), q]
+    return diag[:N]
